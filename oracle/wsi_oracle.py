@@ -1,0 +1,349 @@
+"""CPU ORACLE — test infrastructure only.  NOT a product path, NOT a fallback.
+
+A numpy / torch-fp32 restatement of the reference's sliding-window whole-slide inference path
+(acproject/wsi-segmentation-pipeline).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this module; the
+product package (``wsi_segmentation_pipeline_b200``) never does and fails loudly when its CUDA
+library is missing.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+
+Pinning status
+--------------
+* tile planner, normalisation, ResNet-18 trunk + heads, overlap-add, threshold_probs and the
+  heatmap finalisation are pinned against the *unmodified reference code executed in the build
+  container* (``oracle/ref_harness.py`` -> ``tests/golden/make_golden.py`` ->
+  ``tests/golden/*.npz``; checked by ``tests/test_oracle_golden.py``).
+* the U-Net encoder/decoder arithmetic lives in the third-party package
+  ``segmentation_models_pytorch`` (no version pin in the reference — it ships no requirements
+  file; the call sites ``eval_tumorbed.py:21-28`` use the pre-0.1 API: ``encoder.out_shapes``,
+  callable ``activation``).  That package is absent from /root/reference and from this image,
+  so ``unet_*`` below restates its published architecture (smp 0.0.x ``Unet('resnet18')``:
+  decoder channels (256,128,64,32,16), nearest x2 upsample, concat [x, skip],
+  2x(conv3x3 no-bias + BN + ReLU), final 1x1 conv with bias).  **Parity for the U-Net model is
+  UNPINNED** against smp itself; it is pinned only for the loop around it (the reference's own
+  ``predict_tumorbed`` is run with this restated model to make the goldens).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # myargs.py:127-128
+IMAGENET_STD = (0.229, 0.224, 0.225)    # myargs.py:129-130
+BN_EPS = 1e-5                           # torch.nn.BatchNorm2d default used by resnets_shift.py:37
+
+
+# --------------------------------------------------------------------------------------------
+# A1: tile planner  (utils/dataset.py:143-166, utils/preprocessing.py:60-71)
+# --------------------------------------------------------------------------------------------
+def isforeground(arr: np.ndarray, thresh: float = 0.05) -> bool:
+    """utils/preprocessing.py:60-71 — raises ZeroDivisionError on an empty window, as the
+    reference does (python int / python int)."""
+    return int(np.count_nonzero(arr)) / int(arr.size) >= thresh
+
+
+def plan_tiles(ih, iw, ph, pw, sh, sw, mask=None, m=1.0):
+    """Tile origins (x, y) in scan-level pixels, in the reference's enumeration order:
+    main grid, right column, bottom row, never the corner (utils/dataset.py:147-166).
+    ``mask`` None means all-foreground.  ``m`` = downsample[scan_level]/downsample[2] (:144)."""
+    dx, dy = int(pw * m), int(ph * m)
+
+    def fg(xpos, ypos):
+        if mask is None:
+            return True
+        yp, xp = int(ypos * m), int(xpos * m)
+        return isforeground(mask[yp:yp + dy, xp:xp + dx])
+
+    out = []
+    for ypos in range(1, ih - 1 - ph, sh):
+        for xpos in range(1, iw - 1 - pw, sw):
+            if fg(xpos, ypos):
+                out.append((xpos, ypos))
+    xpos = iw - 1 - pw
+    for ypos in range(1, ih - 1 - ph, sh):
+        if fg(xpos, ypos):
+            out.append((xpos, ypos))
+    ypos = ih - 1 - ph
+    for xpos in range(1, iw - 1 - pw, sw):
+        if fg(xpos, ypos):
+            out.append((xpos, ypos))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# A2/A3: tile gather + normalise  (utils/dataset.py:171-185, utils/preprocessing.py:206-212)
+# --------------------------------------------------------------------------------------------
+def normalise_tile(rgb_u8: np.ndarray) -> torch.Tensor:
+    """ToTensor (u8 HWC -> f32 CHW, /255) then Normalize (sub mean, div std) in fp32, the op
+    order torchvision uses (F.to_tensor: ``.to(float32).div(255)``; F.normalize: ``sub_().div_()``)."""
+    t = torch.from_numpy(np.ascontiguousarray(rgb_u8)).permute(2, 0, 1).contiguous()
+    t = t.to(torch.float32).div(255)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
+    return t.sub_(mean).div_(std)
+
+
+def gather_tiles(raster: np.ndarray, tiles, ph, pw) -> torch.Tensor:
+    """read_region((ds*x, ds*y), level, (pw, ph)) on an in-memory scan-level raster, then the
+    eval augmentor.  Tiles never leave the raster (the planner keeps x+pw <= iw-1)."""
+    return torch.stack([normalise_tile(raster[y:y + ph, x:x + pw]) for (x, y) in tiles])
+
+
+# --------------------------------------------------------------------------------------------
+# A5: ResNet-18 trunk  (resnets_shift.py:30-65 BasicBlock, :111-217 ResNet)
+# --------------------------------------------------------------------------------------------
+def _bn(sd, p, x):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
+                        sd[p + ".weight"], sd[p + ".bias"], False, 0.0, BN_EPS)
+
+
+def _basic_block(sd, p, x, stride):
+    """resnets_shift.py:49-65."""
+    idt = x
+    out = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"], None, stride, 1)))
+    out = _bn(sd, p + ".bn2", F.conv2d(out, sd[p + ".conv2.weight"], None, 1, 1))
+    if (p + ".downsample.0.weight") in sd:
+        idt = _bn(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0))
+    return F.relu(out + idt)
+
+
+def resnet18_stages(sd, x, prefix=""):
+    """Returns [x4(512,/32), x3, x2, x1(64,/4), x0(64,/2)] — the order smp's encoder returns
+    (SURVEY §8a A7); x4 alone is what resnets_shift.ResNet.forward feeds its heads (:196-204)."""
+    p = prefix
+    x0 = F.relu(_bn(sd, p + "bn1", F.conv2d(x, sd[p + "conv1.weight"], None, 2, 3)))
+    x1 = F.max_pool2d(x0, 3, 2, 1)
+    for b in range(2):
+        x1 = _basic_block(sd, f"{p}layer1.{b}", x1, 1)
+    feats = [x1]
+    cur = x1
+    for li in (2, 3, 4):
+        for b in range(2):
+            cur = _basic_block(sd, f"{p}layer{li}.{b}", cur, 2 if b == 0 else 1)
+        feats.append(cur)
+    x1, x2, x3, x4 = feats
+    return [x4, x3, x2, x1, x0]
+
+
+def resnet_multipatch_forward(sd, xs):
+    """resnets_shift.py:189-217: xs [B,P,3,H,W] -> (cat(y_list,0) [P*B,4] patch-major, fc(features) [B,4])."""
+    B, P = xs.shape[:2]
+    xs = xs.transpose(0, 1)
+    x_list, y_list = [], []
+    for ij in range(P):
+        f = resnet18_stages(sd, xs[ij])[0]
+        f = torch.flatten(F.adaptive_avg_pool2d(f, 1), 1)
+        y_list.append(F.linear(f, sd["fc0.weight"], sd["fc0.bias"]))
+        x_list.append(f)
+    feats = torch.cat(x_list, 1).view(B, -1)
+    out = F.linear(F.relu(F.linear(feats, sd["fc.0.weight"], sd["fc.0.bias"])), sd["fc.2.weight"], sd["fc.2.bias"])
+    return torch.cat(y_list, 0), out
+
+
+# --------------------------------------------------------------------------------------------
+# A6: heads  (models/models.py:20-38 Classifier, :41-58 Regressor)
+# --------------------------------------------------------------------------------------------
+def classifier_head(sd, x4, prefix="classifier."):
+    f = torch.flatten(F.adaptive_avg_pool2d(x4, 1), 1)
+    return F.linear(f, sd[prefix + "fc.0.weight"], sd[prefix + "fc.0.bias"])
+
+
+def regressor_head(sd, x4, prefix="regressor."):
+    f = torch.flatten(F.adaptive_avg_pool2d(x4, 1), 1)
+    f = F.relu(F.linear(f, sd[prefix + "fc.0.weight"], sd[prefix + "fc.0.bias"]))
+    return F.linear(f, sd[prefix + "fc.2.weight"], sd[prefix + "fc.2.bias"])
+
+
+def fc0_head(sd, x4):
+    """Per-patch head of resnets_shift.ResNet.forward (:206-209), used by the config-1 adapter."""
+    f = torch.flatten(F.adaptive_avg_pool2d(x4, 1), 1)
+    return F.linear(f, sd["fc0.weight"], sd["fc0.bias"])
+
+
+# --------------------------------------------------------------------------------------------
+# A7: U-Net decoder — RESTATED from the published smp 0.0.x architecture (UNPINNED, see header)
+# --------------------------------------------------------------------------------------------
+def _conv_bn_relu(sd, p, x):
+    return F.relu(_bn(sd, p + ".block.1", F.conv2d(x, sd[p + ".block.0.weight"], None, 1, 1)))
+
+
+def unet_decoder(sd, feats, prefix="decoder."):
+    """feats = [x4, x3, x2, x1, x0]; call site utils/eval.py:200."""
+    x = feats[0]
+    skips = list(feats[1:]) + [None]
+    for i, skip in enumerate(skips, start=1):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if skip is not None:
+            x = torch.cat([x, skip], dim=1)
+        x = _conv_bn_relu(sd, f"{prefix}layer{i}.block.0", x)
+        x = _conv_bn_relu(sd, f"{prefix}layer{i}.block.1", x)
+    return F.conv2d(x, sd[prefix + "final_conv.weight"], sd[prefix + "final_conv.bias"])
+
+
+def model_forward(sd, arch: str, x: torch.Tensor) -> torch.Tensor:
+    """One batch through the model the way predict_tumorbed does (utils/eval.py:196-200).
+    arch: 'resnet18_cls' (config-1 adapter: trunk + fc0), 'unet_cls' (encoder + Classifier),
+    'unet_seg' (encoder + decoder), 'unet_reg' (encoder + Regressor)."""
+    with torch.no_grad():
+        if arch == "resnet18_cls":
+            return fc0_head(sd, resnet18_stages(sd, x)[0])
+        feats = resnet18_stages(sd, x, "encoder.")
+        if arch == "unet_cls":
+            return classifier_head(sd, feats[0])
+        if arch == "unet_reg":
+            return regressor_head(sd, feats[0])
+        if arch == "unet_seg":
+            return unet_decoder(sd, feats)
+    raise ValueError(arch)
+
+
+# --------------------------------------------------------------------------------------------
+# A8/A9: overlap-add  (utils/eval.py:179-215 predict_tumorbed, :42-60 predict_wsis)
+# --------------------------------------------------------------------------------------------
+def stitch(canvas: np.ndarray, tiles, logits: np.ndarray, ph, pw, m=1.0):
+    """canvas [C,H2,W2] f64 += per-tile logits; seg logits [T,C,ph,pw] or cls logits [T,C]
+    broadcast over the tile rectangle.  numpy slicing clips silently at the canvas edge."""
+    dx, dy = int(m * pw), int(m * ph)
+    src = logits
+    while canvas.ndim >= src.ndim:
+        src = np.expand_dims(src, -1)
+    for j, (x, y) in enumerate(tiles):
+        tx, ty = int(m * float(x)), int(m * float(y))
+        canvas[:, ty:ty + dy, tx:tx + dx] += src[j]
+    return canvas
+
+
+def coverage_counts(shape_hw, tiles, ph, pw, m=1.0) -> np.ndarray:
+    """Overlap count map derived from the tile list (the reference holds no count array;
+    SURVEY §0): ``+= 1`` over exactly the rectangles ``stitch`` touches."""
+    cnt = np.zeros(shape_hw, np.int32)
+    dx, dy = int(m * pw), int(m * ph)
+    for (x, y) in tiles:
+        tx, ty = int(m * float(x)), int(m * float(y))
+        cnt[ty:ty + dy, tx:tx + dx] += 1
+    return cnt
+
+
+# --------------------------------------------------------------------------------------------
+# A10/A11: softmax over summed logits, floor, argmax, heatmap  (utils/preprocessing.py:156-172,
+#          utils/eval.py:217-228)
+# --------------------------------------------------------------------------------------------
+def threshold_probs(pred: np.ndarray, class_probs=(0.0, 0.0, 0.0, 0.0)):
+    p = torch.softmax(torch.from_numpy(pred), dim=0)
+    for cj in range(p.shape[0]):
+        p[cj, p[cj, ...] < class_probs[cj]] = 0
+    p = p.numpy()
+    return np.argmax(p, axis=0).astype(np.uint8), p
+
+
+def finalise_heatmap(probs: np.ndarray, mask: np.ndarray, mode: str) -> np.ndarray:
+    h = probs[1] if mode == "cls" else probs[2] + probs[3]
+    return np.uint8(255 * (mask * h))
+
+
+def predict_tumorbed(sd, arch, raster, mask, ph, pw, sh, sw, mode, batch=16, m=1.0, tiles=None,
+                     class_probs=(0.0, 0.0, 0.0, 0.0)):
+    """End-to-end restatement of utils/eval.py:155-229 for one slide whose scan-level raster is
+    ``raster`` u8 [ih,iw,3] and whose level-2 canvas is [int(ih*m), int(iw*m)] (== mask.shape)."""
+    ih, iw = raster.shape[:2]
+    if tiles is None:
+        tiles = plan_tiles(ih, iw, ph, pw, sh, sw, mask, m)
+    C = 4
+    canvas = np.zeros((C,) + tuple(mask.shape), np.float64)
+    all_logits = []
+    for i in range(0, len(tiles), batch):
+        chunk = tiles[i:i + batch]
+        x = gather_tiles(raster, chunk, ph, pw)
+        y = model_forward(sd, arch, x).numpy()
+        all_logits.append(y)
+        stitch(canvas, chunk, y, ph, pw, m)
+    classes, probs = threshold_probs(canvas, class_probs)
+    heat = finalise_heatmap(probs, mask, mode)
+    return {"tiles": tiles, "canvas": canvas, "classes": classes, "probs": probs, "heatmap": heat,
+            "counts": coverage_counts(mask.shape, tiles, ph, pw, m),
+            "logits": np.concatenate(all_logits) if all_logits else np.zeros((0, C), np.float32)}
+
+
+# --------------------------------------------------------------------------------------------
+# random-init weights with the reference's state_dict keys (randomised BN stats)
+# --------------------------------------------------------------------------------------------
+def _randomise_bn(sd, g):
+    for k in list(sd):
+        if k.endswith("running_mean"):
+            b = k[: -len("running_mean")]
+            n = sd[k].numel()
+            sd[b + "running_mean"] = torch.randn(n, generator=g) * 0.1
+            sd[b + "running_var"] = torch.rand(n, generator=g) + 0.5
+            sd[b + "weight"] = torch.rand(n, generator=g) + 0.5
+            sd[b + "bias"] = torch.randn(n, generator=g) * 0.1
+    return sd
+
+
+def _kaiming(shape, g):
+    fan_out = shape[0] * shape[2] * shape[3]
+    return torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
+
+
+def _linear(out_f, in_f, g):
+    bound = 1.0 / in_f ** 0.5
+    return ((torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound,
+            (torch.rand(out_f, generator=g) * 2 - 1) * bound)
+
+
+def _bn_keys(sd, p, n):
+    sd[p + ".weight"] = torch.ones(n)
+    sd[p + ".bias"] = torch.zeros(n)
+    sd[p + ".running_mean"] = torch.zeros(n)
+    sd[p + ".running_var"] = torch.ones(n)
+    sd[p + ".num_batches_tracked"] = torch.tensor(0)
+
+
+def random_resnet18_trunk(g, prefix=""):
+    sd = {}
+    p = prefix
+    sd[p + "conv1.weight"] = _kaiming((64, 3, 7, 7), g)
+    _bn_keys(sd, p + "bn1", 64)
+    cin = 64
+    for li, cout in zip((1, 2, 3, 4), (64, 128, 256, 512)):
+        for b in range(2):
+            q = f"{p}layer{li}.{b}"
+            sd[q + ".conv1.weight"] = _kaiming((cout, cin if b == 0 else cout, 3, 3), g)
+            _bn_keys(sd, q + ".bn1", cout)
+            sd[q + ".conv2.weight"] = _kaiming((cout, cout, 3, 3), g)
+            _bn_keys(sd, q + ".bn2", cout)
+            if b == 0 and li > 1:
+                sd[q + ".downsample.0.weight"] = _kaiming((cout, cin, 1, 1), g)
+                _bn_keys(sd, q + ".downsample.1", cout)
+        cin = cout
+    return sd
+
+
+def random_state_dict(arch: str, seed: int = 0, num_classes: int = 4, with_fc: bool = False):
+    """arch 'resnet18' -> resnets_shift.ResNet keys (fc.* only when with_fc: 33.6 M params);
+    arch 'unet' -> smp.Unet('resnet18') keys + classifier/regressor heads (eval_tumorbed.py:21-28)."""
+    g = torch.Generator().manual_seed(seed)
+    if arch == "resnet18":
+        sd = random_resnet18_trunk(g)
+        sd["fc0.weight"], sd["fc0.bias"] = _linear(4, 512, g)
+        if with_fc:
+            sd["fc.0.weight"], sd["fc.0.bias"] = _linear(4096, 8192, g)
+            sd["fc.2.weight"], sd["fc.2.bias"] = _linear(4, 4096, g)
+        return _randomise_bn(sd, g)
+    if arch == "unet":
+        sd = random_resnet18_trunk(g, "encoder.")
+        ins = (768, 384, 192, 128, 32)
+        outs = (256, 128, 64, 32, 16)
+        for i, (ci, co) in enumerate(zip(ins, outs), start=1):
+            for j, c_in in enumerate((ci, co)):
+                q = f"decoder.layer{i}.block.{j}.block"
+                sd[q + ".0.weight"] = _kaiming((co, c_in, 3, 3), g)
+                _bn_keys(sd, q + ".1", co)
+        sd["decoder.final_conv.weight"] = _kaiming((num_classes, 16, 1, 1), g)
+        sd["decoder.final_conv.bias"] = torch.randn(num_classes, generator=g) * 0.1
+        sd["classifier.fc.0.weight"], sd["classifier.fc.0.bias"] = _linear(num_classes, 512, g)
+        sd["regressor.fc.0.weight"], sd["regressor.fc.0.bias"] = _linear(128, 512, g)
+        sd["regressor.fc.2.weight"], sd["regressor.fc.2.bias"] = _linear(1, 128, g)
+        return _randomise_bn(sd, g)
+    raise ValueError(arch)

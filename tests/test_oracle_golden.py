@@ -1,0 +1,78 @@
+"""Pins the CPU oracle (oracle/wsi_oracle.py) against fixtures produced by executing the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wsi_oracle as O
+from wsi_segmentation_pipeline_b200 import synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def test_plan_matches_reference_enumeration(golden_dir):
+    g = _load(golden_dir, "plan")
+    for ci in range(int(g["n_cases"])):
+        ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g[f"case{ci}_geom"])
+        m = 1.0 if lvl == 2 else 4.0 / 16.0
+        tiles = O.plan_tiles(ih, iw, ph, pw, sh, sw, g[f"case{ci}_mask"], m)
+        np.testing.assert_array_equal(np.array(tiles, np.int32).reshape(-1, 2), g[f"case{ci}_tiles"])
+
+
+def test_config1_tile_count():
+    assert len(O.plan_tiles(2048, 2048, 256, 256, 128, 128)) == 224
+    assert len(O.plan_tiles(20000, 20000, 512, 512, 128, 128)) == 23715
+
+
+def test_normalise_bit_exact(golden_dir):
+    g = _load(golden_dir, "normalise")
+    out = O.normalise_tile(g["tile"]).numpy()
+    np.testing.assert_array_equal(out, g["out"])
+
+
+def test_resnet_multipatch_forward(golden_dir):
+    g = _load(golden_dir, "resnet_fwd")
+    sd = O.random_state_dict("resnet18", 3, with_fc=True)
+    xs = torch.randn(2, 16, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        y, out = O.resnet_multipatch_forward(sd, xs)
+        x4 = O.resnet18_stages(sd, xs[:, 0])[0]
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(x4.numpy(), g["x4"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,arch,mode", [("cls_small", "resnet18_cls", "cls"),
+                                            ("cls_m4", "resnet18_cls", "cls"),
+                                            ("seg_small", "unet_seg", "seg")])
+def test_predict_tumorbed_matches_reference(golden_dir, name, arch, mode):
+    g = _load(golden_dir, name)
+    ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g["geom"])
+    m = 1.0 if lvl == 2 else 0.25
+    sd = O.random_state_dict("resnet18" if arch == "resnet18_cls" else "unet", int(g["seed"]))
+    raster = synth.synth_slide(ih, iw, 1234)
+    r = O.predict_tumorbed(sd, arch, raster, g["mask"], ph, pw, sh, sw, mode, batch=16, m=m)
+    np.testing.assert_array_equal(np.array(r["tiles"], np.int32).reshape(-1, 2), g["tiles"])
+    np.testing.assert_allclose(r["canvas"], g["canvas"], rtol=1e-4, atol=2e-4)
+    # probabilities within the north-star fp32 tolerance, layout identical
+    np.testing.assert_allclose(r["probs"], g["probs"], atol=1e-4)
+    assert r["classes"].shape == g["classes"].shape and r["classes"].dtype == np.uint8
+    assert (r["classes"] == g["classes"]).mean() >= 0.999
+    assert np.abs(r["heatmap"].astype(int) - g["heatmap"].astype(int)).max() <= 1
+    # uncovered pixels: summed logits 0 -> argmax 0, seg heatmap uint8(255*0.5)*mask
+    unc = r["counts"] == 0
+    assert (r["classes"][unc] == 0).all()
+    if mode == "seg":
+        assert (r["heatmap"][unc] == 127 * g["mask"][unc]).all()
+
+
+def test_synth_checksum_is_stable():
+    s = synth.synth_slide(2048, 2048, 1234, y0=100, y1=164)
+    assert s.shape == (64, 2048, 3)
+    full = synth.synth_slide(256, 2048, 1234)
+    np.testing.assert_array_equal(full[100:164], s)
+    assert synth.checksum(synth.synth_slide(128, 160, 7)) == synth.checksum(synth.synth_slide(128, 160, 7))
