@@ -1,0 +1,173 @@
+/* wsi_b200.h — C-ABI of libwsi_b200.so: the B200-native sliding-window whole-slide inference path.
+ *
+ * The reference (acproject/wsi-segmentation-pipeline) is pure Python and has no FFI layer; its
+ * hot path is the duck-typed Python surface described in SURVEY.md §8(b).  This header is the
+ * boundary a maintainer would bind with ctypes/cffi; each entry point cites
+ * the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions: every function returns 0 (WSI_OK) or a negative wsi_status; no exceptions cross
+ * the ABI; the caller owns every buffer it passes in; the library owns wsi_ctx and anything it
+ * returns through an out-pointer (release with wsi_free).  A wsi_ctx is bound to one CUDA device
+ * and is not thread-safe (one per GPU / process).  All device work is ordered on the `stream`
+ * argument (a cudaStream_t passed as void*, NULL = the legacy default stream).  There is no CPU
+ * fallback: without a CUDA device wsi_ctx_create fails with WSI_ERR_CUDA.
+ */
+#ifndef WSI_B200_H
+#define WSI_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define WSI_API __attribute__((visibility("default")))
+#else
+#define WSI_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wsi_ctx wsi_ctx;
+
+typedef enum {
+  WSI_OK = 0,
+  WSI_ERR_INVALID = -1,      /* bad argument */
+  WSI_ERR_CUDA = -2,         /* CUDA runtime / driver error (see wsi_last_error) */
+  WSI_ERR_NOMODEL = -3,      /* wsi_model_load has not been called / tensor missing */
+  WSI_ERR_DEGENERATE = -4,   /* geometry on which the reference itself raises (empty mask window) */
+  WSI_ERR_UNSUPPORTED = -5,  /* e.g. num_classes != 4, seg mode with m != 1 */
+  WSI_ERR_NOMEM = -6
+} wsi_status;
+
+/* Model families on the path.  RESNET18: resnets_shift.py:111-217 (trunk + fc0 [+ fc]).
+ * UNET_R18: smp.Unet('resnet18') + Classifier/Regressor heads, eval_tumorbed.py:21-28. */
+typedef enum { WSI_ARCH_RESNET18 = 0, WSI_ARCH_UNET_R18 = 1 } wsi_arch;
+
+/* What is computed per tile (utils/eval.py:196-200):
+ *   SEG        model.decoder(model.encoder(x))            -> [C, ph, pw] logits, stitched per pixel
+ *   CLS        model.classifier(model.encoder(x)[0])      -> [C] logits broadcast over the tile
+ *              (for WSI_ARCH_RESNET18: fc0(flatten(avgpool(trunk(x)))), resnets_shift.py:206-208)
+ *   REG        model.regressor(model.encoder(x)[0])       -> [1]   (utils/eval.py:315-317,399-400)
+ *   FEATURES   flatten(avgpool(trunk(x)))                 -> [512] (resnets_shift.py:211-212)    */
+typedef enum { WSI_HEAD_SEG = 0, WSI_HEAD_CLS = 1, WSI_HEAD_REG = 2, WSI_HEAD_FEATURES = 3 } wsi_head;
+
+typedef enum { WSI_MEM_HOST = 0, WSI_MEM_DEVICE = 1 } wsi_mem_kind;
+
+/* One fp32 state_dict entry (host memory), named exactly as in the reference's checkpoints
+ * (utils/networks.py:6-10 -> model.load_state_dict(state['state_dict'])). */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} wsi_tensor_desc;
+
+/* A slide (or one row band of it) at scan level.  Replaces the OpenSlide handle + DataLoader
+ * of utils/dataset.py:110-201 for rasters that are already decoded. */
+typedef struct {
+  const uint8_t* rgb;      /* u8 [rows, iw, 3], row `row0` of the scan-level raster first      */
+  int64_t row_stride;      /* bytes between raster rows (>= 3*iw)                               */
+  int32_t rgb_mem;         /* wsi_mem_kind                                                      */
+  int64_t ih, iw;          /* full scan-level dimensions (level_dimensions[scan_level])         */
+  int64_t row0, rows;      /* raster rows present: [row0, row0+rows) (band + halo); 0, ih = all */
+  int32_t ph, pw;          /* tile size (utils/dataset.py params.ph/pw)                         */
+  double m;                /* level_downsamples[scan_level] / level_downsamples[2]              */
+  int64_t H2, W2;          /* level-2 canvas dimensions (utils/eval.py:182)                     */
+  int64_t own0, own1;      /* canvas rows this call owns and writes: [own0, own1); 0, H2 = all  */
+  const uint8_t* mask;     /* level-2 foreground mask rows [own0, own1), u8 {0,1} [own1-own0,W2];
+                              NULL = all ones (utils/eval.py:219,225)                           */
+  int32_t mask_mem;        /* wsi_mem_kind                                                      */
+} wsi_slide_desc;
+
+/* Outputs of one slide/band, all optional except classes+heatmap; rows [own0, own1) only. */
+typedef struct {
+  int32_t mem;             /* wsi_mem_kind of every non-NULL pointer below                      */
+  uint8_t* classes;        /* u8 [rows, W2]   argmax of threshold_probs (preprocessing.py:172)  */
+  uint8_t* heatmap;        /* u8 [rows, W2]   uint8(255*mask*h) (utils/eval.py:220-228)         */
+  float* canvas;           /* f32 [C, rows, W2] summed logits (utils/eval.py:213-215), or NULL  */
+  float* probs;            /* f32 [C, rows, W2] softmax after class_probs floor, or NULL        */
+  int32_t* counts;         /* i32 [rows, W2]  number of tiles covering each pixel, or NULL      */
+  float* tile_logits;      /* f32 [T, C] (CLS) per-tile logits in the order of tiles_xy, or NULL */
+} wsi_out_desc;
+
+/* ---- context ------------------------------------------------------------------------------ */
+WSI_API int wsi_ctx_create(int device, wsi_ctx** out);
+WSI_API int wsi_ctx_destroy(wsi_ctx* ctx);
+WSI_API const char* wsi_last_error(wsi_ctx* ctx);           /* ctx may be NULL: last global error       */
+WSI_API const char* wsi_version(void);
+/* knobs: "batch_tiles" (tiles per forward batch, 0 = auto), "stage_timing" (0/1)               */
+WSI_API int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value);
+WSI_API int wsi_set_class_probs(wsi_ctx* ctx, const float* p, int n);   /* myargs.py:15 class_probs     */
+WSI_API int64_t wsi_kernel_launches(wsi_ctx* ctx);          /* kernels launched by this ctx so far      */
+
+/* ---- model (replaces model.load_state_dict + .cuda(), eval_tumorbed.py:30-46) ---------------- */
+WSI_API int wsi_model_load(wsi_ctx* ctx, int arch, const wsi_tensor_desc* tensors, int n, int num_classes);
+
+/* ---- tile planner (replaces Dataset_wsi.__init__, utils/dataset.py:143-166) ------------------ */
+/* xy_out: malloc'd int32 [T,2] (x,y) in the reference's enumeration order; free with wsi_free.
+ * mask NULL = all foreground.  Host-only: needs no ctx and no GPU.                              */
+WSI_API int wsi_plan_tiles(int64_t ih, int64_t iw, int32_t ph, int32_t pw, int32_t sh, int32_t sw,
+                   const uint8_t* mask, int64_t mh, int64_t mw, double m,
+                   int32_t** xy_out, int64_t* n_out);
+WSI_API void wsi_free(void* p);
+
+/* ---- row-band partition for multi-GPU (no reference counterpart) ----------------- */
+/* bands[k] = {own0, own1, row0, row1}: canvas rows owned, and scan-level raster rows needed
+ * (own rows + halo so that every tile intersecting the band is complete).  seg/m==1 geometry.  */
+WSI_API int wsi_band_partition(int64_t ih, int32_t ph, int32_t sh, int32_t nranks, int64_t* bands /*[nranks*4]*/);
+/* keep the tiles that intersect canvas rows [own0, own1); idx_out malloc'd int64 indices        */
+WSI_API int wsi_band_tiles(const int32_t* xy, int64_t n, int32_t ph, double m, int64_t own0, int64_t own1,
+                   int64_t** idx_out, int64_t* n_out);
+
+/* ---- the hot path (replaces the loop of predict_tumorbed, utils/eval.py:190-228) ------------- */
+WSI_API int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,
+                  int head, const wsi_out_desc* out, void* stream);
+
+/* ---- one batch through the network (nn.Module shim forward; utils/eval.py:196-200) ----------- */
+/* x: f32 [n, 3, h, w] already normalised (standard_augmentor output); out: SEG f32 [n,C,h,w],
+ * CLS [n,C], REG [n,1], FEATURES [n,512].  Both in `mem` memory.                                 */
+WSI_API int wsi_forward_batch(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_t w, int head,
+                      float* out, int mem, void* stream);
+/* same, but tiles are cut from a u8 raster with the fused gather+normalise kernel               */
+WSI_API int wsi_forward_tiles(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,
+                      int head, float* out, int mem, void* stream);
+
+/* ---- synthetic slide on device (twin of synth.py) -------------------------------- */
+WSI_API int wsi_synth_slide(wsi_ctx* ctx, int64_t ih, int64_t iw, uint32_t seed, int64_t y0, int64_t y1,
+                    const uint8_t* lut /*host u8[16*8*3]*/, uint8_t* rgb_dev, int64_t row_stride,
+                    uint8_t* mask_dev_or_null, void* stream);
+
+/* ---- per-kernel debug/bench entry points (tests/, bench.py roofline legs) -------------------- */
+/* generic conv through the tcgen05 implicit-GEMM kernel: x bf16 NHWC [n,h,w,cin] (device),
+ * w f32 OIHW (host), scale/bias f32 [cout] (host, may be NULL = 1/0), res bf16 NHWC or NULL,
+ * y bf16 NHWC [n,oh,ow,cout] (device).  up2: x is nearest-upsampled x2 and concatenated with
+ * `skip` (bf16 NHWC [n,2h,2w,cskip] or NULL) before a 3x3/s1 conv (smp DecoderBlock).           */
+WSI_API int wsi_debug_conv(wsi_ctx* ctx, const void* x, int n, int h, int w, int cin,
+                   const float* wt, int cout, int ksize, int stride, int pad,
+                   const float* scale, const float* bias, const void* res, int relu,
+                   int up2, const void* skip, int cskip, void* y, void* stream);
+/* K0 alone: tiles cut from the raster by the fused gather + normalise kernel.
+ * norm_out: f32 [n,3,ph,pw] (device) = standard_augmentor(True) output, bit-exact
+ * (utils/preprocessing.py:209-212); padded_out: bf16 [n,ph+6,pw+8,4] (device) = the stem operand
+ * (RN-to-bf16 of the same values, zero border, 4th channel 0).  Either may be NULL.            */
+WSI_API int wsi_debug_gather(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int n,
+                     float* norm_out, void* padded_out, void* stream);
+/* stem: tiles u8 raster -> gather/normalise -> 7x7/s2 conv + BN + ReLU; y bf16 NHWC [n,ph/2,pw/2,64] */
+WSI_API int wsi_debug_stem(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int n,
+                   const float* wt /*[64,3,7,7]*/, const float* scale, const float* bias, void* y,
+                   void* stream);
+/* max pool 3x3/s2/p1 on bf16 NHWC (resnets_shift.py:126) */
+WSI_API int wsi_debug_maxpool(wsi_ctx* ctx, const void* x, int n, int h, int w, int c, void* y, void* stream);
+
+/* ---- stage statistics (bench.py roofline legs) ------------------------------------------------ */
+/* With option "stage_timing" = 1, wsi_run_slide brackets every stage with CUDA events on the
+ * launching stream and accumulates, per stage name ("gather", "stem", "maxpool", "conv", "head",
+ * "stitch", "finalise", "h2d", "d2h"): device milliseconds, kernel launches and algorithmic work
+ * (FLOPs for stem/conv, bytes otherwise).  Reset with wsi_stage_reset.            */
+WSI_API int wsi_stage_stats(wsi_ctx* ctx, const char* stage, double* ms_out, int64_t* launches_out, double* work_out);
+WSI_API int wsi_stage_reset(wsi_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSI_B200_H */

@@ -1,0 +1,165 @@
+"""GPU parity tests of the whole path through the C-ABI: network forward vs the oracle's fp32
+restatement, and wsi_run_slide vs (a) the oracle on the same seeded inputs and (b) the golden
+fixtures produced by the unmodified reference (tests/golden/make_golden.py).
+
+Tolerances (BASELINE.json north_star, bf16 build): tile coordinates, overlap counts and the
+argmax mask LAYOUT bit-exact; probabilities within 1e-2 max-abs and >= 99.9 % argmax-pixel
+agreement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wsi_oracle as O
+from wsi_segmentation_pipeline_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-2        # north_star: bf16 probabilities within 1e-2 max-abs
+ARGMAX_AGREE = 0.999   # north_star: >= 99.9 % argmax-pixel agreement
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _load_model(ctx, arch, seed):
+    sd = O.random_state_dict("resnet18" if arch == "resnet18_cls" else "unet", seed)
+    ctx.load_state_dict(capi.ARCH_RESNET18 if arch == "resnet18_cls" else capi.ARCH_UNET_R18, sd)
+    return sd
+
+
+def _rel_err(got, ref):
+    return (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+
+
+@pytest.mark.parametrize("arch,head,hw,n", [
+    ("resnet18_cls", capi.HEAD_CLS, 64, 7),
+    ("resnet18_cls", capi.HEAD_FEATURES, 64, 3),
+    ("resnet18_cls", capi.HEAD_CLS, 256, 4),
+    ("unet_cls", capi.HEAD_CLS, 128, 3),
+    ("unet_reg", capi.HEAD_REG, 128, 3),
+    ("unet_seg", capi.HEAD_SEG, 64, 5),
+    ("unet_seg", capi.HEAD_SEG, 256, 2),
+])
+def test_forward_batch_matches_oracle(ctx, arch, head, hw, n):
+    sd = _load_model(ctx, arch, 2)
+    x = torch.randn(n, 3, hw, hw, generator=torch.Generator().manual_seed(7))
+    y = ctx.forward_batch(x.cuda(), head).cpu()
+    if head == capi.HEAD_FEATURES:
+        with torch.no_grad():
+            ref = torch.flatten(torch.nn.functional.adaptive_avg_pool2d(O.resnet18_stages(sd, x)[0], 1), 1)
+    else:
+        ref = O.model_forward(sd, arch, x)
+    assert y.shape == ref.shape
+    assert _rel_err(y, ref) < 0.03, f"{arch}/{head}: rel err {_rel_err(y, ref):.4f}"
+
+
+def test_forward_batch_host_memory_and_tiles_agree(ctx):
+    sd = _load_model(ctx, "unet_seg", 2)
+    ih, iw, p = 200, 260, 64
+    raster = synth.synth_slide(ih, iw, 3)
+    tiles = np.array([[1, 1], [100, 50], [iw - 1 - p, ih - 1 - p]], np.int32)
+    sl = ctx.slide_desc(raster, ih, iw, p, p)
+    a = ctx.forward_tiles(sl, tiles, capi.HEAD_SEG)
+    x = O.gather_tiles(raster, [tuple(t) for t in tiles], p, p)
+    b = ctx.forward_batch(x, capi.HEAD_SEG)          # host tensors in, host tensor out
+    assert torch.equal(a, b), "gather path and NCHW path must feed identical bf16 operands"
+
+
+def _run(ctx, raster, mask, tiles, ph, pw, m, head, **kw):
+    ih, iw = raster.shape[:2]
+    sl = ctx.slide_desc(raster, ih, iw, ph, pw, m=m, H2=mask.shape[0], W2=mask.shape[1], mask=mask)
+    return ctx.run_slide(sl, tiles, head, want_canvas=True, want_probs=True, want_counts=True, **kw)
+
+
+@pytest.mark.parametrize("name,arch,mode", [("cls_small", "resnet18_cls", "cls"), ("cls_m4", "resnet18_cls", "cls"),
+                                            ("seg_small", "unet_seg", "seg")])
+def test_run_slide_matches_reference_golden(ctx, golden_dir, name, arch, mode):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g["geom"])
+    m = 1.0 if lvl == 2 else 0.25
+    _load_model(ctx, arch, int(g["seed"]))
+    raster = synth.synth_slide(ih, iw, 1234)
+    mask = np.ascontiguousarray(g["mask"])
+    tiles = capi.plan_tiles(ih, iw, ph, pw, sh, sw, mask, m)
+    np.testing.assert_array_equal(tiles, g["tiles"])                       # coordinates bit-exact
+    head = capi.HEAD_CLS if mode == "cls" else capi.HEAD_SEG
+    r = _run(ctx, raster, mask, tiles, ph, pw, m, head, want_tile_logits=(mode == "cls"))
+    counts = O.coverage_counts(mask.shape, [tuple(t) for t in tiles], ph, pw, m)
+    np.testing.assert_array_equal(r["counts"].numpy(), counts)             # overlap counts bit-exact
+    classes, probs, heat = r["classes"].numpy(), r["probs"].numpy(), r["heatmap"].numpy()
+    assert classes.shape == g["classes"].shape and classes.dtype == np.uint8
+    assert np.abs(probs - g["probs"]).max() <= PROB_TOL
+    assert (classes == g["classes"]).mean() >= ARGMAX_AGREE
+    unc = counts == 0
+    assert (classes[unc] == 0).all()                                       # uncovered: first-max tie-break
+    exp_unc = (63 if mode == "cls" else 127) * mask[unc]                   # uint8(255*0.25) / uint8(255*0.5)
+    np.testing.assert_array_equal(heat[unc], exp_unc)
+    assert np.abs(heat.astype(int) - g["heatmap"].astype(int)).max() <= 3  # 255 * PROB_TOL, truncation
+    # the classes/heatmap are a pure function of the canvas (same finalise arithmetic as the oracle)
+    cls2, p2 = O.threshold_probs(r["canvas"].numpy().astype(np.float64))
+    assert (cls2 == classes).mean() >= 0.9999
+    assert np.abs(p2 - probs).max() < 1e-5
+
+
+def test_run_slide_order_and_band_invariance(ctx):
+    """the reference shuffles tiles (utils/dataset.py:192); results must not depend
+    on tile order, and 1/2/3 row bands must give byte-identical masks and heatmaps."""
+    ih, iw, p, s = 352, 416, 64, 32
+    _load_model(ctx, "unet_seg", 4)
+    raster = synth.synth_slide(ih, iw, 1234)
+    mask = np.ascontiguousarray(synth.synth_mask(ih * 8, iw * 8, 77)[::8, ::8])
+    tiles = capi.plan_tiles(ih, iw, p, p, s, s, mask, 1.0)
+    base = _run(ctx, raster, mask, tiles, p, p, 1.0, capi.HEAD_SEG)
+    perm = np.random.default_rng(0).permutation(len(tiles))
+    shuf = _run(ctx, raster, mask, tiles[perm], p, p, 1.0, capi.HEAD_SEG)
+    for k in ("classes", "heatmap", "canvas", "counts"):
+        assert torch.equal(base[k], shuf[k]), k
+    for nb in (2, 3):
+        bands = capi.band_partition(ih, p, s, nb)
+        cls_parts, heat_parts = [], []
+        for own0, own1, row0, row1 in bands:
+            idx = capi.band_tiles(tiles, p, 1.0, own0, own1)
+            sl = ctx.slide_desc(np.ascontiguousarray(raster[row0:row1]), ih, iw, p, p, mask=np.ascontiguousarray(mask[own0:own1]),
+                                row0=row0, rows=row1 - row0, own0=own0, own1=own1)
+            r = ctx.run_slide(sl, tiles[idx], capi.HEAD_SEG)
+            cls_parts.append(r["classes"])
+            heat_parts.append(r["heatmap"])
+        assert bands[0, 0] == 0 and bands[-1, 1] == ih
+        assert torch.equal(torch.cat(cls_parts), base["classes"]), f"{nb} bands: classes differ"
+        assert torch.equal(torch.cat(heat_parts), base["heatmap"]), f"{nb} bands: heatmap differs"
+
+
+def test_run_slide_device_resident_io(ctx):
+    ih, iw, p, s = 200, 300, 64, 32
+    _load_model(ctx, "resnet18_cls", 1)
+    raster = synth.synth_slide(ih, iw, 1)
+    tiles = capi.plan_tiles(ih, iw, p, p, s, s)
+    host = ctx.run_slide(ctx.slide_desc(raster, ih, iw, p, p), tiles, capi.HEAD_CLS)
+    dev = ctx.run_slide(ctx.slide_desc(torch.from_numpy(raster).cuda(), ih, iw, p, p), tiles, capi.HEAD_CLS, device_out=True)
+    torch.cuda.synchronize()
+    assert dev["classes"].is_cuda and torch.equal(dev["classes"].cpu(), host["classes"])
+    assert torch.equal(dev["heatmap"].cpu(), host["heatmap"])
+    assert ctx.kernel_launches > 0
+
+
+def test_empty_tile_list_and_errors(ctx):
+    _load_model(ctx, "unet_seg", 0)
+    raster = synth.synth_slide(128, 128, 1)
+    mask = np.ones((128, 128), np.uint8)
+    r = _run(ctx, raster, mask, np.zeros((0, 2), np.int32), 64, 64, 1.0, capi.HEAD_SEG)
+    assert (r["classes"].numpy() == 0).all() and (r["heatmap"].numpy() == 127).all() and (r["counts"].numpy() == 0).all()
+    with pytest.raises(capi.WsiError):      # tile leaves the raster
+        _run(ctx, raster, mask, np.array([[100, 100]], np.int32), 64, 64, 1.0, capi.HEAD_SEG)
+    with pytest.raises(capi.WsiError):      # seg needs m == 1
+        sl = ctx.slide_desc(raster, 128, 128, 64, 64, m=0.25, H2=32, W2=32)
+        ctx.run_slide(sl, np.array([[1, 1]], np.int32), capi.HEAD_SEG)
+    c2 = capi.Context(0)
+    with pytest.raises(capi.WsiError):      # no model loaded
+        c2.run_slide(c2.slide_desc(raster, 128, 128, 64, 64), np.array([[1, 1]], np.int32), capi.HEAD_SEG)
+    c2.close()

@@ -1,0 +1,181 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (libwsi_b200.so).
+
+Integer/byte work is compared bit-exactly with the oracle; the bf16 tensor-core convolutions are
+compared with a plain PyTorch fp32 reference of the same op evaluated on the same bf16-rounded
+operands (so the only differences are fp32 accumulation order and the final bf16 rounding)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import wsi_oracle as O
+from wsi_segmentation_pipeline_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _nhwc_bf16(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _nchw_f32(y_nhwc):
+    return y_nhwc.to(torch.float32).permute(0, 3, 1, 2).contiguous()
+
+
+def _assert_close_bf16(got, ref, what):
+    """got: bf16-rounded kernel output; ref: fp32 reference.  One bf16 ulp (2^-8 relative) plus
+    fp32 accumulation noise."""
+    err = (got - ref).abs()
+    tol = ref.abs() * (2.0 ** -7) + 1e-2
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} mismatches, max err {err.max().item():.4g} (ref max {ref.abs().max().item():.4g})"
+
+
+# ------------------------------------------------------------------------------------------
+# K0 gather + normalise
+# ------------------------------------------------------------------------------------------
+def test_gather_normalise_bit_exact(ctx):
+    ih, iw, ph, pw = 300, 421, 64, 48
+    raster = synth.synth_slide(ih, iw, 99)
+    tiles = np.array([[1, 1], [41, 33], [iw - 1 - pw, 97], [17, ih - 1 - ph], [372, 235]], np.int32)
+    sl = ctx.slide_desc(raster, ih, iw, ph, pw)
+    norm, padded = ctx.debug_gather(sl, tiles, want_padded=True)
+    ref = O.gather_tiles(raster, [tuple(t) for t in tiles], ph, pw)
+    assert torch.equal(norm.cpu(), ref), "fp32 normalise must be bit-exact with ToTensor+Normalize"
+    pad = padded.cpu().to(torch.float32)
+    inner = pad[:, 3:3 + ph, 3:3 + pw, :3].permute(0, 3, 1, 2)
+    assert torch.equal(inner, _bf16_round(ref)), "bf16 operand must be RN(fp32 normalise)"
+    border = pad.clone()
+    border[:, 3:3 + ph, 3:3 + pw, :3] = 0
+    assert border.abs().max().item() == 0.0, "padding / 4th channel must be zero"
+
+
+def test_gather_from_device_raster_and_band(ctx):
+    ih, iw, ph, pw = 256, 320, 64, 64
+    raster = synth.synth_slide(ih, iw, 5)
+    band = torch.from_numpy(raster[64:224]).cuda()
+    tiles = np.array([[3, 64], [100, 100], [iw - 1 - pw, 224 - ph]], np.int32)
+    sl = ctx.slide_desc(band, ih, iw, ph, pw, row0=64, rows=160)
+    norm = ctx.debug_gather(sl, tiles)
+    ref = O.gather_tiles(raster, [tuple(t) for t in tiles], ph, pw)
+    assert torch.equal(norm.cpu(), ref)
+    with pytest.raises(capi.WsiError):
+        ctx.debug_gather(sl, np.array([[0, 10]], np.int32))       # rows not present in the band
+
+
+def test_synth_device_matches_host(ctx):
+    ih, iw = 700, 531
+    rgb, mask = ctx.synth_slide(ih, iw, 1234, y0=100, y1=420, with_mask=True)
+    assert np.array_equal(rgb.cpu().numpy(), synth.synth_slide(ih, iw, 1234, 100, 420))
+    assert np.array_equal(mask.cpu().numpy(), synth.synth_mask(ih, iw, 1234, 100, 420))
+
+
+# ------------------------------------------------------------------------------------------
+# max pool
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,h,w,c", [(3, 32, 32, 64), (2, 17, 23, 64), (1, 128, 128, 64)])
+def test_maxpool(ctx, n, h, w, c):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, c, h, w, generator=g).cuda()
+    y = ctx.debug_maxpool(_nhwc_bf16(x))
+    ref = F.max_pool2d(_bf16_round(x), 3, 2, 1)
+    assert torch.equal(_nchw_f32(y), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 implicit-GEMM convolutions
+# ------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, res, relu
+    (2, 16, 16, 64, 64, 3, 1, 1, False, False),      # BLOCK_K 64, BLOCK_N 64, exactly 4 M tiles
+    (3, 16, 16, 64, 64, 3, 1, 1, True, True),        # residual + relu epilogue
+    (2, 16, 16, 128, 128, 3, 1, 1, True, True),      # BLOCK_N 128, 2 channel chunks per tap
+    (5, 8, 8, 256, 256, 3, 1, 1, False, True),       # N tiles x 2, batch packs 2 images per M tile
+    (3, 4, 4, 512, 512, 3, 1, 1, True, True),        # deep layer: bn = 8 images per M tile (ragged)
+    (2, 16, 16, 64, 128, 3, 2, 1, False, True),      # stride 2 through parity views
+    (2, 16, 16, 64, 128, 1, 2, 0, False, False),     # 1x1/s2 projection
+    (1, 32, 32, 32, 16, 3, 1, 1, False, True),       # BLOCK_K 32, BLOCK_N 16
+    (1, 32, 32, 16, 16, 3, 1, 1, False, True),       # BLOCK_K 16
+    (2, 20, 28, 64, 64, 3, 1, 1, False, False),      # extents that are not powers of two
+    (1, 64, 64, 64, 64, 3, 1, 1, True, True),        # many M tiles per CTA (persistent loop, 2 TMEM buffers)
+    (2, 2, 2, 512, 512, 3, 1, 1, False, True),       # 2x2 feature map (64 px tiles at /32)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "n{}_{}x{}_c{}to{}_k{}s{}".format(*c[:7]))
+def test_conv_igemm(ctx, case):
+    n, h, w, cin, cout, k, stride, pad, use_res, relu = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(n, cin, h, w, generator=g).cuda()
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = torch.randn(n, cout, oh, ow, generator=g).cuda() if use_res else None
+    y = ctx.debug_conv(_nhwc_bf16(x), wt, stride=stride, pad=pad, scale=scale, bias=bias,
+                       res=_nhwc_bf16(res) if use_res else None, relu=relu)
+    ref = F.conv2d(_bf16_round(x), _bf16_round(wt).cuda(), None, stride, pad)
+    ref = ref * scale.cuda().view(1, -1, 1, 1) + bias.cuda().view(1, -1, 1, 1)
+    if use_res:
+        ref = ref + _bf16_round(res)
+    if relu:
+        ref = F.relu(ref)
+    _assert_close_bf16(_nchw_f32(y), ref, f"conv {case}")
+
+
+UP_CASES = [
+    # n, h, w (low-res), cx, cskip, cout
+    (2, 8, 8, 64, 64, 64),        # x2 upsample + concat skip, BLOCK_K 64
+    (1, 4, 4, 512, 256, 256),     # decoder level 1 shape (768 -> 256)
+    (2, 16, 16, 64, 64, 32),      # decoder level 4 shape (128 -> 32)
+    (1, 16, 16, 32, 0, 16),       # decoder level 5: no skip, BLOCK_K 32
+    (3, 1, 1, 512, 256, 256),     # 1x1 low-res map (64 px tiles)
+]
+
+
+@pytest.mark.parametrize("case", UP_CASES, ids=lambda c: "n{}_{}x{}_c{}+{}to{}".format(*c))
+def test_conv_upsample_concat(ctx, case):
+    n, h, w, cx, cskip, cout = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(n, cx, h, w, generator=g).cuda()
+    skip = torch.randn(n, cskip, 2 * h, 2 * w, generator=g).cuda() if cskip else None
+    cin = cx + cskip
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    y = ctx.debug_conv(_nhwc_bf16(x), wt, stride=1, pad=1, scale=scale, bias=bias, relu=True, up2=True,
+                       skip=_nhwc_bf16(skip) if cskip else None)
+    xin = F.interpolate(_bf16_round(x), scale_factor=2, mode="nearest")
+    if cskip:
+        xin = torch.cat([xin, _bf16_round(skip)], 1)
+    ref = F.relu(F.conv2d(xin, _bf16_round(wt).cuda(), None, 1, 1) * scale.cuda().view(1, -1, 1, 1) + bias.cuda().view(1, -1, 1, 1))
+    _assert_close_bf16(_nchw_f32(y), ref, f"up conv {case}")
+
+
+@pytest.mark.parametrize("ph,pw,n", [(64, 64, 5), (256, 256, 2), (32, 96, 3)])
+def test_stem(ctx, ph, pw, n):
+    ih, iw = 600, 700
+    raster = synth.synth_slide(ih, iw, 11)
+    g = torch.Generator().manual_seed(3)
+    tiles = np.stack([torch.randint(0, iw - pw, (n,), generator=g).numpy(), torch.randint(0, ih - ph, (n,), generator=g).numpy()], 1).astype(np.int32)
+    wt = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / (64 * 49)) ** 0.5
+    scale = torch.rand(64, generator=g) + 0.5
+    bias = torch.randn(64, generator=g) * 0.1
+    sl = ctx.slide_desc(raster, ih, iw, ph, pw)
+    y = ctx.debug_stem(sl, tiles, wt, scale, bias)
+    x = _bf16_round(O.gather_tiles(raster, [tuple(t) for t in tiles], ph, pw)).cuda()
+    ref = F.relu(F.conv2d(x, _bf16_round(wt).cuda(), None, 2, 3) * scale.cuda().view(1, -1, 1, 1) + bias.cuda().view(1, -1, 1, 1))
+    _assert_close_bf16(_nchw_f32(y), ref, f"stem {ph}x{pw}")

@@ -1,0 +1,288 @@
+// conv_igemm.cu — host side of the tcgen05 implicit-GEMM convolution (see conv_igemm.cuh).
+#include "conv_igemm.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace wsi {
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda) ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+void init_tensor_map_api() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  });
+  WSI_REQUIRE(g_encode != nullptr, WSI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+}
+
+static CUtensorMapSwizzle swizzle_for(int block_k) {
+  return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 4-D bf16 map: dims (d0 contiguous .. d3), byte strides for d1..d3
+static void encode4(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides[3],
+                    const uint32_t box[4], int block_k) {
+  init_tensor_map_api();
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  WSI_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, WSI_ERR_INVALID, "TMA base not 16-byte aligned");
+  for (int i = 0; i < 3; ++i) WSI_REQUIRE(strides[i] % 16 == 0, WSI_ERR_INVALID, "TMA stride %d = %llu not a multiple of 16", i, (unsigned long long)strides[i]);
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WSI_REQUIRE(r == CUDA_SUCCESS, WSI_ERR_CUDA,
+              "cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) box=(%u,%u,%u,%u) strides=(%llu,%llu,%llu)", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+              box[0], box[1], box[2], box[3], (unsigned long long)strides[0], (unsigned long long)strides[1], (unsigned long long)strides[2]);
+}
+
+static void encode2(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t stride1, uint32_t b0, uint32_t b1, int block_k) {
+  init_tensor_map_api();
+  const cuuint64_t dims[2] = {d0, d1};
+  const cuuint64_t strides[1] = {stride1};
+  const cuuint32_t box[2] = {b0, b1};
+  const cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WSI_REQUIRE(r == CUDA_SUCCESS, WSI_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d dims=(%llu,%llu) box=(%u,%u)", (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, b0, b1);
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+static void choose_box(int A_h, int A_w, int* bw, int* bh, int* bn) {
+  *bw = std::min(16, pow2_floor(std::max(A_w, 1)));
+  *bh = std::min(kBlockM / *bw, pow2_ceil(std::max(A_h, 1)));
+  *bn = kBlockM / (*bw * *bh);
+}
+
+// plain NHWC view
+static void map_plain(CUtensorMap* m, const TensorView& t, int block_k, int bw, int bh, int bn) {
+  const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)t.W, (uint64_t)t.H, (uint64_t)t.N};
+  const uint64_t st[3] = {(uint64_t)t.C * 2, (uint64_t)t.W * t.C * 2, (uint64_t)t.H * t.W * t.C * 2};
+  const uint32_t box[4] = {(uint32_t)block_k, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  encode4(m, t.ptr, dims, st, box, block_k);
+}
+// (hp, wp) parity view: element (a, b) = t[2a+hp, 2b+wp]
+static void map_parity(CUtensorMap* m, const TensorView& t, int hp, int wp, int block_k, int bw, int bh, int bn) {
+  const char* base = static_cast<const char*>(t.ptr) + ((size_t)hp * t.W + wp) * t.C * 2;
+  const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)((t.W - wp + 1) / 2), (uint64_t)((t.H - hp + 1) / 2), (uint64_t)t.N};
+  const uint64_t st[3] = {(uint64_t)t.C * 4, (uint64_t)t.W * t.C * 4, (uint64_t)t.H * t.W * t.C * 2};
+  const uint32_t box[4] = {(uint32_t)block_k, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  encode4(m, base, dims, st, box, block_k);
+}
+
+static inline int floor_div2(int t) { return (t >= 0) ? t / 2 : -((-t + 1) / 2); }
+
+void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
+                   const float* scale, const float* bias, const void* residual, void* out,
+                   const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms) {
+  WSI_REQUIRE(!parts.empty() && parts.size() <= 2, WSI_ERR_INVALID, "conv: 1 or 2 input parts");
+  bool any_up = false;
+  for (auto& q : parts) any_up |= q.up2;
+  const int k = spec.ksize;
+  int Hin = 0, Win = 0, N = parts[0].t.N, cin = 0;
+  for (auto& q : parts) {
+    const int h = q.up2 ? 2 * q.t.H : q.t.H, w = q.up2 ? 2 * q.t.W : q.t.W;
+    if (Hin == 0) { Hin = h; Win = w; }
+    WSI_REQUIRE(h == Hin && w == Win && q.t.N == N, WSI_ERR_INVALID, "conv: input parts disagree on shape");
+    WSI_REQUIRE(q.t.C % 16 == 0, WSI_ERR_UNSUPPORTED, "conv: channels (%d) must be a multiple of 16", q.t.C);
+    cin += q.t.C;
+  }
+  int bk = 64;
+  for (auto& q : parts) while (q.t.C % bk) bk /= 2;
+  const int OH = (Hin + 2 * spec.pad - k) / spec.stride + 1, OW = (Win + 2 * spec.pad - k) / spec.stride + 1;
+  WSI_REQUIRE(spec.cout % 16 == 0, WSI_ERR_UNSUPPORTED, "conv: cout (%d) must be a multiple of 16", spec.cout);
+  int bn_out = 128;
+  while (spec.cout % bn_out) bn_out /= 2;
+  block_n_ = bn_out;
+  block_k_ = bk;
+
+  ConvParams& p = p_;
+  p = ConvParams{};
+  p.N = N; p.OH = OH; p.OW = OW; p.Cout = spec.cout;
+  p.relu = spec.relu ? 1 : 0;
+  p.res = static_cast<const bf16*>(residual);
+  p.out = static_cast<bf16*>(out);
+  p.error_flag = error_flag;
+
+  std::vector<KBlock> table;
+  int num_parity = 1;
+  if (any_up) {
+    WSI_REQUIRE(k == 3 && spec.stride == 1 && spec.pad == 1, WSI_ERR_UNSUPPORTED, "up2 conv must be 3x3/s1/p1");
+    WSI_REQUIRE(parts[0].up2 && (parts.size() == 1 || !parts[1].up2), WSI_ERR_UNSUPPORTED, "up2 conv: parts = [up2 x, skip]");
+    p.sigma = 2; num_parity = 4;
+    p.A_h = OH / 2; p.A_w = OW / 2;
+  } else {
+    WSI_REQUIRE(spec.stride == 1 || (spec.stride == 2 && parts.size() == 1), WSI_ERR_UNSUPPORTED, "conv: stride %d with %zu parts", spec.stride, parts.size());
+    p.sigma = 1;
+    p.A_h = OH; p.A_w = OW;
+  }
+  choose_box(p.A_h, p.A_w, &p.bw, &p.bh, &p.bn);
+
+  // tensor maps
+  if (any_up) {
+    map_plain(&amaps_.m[0], parts[0].t, bk, p.bw, p.bh, p.bn);
+    if (parts.size() == 2)
+      for (int hp = 0; hp < 2; ++hp)
+        for (int wp = 0; wp < 2; ++wp) map_parity(&amaps_.m[1 + hp * 2 + wp], parts[1].t, hp, wp, bk, p.bw, p.bh, p.bn);
+  } else if (spec.stride == 1) {
+    for (size_t i = 0; i < parts.size(); ++i) map_plain(&amaps_.m[i], parts[i].t, bk, p.bw, p.bh, p.bn);
+  } else {
+    for (int hp = 0; hp < 2; ++hp)
+      for (int wp = 0; wp < 2; ++wp) map_parity(&amaps_.m[hp * 2 + wp], parts[0].t, hp, wp, bk, p.bw, p.bh, p.bn);
+  }
+  for (int i = 0; i < kMaxAMaps; ++i)  // unused slots alias map 0 so every descriptor is valid
+    if (i >= (any_up ? (parts.size() == 2 ? 5 : 1) : (spec.stride == 1 ? (int)parts.size() : 4))) amaps_.m[i] = amaps_.m[0];
+
+  // K-block table (per parity) and packed weights (parity independent)
+  const int taps = k * k;
+  int kb_per_tap = 0;
+  for (auto& q : parts) kb_per_tap += q.t.C / bk;
+  const int num_kb = taps * kb_per_tap;
+  WSI_REQUIRE(num_kb <= 128, WSI_ERR_UNSUPPORTED, "conv: %d K blocks > 128", num_kb);
+  const int K = num_kb * bk;
+  std::vector<uint16_t> wp((size_t)spec.cout * K);
+  for (int par = 0; par < num_parity; ++par) {
+    const int py = par >> 1, px = par & 1;
+    for (int r = 0; r < k; ++r)
+      for (int s = 0; s < k; ++s) {
+        int part_off = 0;
+        for (size_t pi = 0; pi < parts.size(); ++pi) {
+          const auto& q = parts[pi];
+          for (int c0 = 0; c0 < q.t.C; c0 += bk) {
+            KBlock e{};
+            e.c0 = c0;
+            if (any_up) {
+              const int ty = py + r - 1, tx = px + s - 1;
+              if (q.up2) {
+                e.map = 0; e.da = (int8_t)floor_div2(ty); e.db = (int8_t)floor_div2(tx);
+              } else {
+                const int hp = ty & 1, wpp = tx & 1;
+                e.map = (int8_t)(1 + hp * 2 + wpp); e.da = (int8_t)((ty - hp) / 2); e.db = (int8_t)((tx - wpp) / 2);
+              }
+            } else if (spec.stride == 1) {
+              e.map = (int8_t)pi; e.da = (int8_t)(r - spec.pad); e.db = (int8_t)(s - spec.pad);
+            } else {
+              const int ty = r - spec.pad, tx = s - spec.pad;
+              const int hp = ty & 1, wpp = tx & 1;
+              e.map = (int8_t)(hp * 2 + wpp); e.da = (int8_t)((ty - hp) / 2); e.db = (int8_t)((tx - wpp) / 2);
+            }
+            if (par == 0) {
+              const int kb = (int)table.size();
+              for (int co = 0; co < spec.cout; ++co)
+                for (int j = 0; j < bk; ++j) {
+                  const float v = w_oihw[(((size_t)co * cin + part_off + c0 + j) * k + r) * k + s];
+                  wp[(size_t)co * K + (size_t)kb * bk + j] = f32_to_bf16_bits(v);
+                }
+            }
+            table.push_back(e);
+          }
+          part_off += q.t.C;
+        }
+      }
+  }
+  p.num_kb = num_kb;
+  flops_ = 2.0 * N * OH * OW * (double)spec.cout * cin * taps;
+
+  if (spec.head) {
+    WSI_REQUIRE(spec.cout == 16 && head_w && head_b && head_out, WSI_ERR_INVALID, "fused head needs cout == 16");
+    std::vector<float> hw(head_w, head_w + 64), hb(head_b, head_b + 4);
+    upload(headw_, hw); upload(headb_, hb);
+    p.head_w = headw_.as<float>(); p.head_b = headb_.as<float>(); p.head_out = head_out;
+    flops_ += 2.0 * N * OH * OW * 16 * 4;
+  }
+  finish(table, num_parity, wp, K, scale, bias, num_sms);
+}
+
+void ConvOp::build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw, const float* scale,
+                        const float* bias, void* out, int* error_flag, int num_sms) {
+  WSI_REQUIRE(ph % 2 == 0 && pw % 2 == 0, WSI_ERR_UNSUPPORTED, "stem: tile size must be even");
+  block_n_ = 64; block_k_ = 32;
+  ConvParams& p = p_;
+  p = ConvParams{};
+  p.N = n; p.OH = ph / 2; p.OW = pw / 2; p.Cout = 64;
+  p.sigma = 1; p.A_h = p.OH; p.A_w = p.OW;
+  p.relu = 1; p.out = static_cast<bf16*>(out); p.error_flag = error_flag;
+  choose_box(p.A_h, p.A_w, &p.bw, &p.bh, &p.bn);
+  const uint64_t pitch = (uint64_t)(pw + 8) * 8, tile_bytes = (uint64_t)(ph + 6) * pitch;
+  for (int hp = 0; hp < 2; ++hp) {
+    // overlapping-window view: dim0 = 32 elements (8 px x 4 ch) starting every 2 px (16 B)
+    const char* base = static_cast<const char*>(padded_tiles) + hp * pitch;
+    const uint64_t dims[4] = {32, (uint64_t)p.OW, (uint64_t)((ph + 6) / 2), (uint64_t)n};
+    const uint64_t st[3] = {16, 2 * pitch, tile_bytes};
+    const uint32_t box[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    encode4(&amaps_.m[hp], base, dims, st, box, 32);
+  }
+  for (int i = 2; i < kMaxAMaps; ++i) amaps_.m[i] = amaps_.m[0];
+  std::vector<KBlock> table;
+  const int K = 7 * 32;
+  std::vector<uint16_t> wp((size_t)64 * K, 0);
+  for (int r = 0; r < 7; ++r) {
+    KBlock e{};
+    e.map = (int8_t)(r & 1); e.da = (int8_t)(r >> 1); e.db = 0; e.c0 = 0;
+    table.push_back(e);
+    for (int co = 0; co < 64; ++co)
+      for (int s = 0; s < 7; ++s)
+        for (int c = 0; c < 3; ++c)
+          wp[(size_t)co * K + r * 32 + s * 4 + c] = f32_to_bf16_bits(w_oihw[(((size_t)co * 3 + c) * 7 + r) * 7 + s]);
+  }
+  p.num_kb = 7;
+  flops_ = 2.0 * n * p.OH * p.OW * 64.0 * 147.0;
+  finish(table, 1, wp, K, scale, bias, num_sms);
+}
+
+void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std::vector<uint16_t>& wpacked, int K,
+                    const float* scale, const float* bias, int num_sms) {
+  ConvParams& p = p_;
+  p.num_parity = num_parity;
+  upload(w_, wpacked);
+  std::vector<float> sc(p.Cout, 1.f), bi(p.Cout, 0.f);
+  if (scale) sc.assign(scale, scale + p.Cout);
+  if (bias) bi.assign(bias, bias + p.Cout);
+  upload(scale_, sc); upload(bias_, bi);
+  upload(tbl_, table);
+  p.scale = scale_.as<float>(); p.bias = bias_.as<float>(); p.kblocks = tbl_.as<KBlock>();
+  encode2(&bmap_, w_.p, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, (uint32_t)block_k_, (uint32_t)block_n_, block_k_);
+  p.tiles_w = (int)ceil_div(p.A_w, p.bw);
+  p.tiles_h = (int)ceil_div(p.A_h, p.bh);
+  p.tiles_n = (int)ceil_div(p.N, p.bn);
+  p.tiles_co = p.Cout / block_n_;
+  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co * num_parity;
+  WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "conv: too many tiles");
+  grid_ = (int)std::min<long long>(total, num_sms);
+  CUDA_CHECK(cudaStreamSynchronize(0));   // uploads above used the default stream
+}
+
+template <int BN, int BK>
+static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
+  using S = ConvSmem<BN, BK>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  conv_igemm_kernel<BN, BK><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
+#define WSI_CASE(BN, BK) \
+  if (block_n_ == BN && block_k_ == BK) { launch_inst<BN, BK>(amaps_, bmap_, p_, grid_, stream); if (lc) lc->n++; return; }
+  WSI_CASE(128, 64) WSI_CASE(64, 64) WSI_CASE(32, 64) WSI_CASE(16, 64)
+  WSI_CASE(128, 32) WSI_CASE(64, 32) WSI_CASE(32, 32) WSI_CASE(16, 32)
+  WSI_CASE(128, 16) WSI_CASE(64, 16) WSI_CASE(32, 16) WSI_CASE(16, 16)
+#undef WSI_CASE
+  WSI_THROW(WSI_ERR_UNSUPPORTED, "conv: no kernel instance for BLOCK_N=%d BLOCK_K=%d", block_n_, block_k_);
+}
+
+}  // namespace wsi

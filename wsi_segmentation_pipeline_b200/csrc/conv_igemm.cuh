@@ -1,0 +1,471 @@
+// conv_igemm.cuh — implicit-GEMM convolution on 5th-gen tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+//
+// Every dense contraction on the reference's hot path is a convolution over NHWC tiles
+// (SURVEY.md §2a K1-K3, K5): 7x7/s2 stem (resnets_shift.py:122), 3x3 s1/s2 BasicBlock convs
+// (:41-44), 1x1/s2 projections (:173-177) and the smp decoder's upsample+concat+3x3 convs.
+// All of them run through ONE table-driven kernel:
+//
+//   D[128 output pixels, BLOCK_N out channels] += A[128 pixels, BLOCK_K] * B[BLOCK_N, BLOCK_K]^T
+//
+// * A (activations, bf16 NHWC) is never im2col'ed in memory: for each K block (one filter tap x
+//   one channel chunk) the producer issues a 4-D TMA box load {BLOCK_K ch, bw, bh, bn} whose
+//   origin is shifted by the tap offset; TMA's out-of-bounds zero fill IS the conv zero padding.
+// * stride-2 convs read through "parity views" of the input (one tensor map per (row,col) parity
+//   with doubled strides), so the same box load works.
+// * the decoder's nearest x2 upsample + channel concat is folded into the operand addressing:
+//   output pixels are processed per parity class (oh%2, ow%2), for which every tap of the
+//   upsampled operand is a plain box of the half-resolution tensor, and the skip operand is a
+//   parity view.  No upsampled or concatenated tensor ever exists in HBM.
+// * the stem reads the gather kernel's zero-padded 4-channel tiles through an overlapping-window
+//   map (dim1 stride 16 B): one K block = one filter row = 8 px x 4 ch = 32 elements.
+// * B (weights) is pre-packed [Cout][K] bf16, K ordered exactly as the K-block table.
+// * accumulators live in TMEM (double buffered: the epilogue of tile i overlaps the MMAs of
+//   tile i+1); the epilogue applies folded BN scale/bias (+ residual) (+ ReLU) in fp32 and
+//   stores bf16 NHWC, or for the last decoder conv applies the fused 1x1 `final_conv` head and
+//   stores fp32 logits.
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
+//   Persistent CTAs (grid = min(tiles, #SM)), static round-robin tile schedule, N-tile fastest so
+//   CTAs sharing an A tile run together and hit L2.
+#pragma once
+#include "common.cuh"
+
+namespace wsi {
+
+constexpr int kMaxAMaps = 5;
+constexpr int kBlockM = 128;
+constexpr int kNumThreads = 192;
+
+struct KBlock {      // one K block of the implicit GEMM
+  int8_t map;        // which A tensor map
+  int8_t da, db;     // box origin offset in (row, col) of that map's lattice
+  int8_t _pad;
+  int32_t c0;        // channel origin in that map
+};
+
+struct ConvParams {
+  int N, OH, OW, Cout;        // output tensor [N, OH, OW, Cout]
+  int sigma;                  // output lattice stride: pixel = (sigma*a + py, sigma*b + px)
+  int num_parity;             // 1, or 4 when sigma == 2 (py, px in {0,1}^2)
+  int A_h, A_w;               // lattice extents
+  int bw, bh, bn;             // M tile = bn x bh x bw lattice points (product 128)
+  int tiles_w, tiles_h, tiles_n, tiles_co;
+  int num_kb;                 // K blocks per parity
+  int relu;
+  const float* scale;         // [Cout] folded BN scale (or 1)
+  const float* bias;          // [Cout] folded BN bias (or conv bias)
+  const bf16* res;            // residual, same shape as out, or nullptr
+  bf16* out;                  // may be nullptr when head_out is set
+  const float* head_w;        // fused 1x1 head: [4][16]
+  const float* head_b;        // [4]
+  float* head_out;            // [N, OH, OW, 4] fp32
+  const KBlock* kblocks;      // [num_parity][num_kb]
+  int* error_flag;            // set to 1 by a timed-out barrier wait
+};
+
+struct AMaps {
+  CUtensorMap m[kMaxAMaps];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box (a hang costs a strike); after ~2 s of
+// SM clocks the kernel records the failure and traps.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (error_flag) atomicExch(error_flag, 100 + tag);
+      printf("wsi conv_igemm: barrier wait timed out (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+}  // namespace ptx
+
+// SM100 shared-memory matrix descriptor, K-major operand, rows of (BLOCK_K*2) bytes packed densely,
+// swizzle width == row width (128/64/32 B); 8-row core-matrix groups are 8*row bytes apart (SBO).
+template <int BLOCK_K>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  constexpr uint32_t row_bytes = BLOCK_K * 2;
+  constexpr uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);  // UMMA::LayoutType
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                              // LBO (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;        // SBO [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell) [46,48)
+  d |= layout << 61;                                   // swizzle mode [61,64)
+  return d;
+}
+
+template <int BLOCK_N>
+__host__ __device__ constexpr uint32_t make_idesc_bf16() {
+  return (1u << 4)                       // D format  = F32
+         | (1u << 7)                     // A format  = BF16
+         | (1u << 10)                    // B format  = BF16
+         | (0u << 15) | (0u << 16)       // A, B K-major
+         | ((uint32_t)(BLOCK_N >> 3) << 17)
+         | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int BLOCK_N, int BLOCK_K>
+struct ConvSmem {
+  static constexpr int kABytes = kBlockM * BLOCK_K * 2;
+  static constexpr int kBBytesRaw = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBBytes = (kBBytesRaw + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesWanted = (160 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesWanted > 8 ? 8 : (kStagesWanted < 2 ? 2 : kStagesWanted);
+  static constexpr int kTableBytes = 4 * 128 * (int)sizeof(KBlock);   // up to 4 parities x 128 K blocks
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = 1024 /*align slack*/ + kStages * kStageBytes + kTableBytes + kBarBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  KBlock* tbl = reinterpret_cast<KBlock*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + S::kTableBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + S::kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * S::kStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * S::kStages + 2;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = p.num_kb;
+
+  // K-block table -> smem
+  for (int i = threadIdx.x; i < p.num_parity * num_kb; i += blockDim.x) tbl[i] = p.kblocks[i];
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < S::kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&bmap);
+    ptx::prefetch_tmap(&amaps.m[0]);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_holder, S::kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int tiles_per_par = p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_co;
+  const int total_tiles = tiles_per_par * p.num_parity;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int ct = r % p.tiles_co; r /= p.tiles_co;
+        const int par = r % p.num_parity; r /= p.num_parity;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int tn = r;
+        const int n0 = tn * p.bn, a0 = th * p.bh, b0 = tw * p.bw, co0 = ct * BLOCK_N;
+        const KBlock* kb_tbl = tbl + par * num_kb;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 1);
+          ptx::mbar_expect_tx(&full[stage], S::kABytes + S::kBBytesRaw);
+          const KBlock e = kb_tbl[kb];
+          uint8_t* sA = stage_base + stage * S::kStageBytes;
+          uint8_t* sB = sA + S::kABytes;
+          const CUtensorMap* am = &amaps.m[0];
+          switch (e.map) {
+            case 1: am = &amaps.m[1]; break;
+            case 2: am = &amaps.m[2]; break;
+            case 3: am = &amaps.m[3]; break;
+            case 4: am = &amaps.m[4]; break;
+            default: break;
+          }
+          ptx::tma_load_4d(sA, am, &full[stage], e.c0, b0 + e.db, a0 + e.da, n0);
+          ptx::tma_load_2d(sB, &bmap, &full[stage], kb * BLOCK_K, co0);
+          if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16<BLOCK_N>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 2);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full[stage], phase, p.error_flag, 3);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(stage_base + stage * S::kStageBytes);
+          const uint32_t b_addr = a_addr + S::kABytes;
+          const uint64_t adesc = make_kmajor_desc<BLOCK_K>(a_addr);
+          const uint64_t bdesc = make_kmajor_desc<BLOCK_K>(b_addr);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advancing 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
+            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          ptx::umma_commit(&empty[stage]);      // frees the smem stage when these MMAs retire
+          if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ================================ epilogue (4 warps) ==========================
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;             // M index inside the tile == TMEM lane
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int ct = r % p.tiles_co; r /= p.tiles_co;
+      const int par = r % p.num_parity; r /= p.num_parity;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      const int tn = r;
+      const int co0 = ct * BLOCK_N;
+      // lattice point of this row
+      const int wl = row % p.bw;
+      const int hl = (row / p.bw) % p.bh;
+      const int nl = row / (p.bw * p.bh);
+      const int n = tn * p.bn + nl, a = th * p.bh + hl, b = tw * p.bw + wl;
+      const bool valid = (n < p.N) && (a < p.A_h) && (b < p.A_w);
+      const int oh = p.sigma * a + (par >> 1), ow = p.sigma * b + (par & 1);
+      const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
+
+      ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 4);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+
+      float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld16(t_row + (uint32_t)c, v);
+        ptx::tmem_ld_wait();
+        float y[16];
+        const float4* sc4 = reinterpret_cast<const float4*>(p.scale + co0 + c);
+        const float4* bi4 = reinterpret_cast<const float4*>(p.bias + co0 + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 s = __ldg(sc4 + j), bb = __ldg(bi4 + j);
+          y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), s.x, bb.x);
+          y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), s.y, bb.y);
+          y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), s.z, bb.z);
+          y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), s.w, bb.w);
+        }
+        if (valid) {
+          const size_t off = pix * p.Cout + co0 + c;
+          if (p.res != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint4 rv = __ldg(rp + j);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                y[8 * j + 2 * t + 0] += __uint_as_float(w[t] << 16);
+                y[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          if (p.head_out != nullptr) {
+            // fused final 1x1 conv (Cout == BLOCK_N == 16): logits = W[4x16] y + b
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) s = fmaf(y[j], __ldg(p.head_w + k * 16 + j), s);
+              head_acc[k] += s;
+            }
+          }
+          if (p.out != nullptr) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+                w[t] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      if (valid && p.head_out != nullptr) {
+        float4 o;
+        o.x = head_acc[0] + __ldg(p.head_b + 0);
+        o.y = head_acc[1] + __ldg(p.head_b + 1);
+        o.z = head_acc[2] + __ldg(p.head_b + 2);
+        o.w = head_acc[3] + __ldg(p.head_b + 3);
+        reinterpret_cast<float4*>(p.head_out)[pix] = o;
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, S::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct TensorView {          // bf16 NHWC activation tensor in HBM
+  const void* ptr = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+};
+
+// One operand part of a conv input (the input is the channel concat of its parts).
+struct ConvInputPart {
+  TensorView t;
+  bool up2 = false;          // nearest x2 upsampled view of t
+};
+
+struct ConvSpec {
+  int ksize = 3, stride = 1, pad = 1;
+  int cout = 0;
+  bool relu = false;
+  bool head = false;         // fused final 1x1 conv (cout must be 16)
+};
+
+// A fully prepared conv launch: tensor maps, K-block table, packed weights, epilogue params.
+class ConvOp {
+ public:
+  ConvOp() = default;
+  ConvOp(ConvOp&&) = default;
+  ConvOp& operator=(ConvOp&&) = default;
+
+  // weights: fp32 OIHW [cout][cin_total][k][k]; scale/bias may be nullptr (1 / 0).
+  void build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
+             const float* scale, const float* bias, const void* residual, void* out,
+             const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms);
+  // stem: x = gather output, zero-padded tiles [n][ph+6][pw+8][4] bf16; 7x7/s2/p3, cout 64.
+  void build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw /*[64,3,7,7]*/,
+                  const float* scale, const float* bias, void* out, int* error_flag, int num_sms);
+  void launch(cudaStream_t stream, LaunchCounter* lc) const;
+  double flops() const { return flops_; }
+  int block_n() const { return block_n_; }
+  int block_k() const { return block_k_; }
+
+ private:
+  void finish(const std::vector<KBlock>& table, int num_parity, const std::vector<uint16_t>& wpacked, int K,
+              const float* scale, const float* bias, int num_sms);
+  AMaps amaps_{};
+  CUtensorMap bmap_{};
+  ConvParams p_{};
+  DevBuf w_, scale_, bias_, tbl_, headw_, headb_;
+  int block_n_ = 0, block_k_ = 0, grid_ = 0;
+  double flops_ = 0;
+};
+
+void init_tensor_map_api();   // resolves cuTensorMapEncodeTiled through the runtime (no -lcuda link)
+
+}  // namespace wsi

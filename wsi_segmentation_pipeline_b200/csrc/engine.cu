@@ -1,0 +1,942 @@
+// engine.cu — libwsi_b200's context, network plans and the C-ABI entry points (include/wsi_b200.h).
+//
+// The sliding-window loop of the reference (utils/eval.py:190-228) becomes, per slide / row band:
+//   sort tiles by canvas origin -> for each batch of tiles { gather+normalise (K0) -> stem ->
+//   max-pool -> tcgen05 implicit-GEMM convs (K2/K3/K5) -> head | fused 1x1 logits } ->
+//   atomic-free overlap-accumulate into an fp32 canvas (K6) -> softmax/argmax/heatmap (K7).
+// Everything is stream-ordered on the caller's stream; host buffers are copied in/out at the ends.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <numeric>
+
+#include "conv_igemm.cuh"
+#include "kernels.cuh"
+
+namespace wsi {
+
+static thread_local std::string g_last_error;
+void set_global_error(const std::string& m) { g_last_error = m; }
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct Act {  // bf16 NHWC activation in HBM
+  DevBuf buf;
+  int N = 0, H = 0, W = 0, C = 0;
+  TensorView view() const { return TensorView{buf.p, N, H, W, C}; }
+  size_t bytes() const { return (size_t)N * H * W * C * 2; }
+};
+
+enum StageId { ST_GATHER = 0, ST_STEM, ST_MAXPOOL, ST_CONV, ST_HEAD, ST_STITCH, ST_FINALISE, ST_H2D, ST_D2H, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"gather", "stem", "maxpool", "conv", "head", "stitch", "finalise", "h2d", "d2h"};
+
+struct StageAcc {
+  double ms = 0, work = 0;
+  int64_t launches = 0;
+};
+
+struct EventSpan {
+  cudaEvent_t a, b;
+  int stage;
+};
+
+}  // namespace wsi
+
+using namespace wsi;
+
+struct NetPlan;
+
+struct wsi_ctx {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  LaunchCounter lc;
+  int arch = -1;
+  int num_classes = 4;
+  std::map<std::string, HostTensor> sd;
+  float class_probs[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t batch_tiles = 0;
+  int stage_timing = 0;
+  DevBuf lut;        // f32 [3][256] normalise table
+  DevBuf err_flag;   // int, set by a timed-out barrier wait inside the conv kernel
+  std::unique_ptr<NetPlan> plan;
+  // stage statistics
+  StageAcc acc[ST_COUNT];
+  std::vector<EventSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
+  // scratch reused across slides
+  DevBuf raster, maskbuf, canvas, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, tile_logits, scratch_f32, counts;
+};
+
+namespace wsi {
+
+// ---------------------------------------------------------------------------------------------
+// stage timing: CUDA events on the launching stream, resolved lazily after a sync
+// ---------------------------------------------------------------------------------------------
+struct StageScope {
+  wsi_ctx* c;
+  cudaStream_t s;
+  int stage;
+  int64_t l0;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageScope(wsi_ctx* ctx, cudaStream_t st, int stage_id, double work) : c(ctx), s(st), stage(stage_id), l0(ctx->lc.n) {
+    c->acc[stage].work += work;
+    if (!c->stage_timing) return;
+    a = get_event();
+    b = get_event();
+    cudaEventRecord(a, s);
+  }
+  ~StageScope() {
+    c->acc[stage].launches += c->lc.n - l0;
+    if (!a) return;
+    cudaEventRecord(b, s);
+    c->spans.push_back(EventSpan{a, b, stage});
+  }
+  cudaEvent_t get_event() {
+    if (!c->event_pool.empty()) {
+      cudaEvent_t e = c->event_pool.back();
+      c->event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+
+static void resolve_spans(wsi_ctx* c) {
+  for (auto& sp : c->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) c->acc[sp.stage].ms += ms;
+    c->event_pool.push_back(sp.a);
+    c->event_pool.push_back(sp.b);
+  }
+  c->spans.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+// model helpers
+// ---------------------------------------------------------------------------------------------
+static const HostTensor& weight(const wsi_ctx* c, const std::string& name) {
+  auto it = c->sd.find(name);
+  if (it == c->sd.end()) WSI_THROW(WSI_ERR_NOMODEL, "state_dict entry '%s' is missing", name.c_str());
+  return it->second;
+}
+static bool has_weight(const wsi_ctx* c, const std::string& name) { return c->sd.find(name) != c->sd.end(); }
+
+struct Folded {
+  std::vector<float> scale, bias;
+};
+// eval-mode BatchNorm2d (eps 1e-5, resnets_shift.py:37) folded to y = x*scale + bias
+static Folded fold_bn(const wsi_ctx* c, const std::string& p, int channels) {
+  const HostTensor &w = weight(c, p + ".weight"), &b = weight(c, p + ".bias"), &mu = weight(c, p + ".running_mean"),
+                   &var = weight(c, p + ".running_var");
+  WSI_REQUIRE(w.numel() == channels && b.numel() == channels && mu.numel() == channels && var.numel() == channels,
+              WSI_ERR_NOMODEL, "BatchNorm '%s' has the wrong size (want %d)", p.c_str(), channels);
+  Folded f;
+  f.scale.resize(channels);
+  f.bias.resize(channels);
+  for (int i = 0; i < channels; ++i) {
+    const float s = w.data[i] / std::sqrt(var.data[i] + 1e-5f);
+    f.scale[i] = s;
+    f.bias[i] = b.data[i] - mu.data[i] * s;
+  }
+  return f;
+}
+
+static const HostTensor& conv_weight(const wsi_ctx* c, const std::string& name, int cout, int cin, int k) {
+  const HostTensor& w = weight(c, name);
+  WSI_REQUIRE(w.shape.size() == 4 && w.shape[0] == cout && w.shape[1] == cin && w.shape[2] == k && w.shape[3] == k,
+              WSI_ERR_NOMODEL, "conv weight '%s' has the wrong shape (want [%d,%d,%d,%d])", name.c_str(), cout, cin, k, k);
+  return w;
+}
+
+}  // namespace wsi
+
+// ---------------------------------------------------------------------------------------------
+// NetPlan: one batch of `cap` tiles of ph x pw through the network, all buffers and tensor maps
+// prepared once.  Trunk: resnets_shift.py:196-204 (== smp ResNetEncoder); decoder: smp Unet.
+// ---------------------------------------------------------------------------------------------
+struct NetPlan {
+  int arch = -1, head = -1, cap = 0, ph = 0, pw = 0;
+  struct Step {
+    int kind;  // 0 conv, 1 maxpool, 2 pool+head
+    int stage;
+    ConvOp* op = nullptr;
+    Act *in = nullptr, *out = nullptr;
+  };
+  std::vector<std::unique_ptr<Act>> acts;
+  std::vector<std::unique_ptr<ConvOp>> ops;
+  std::vector<Step> steps;
+  DevBuf in_pad;                 // [cap][ph+6][pw+8][4] bf16, zero border
+  DevBuf logits;                 // SEG: f32 [cap][ph][pw][4]; CLS/REG/FEATURES: f32 [cap][out_dim]
+  DevBuf hw1, hb1, hw2, hb2;     // head weights
+  int n1 = 0, n2 = 0, out_dim = 0;
+  Act* x4 = nullptr;
+  double conv_flops = 0, stem_flops = 0;   // per batch of `cap` tiles (algorithmic: 2*MAC, no padding)
+  std::vector<Act*> feats;                 // [x4, x3, x2, x1, x0]
+
+  Act* new_act(int N, int H, int W, int C) {
+    acts.emplace_back(new Act());
+    Act* a = acts.back().get();
+    a->N = N; a->H = H; a->W = W; a->C = C;
+    a->buf.alloc(a->bytes());
+    return a;
+  }
+  ConvOp* new_op() {
+    ops.emplace_back(new ConvOp());
+    return ops.back().get();
+  }
+
+  void build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_);
+  void run(wsi_ctx* c, cudaStream_t s);
+};
+
+void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_) {
+  arch = arch_; head = head_; cap = cap_; ph = ph_; pw = pw_;
+  WSI_REQUIRE(cap > 0 && ph > 0 && pw > 0, WSI_ERR_INVALID, "plan: empty batch");
+  WSI_REQUIRE(ph % 2 == 0 && pw % 2 == 0 && ph >= 8 && pw >= 8, WSI_ERR_UNSUPPORTED, "tile size %dx%d: must be even and >= 8", ph, pw);
+  if (head == WSI_HEAD_SEG) {
+    WSI_REQUIRE(arch == WSI_ARCH_UNET_R18, WSI_ERR_UNSUPPORTED, "SEG head needs the U-Net model");
+    WSI_REQUIRE(ph % 32 == 0 && pw % 32 == 0, WSI_ERR_UNSUPPORTED, "SEG: tile size %dx%d must be a multiple of 32 (5 encoder stages)", ph, pw);
+    WSI_REQUIRE(c->num_classes == 4, WSI_ERR_UNSUPPORTED, "SEG: num_classes must be 4 (got %d)", c->num_classes);
+  }
+  const std::string tp = (arch == WSI_ARCH_UNET_R18) ? "encoder." : "";
+  int* ef = c->err_flag.as<int>();
+  const int sms = c->num_sms;
+
+  in_pad.alloc((size_t)cap * (ph + 6) * (pw + 8) * 4 * 2);
+  CUDA_CHECK(cudaMemset(in_pad.p, 0, in_pad.bytes));
+
+  // ---- stem: conv1 7x7/s2/p3 + bn1 + relu (resnets_shift.py:196-198) ----
+  Act* x0 = new_act(cap, ph / 2, pw / 2, 64);
+  {
+    const HostTensor& w = conv_weight(c, tp + "conv1.weight", 64, 3, 7);
+    const Folded f = fold_bn(c, tp + "bn1", 64);
+    ConvOp* op = new_op();
+    op->build_stem(in_pad.p, cap, ph, pw, w.data.data(), f.scale.data(), f.bias.data(), x0->buf.p, ef, sms);
+    steps.push_back(Step{0, ST_STEM, op, nullptr, x0});
+    stem_flops = op->flops();
+  }
+  // ---- maxpool 3x3/s2/p1 (:199) ----
+  Act* p0 = new_act(cap, (x0->H - 1) / 2 + 1, (x0->W - 1) / 2 + 1, 64);
+  steps.push_back(Step{1, ST_MAXPOOL, nullptr, x0, p0});
+
+  auto add_conv = [&](const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w, const Folded* f,
+                      const Act* res, Act* out, const float* hw = nullptr, const float* hb = nullptr, float* hout = nullptr) {
+    ConvOp* op = new_op();
+    op->build(parts, spec, w, f ? f->scale.data() : nullptr, f ? f->bias.data() : nullptr, res ? res->buf.p : nullptr,
+              out ? out->buf.p : nullptr, hw, hb, hout, ef, sms);
+    steps.push_back(Step{0, ST_CONV, op, nullptr, out});
+    conv_flops += op->flops();
+  };
+
+  // ---- layer1..layer4, BasicBlock (resnets_shift.py:49-65) ----
+  Act* cur = p0;
+  int cin = 64;
+  std::vector<Act*> stage_out;
+  for (int li = 1; li <= 4; ++li) {
+    const int cout = 64 << (li - 1);
+    for (int b = 0; b < 2; ++b) {
+      const int stride = (li > 1 && b == 0) ? 2 : 1;
+      const std::string q = tp + "layer" + std::to_string(li) + "." + std::to_string(b);
+      const int bc_in = (b == 0) ? cin : cout;
+      const int OH = (cur->H + 2 - 3) / stride + 1, OW = (cur->W + 2 - 3) / stride + 1;
+      Act* t = new_act(cap, OH, OW, cout);
+      {
+        const HostTensor& w = conv_weight(c, q + ".conv1.weight", cout, bc_in, 3);
+        const Folded f = fold_bn(c, q + ".bn1", cout);
+        ConvSpec sp; sp.ksize = 3; sp.stride = stride; sp.pad = 1; sp.cout = cout; sp.relu = true;
+        add_conv({ConvInputPart{cur->view(), false}}, sp, w.data.data(), &f, nullptr, t);
+      }
+      Act* res = cur;
+      if (has_weight(c, q + ".downsample.0.weight")) {
+        const HostTensor& w = conv_weight(c, q + ".downsample.0.weight", cout, bc_in, 1);
+        const Folded f = fold_bn(c, q + ".downsample.1", cout);
+        Act* d = new_act(cap, OH, OW, cout);
+        ConvSpec sp; sp.ksize = 1; sp.stride = stride; sp.pad = 0; sp.cout = cout; sp.relu = false;
+        add_conv({ConvInputPart{cur->view(), false}}, sp, w.data.data(), &f, nullptr, d);
+        res = d;
+      } else {
+        WSI_REQUIRE(stride == 1 && bc_in == cout, WSI_ERR_NOMODEL, "block %s needs a downsample projection", q.c_str());
+      }
+      Act* out = new_act(cap, OH, OW, cout);
+      {
+        const HostTensor& w = conv_weight(c, q + ".conv2.weight", cout, cout, 3);
+        const Folded f = fold_bn(c, q + ".bn2", cout);
+        ConvSpec sp; sp.ksize = 3; sp.stride = 1; sp.pad = 1; sp.cout = cout; sp.relu = true;
+        add_conv({ConvInputPart{t->view(), false}}, sp, w.data.data(), &f, res, out);
+      }
+      cur = out;
+    }
+    cin = cout;
+    stage_out.push_back(cur);
+  }
+  x4 = stage_out[3];
+  feats = {stage_out[3], stage_out[2], stage_out[1], stage_out[0], x0};
+
+  auto upload_f = [&](DevBuf& b, const HostTensor& t) { upload(b, t.data); };
+
+  if (head == WSI_HEAD_SEG) {
+    // ---- smp Unet decoder: 5 x {nearest x2, concat skip, 2 x (conv3x3 + BN + ReLU)}, final 1x1 (+bias) ----
+    const int outs[5] = {256, 128, 64, 32, 16};
+    Act* x = x4;
+    logits.alloc((size_t)cap * ph * pw * 4 * sizeof(float));
+    for (int i = 1; i <= 5; ++i) {
+      Act* skip = (i <= 4) ? feats[i] : nullptr;
+      const int co = outs[i - 1];
+      const int ci = x->C + (skip ? skip->C : 0);
+      const std::string q = "decoder.layer" + std::to_string(i) + ".block.";
+      if (skip) WSI_REQUIRE(skip->H == 2 * x->H && skip->W == 2 * x->W, WSI_ERR_UNSUPPORTED, "decoder level %d: skip shape mismatch", i);
+      Act* a = new_act(cap, 2 * x->H, 2 * x->W, co);
+      {
+        const HostTensor& w = conv_weight(c, q + "0.block.0.weight", co, ci, 3);
+        const Folded f = fold_bn(c, q + "0.block.1", co);
+        ConvSpec sp; sp.ksize = 3; sp.stride = 1; sp.pad = 1; sp.cout = co; sp.relu = true;
+        std::vector<ConvInputPart> parts{ConvInputPart{x->view(), true}};
+        if (skip) parts.push_back(ConvInputPart{skip->view(), false});
+        add_conv(parts, sp, w.data.data(), &f, nullptr, a);
+      }
+      const HostTensor& w = conv_weight(c, q + "1.block.0.weight", co, co, 3);
+      const Folded f = fold_bn(c, q + "1.block.1", co);
+      ConvSpec sp; sp.ksize = 3; sp.stride = 1; sp.pad = 1; sp.cout = co; sp.relu = true;
+      if (i < 5) {
+        Act* b = new_act(cap, a->H, a->W, co);
+        add_conv({ConvInputPart{a->view(), false}}, sp, w.data.data(), &f, nullptr, b);
+        x = b;
+      } else {
+        const HostTensor& fw = conv_weight(c, "decoder.final_conv.weight", 4, 16, 1);
+        const HostTensor& fb = weight(c, "decoder.final_conv.bias");
+        WSI_REQUIRE(fb.numel() == 4, WSI_ERR_NOMODEL, "decoder.final_conv.bias must have 4 entries");
+        sp.head = true;
+        add_conv({ConvInputPart{a->view(), false}}, sp, w.data.data(), &f, nullptr, nullptr, fw.data.data(), fb.data.data(),
+                 logits.as<float>());
+      }
+    }
+    out_dim = 4;
+  } else {
+    std::string w1n, b1n, w2n, b2n;
+    if (head == WSI_HEAD_CLS) {
+      if (arch == WSI_ARCH_RESNET18) { w1n = "fc0.weight"; b1n = "fc0.bias"; }                 // resnets_shift.py:140,208
+      else { w1n = "classifier.fc.0.weight"; b1n = "classifier.fc.0.bias"; }                   // models/models.py:27,36
+    } else if (head == WSI_HEAD_REG) {
+      WSI_REQUIRE(arch == WSI_ARCH_UNET_R18, WSI_ERR_UNSUPPORTED, "REG head needs the U-Net model (Regressor, models/models.py:41-58)");
+      w1n = "regressor.fc.0.weight"; b1n = "regressor.fc.0.bias"; w2n = "regressor.fc.2.weight"; b2n = "regressor.fc.2.bias";
+    } else {
+      WSI_REQUIRE(head == WSI_HEAD_FEATURES, WSI_ERR_INVALID, "unknown head %d", head);
+    }
+    if (!w1n.empty()) {
+      const HostTensor &w1 = weight(c, w1n), &b1 = weight(c, b1n);
+      WSI_REQUIRE(w1.shape.size() == 2 && w1.shape[1] == 512 && b1.numel() == w1.shape[0], WSI_ERR_NOMODEL, "head '%s' must be [n,512]", w1n.c_str());
+      n1 = (int)w1.shape[0];
+      upload_f(hw1, w1); upload_f(hb1, b1);
+      out_dim = n1;
+      if (!w2n.empty()) {
+        const HostTensor &w2 = weight(c, w2n), &b2 = weight(c, b2n);
+        WSI_REQUIRE(w2.shape.size() == 2 && w2.shape[1] == n1 && b2.numel() == w2.shape[0], WSI_ERR_NOMODEL, "head '%s' must be [n,%d]", w2n.c_str(), n1);
+        n2 = (int)w2.shape[0];
+        upload_f(hw2, w2); upload_f(hb2, b2);
+        out_dim = n2;
+      }
+    } else {
+      out_dim = 512;
+    }
+    logits.alloc((size_t)cap * out_dim * sizeof(float));
+    steps.push_back(Step{2, ST_HEAD, nullptr, x4, nullptr});
+  }
+  CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
+  size_t i = 0;
+  while (i < steps.size()) {
+    const int stage = steps[i].stage;
+    double work = 0;
+    size_t j = i;
+    while (j < steps.size() && steps[j].stage == stage) {
+      if (steps[j].kind == 0) work += steps[j].op->flops();
+      else if (steps[j].kind == 1) work += (double)steps[j].in->bytes() + (double)steps[j].out->bytes();
+      else work += (double)steps[j].in->bytes();
+      ++j;
+    }
+    StageScope scope(c, s, stage, work);
+    for (; i < j; ++i) {
+      const Step& st = steps[i];
+      if (st.kind == 0) {
+        st.op->launch(s, &c->lc);
+      } else if (st.kind == 1) {
+        launch_maxpool(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
+      } else {
+        const bool feat = (head == WSI_HEAD_FEATURES);
+        launch_pool_head(x4->buf.as<bf16>(), cap, x4->H * x4->W, x4->C, hw1.as<float>(), hb1.as<float>(), n1, hw2.as<float>(),
+                         hb2.as<float>(), n2, feat ? logits.as<float>() : nullptr, logits.as<float>(), s, &c->lc);
+      }
+    }
+  }
+}
+
+namespace wsi {
+
+static NetPlan* get_plan(wsi_ctx* c, int head, int n, int ph, int pw) {
+  WSI_REQUIRE(c->arch >= 0, WSI_ERR_NOMODEL, "wsi_model_load has not been called");
+  NetPlan* p = c->plan.get();
+  if (p && p->arch == c->arch && p->head == head && p->ph == ph && p->pw == pw && p->cap >= n && p->cap <= std::max(2 * n, 8)) return p;
+  c->plan.reset();
+  c->plan.reset(new NetPlan());
+  c->plan->build(c, c->arch, head, n, ph, pw);
+  return c->plan.get();
+}
+
+static void check_device_flag(wsi_ctx* c, cudaStream_t s) {
+  int flag = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  WSI_REQUIRE(flag == 0, WSI_ERR_CUDA, "conv kernel pipeline barrier timed out (code %d)", flag);
+}
+
+static int64_t auto_batch(const wsi_ctx* c, int ph, int pw, int64_t T) {
+  int64_t b = c->batch_tiles;
+  if (b <= 0) {
+    // ~8 Mpx of tile area per batch: enough output tiles to fill 148 SMs in the deepest layers while
+    // the working set of the high-resolution layers stays near the 126 MB L2
+    b = std::max<int64_t>(1, (8LL << 20) / ((int64_t)ph * pw));
+    b = std::min<int64_t>(b, 1024);
+  }
+  return std::max<int64_t>(1, std::min<int64_t>(b, T));
+}
+
+struct SlideGeom {
+  int64_t dx, dy;
+};
+
+static void validate_slide(const wsi_slide_desc* sl) {
+  WSI_REQUIRE(sl && sl->rgb, WSI_ERR_INVALID, "slide raster is NULL");
+  WSI_REQUIRE(sl->ih > 0 && sl->iw > 0 && sl->ph > 0 && sl->pw > 0, WSI_ERR_INVALID, "bad slide geometry");
+  WSI_REQUIRE(sl->row_stride >= 3 * sl->iw, WSI_ERR_INVALID, "row_stride %lld < 3*iw", (long long)sl->row_stride);
+  WSI_REQUIRE(sl->row0 >= 0 && sl->rows >= 0 && sl->row0 + sl->rows <= sl->ih, WSI_ERR_INVALID, "raster rows [%lld,+%lld) outside the slide",
+              (long long)sl->row0, (long long)sl->rows);
+}
+
+// raster (band) resident on the device; returns the device pointer and stride
+static const uint8_t* stage_raster(wsi_ctx* c, const wsi_slide_desc* sl, int64_t rows, int64_t* stride_out, cudaStream_t s) {
+  if (sl->rgb_mem == WSI_MEM_DEVICE) {
+    *stride_out = sl->row_stride;
+    return sl->rgb;
+  }
+  const int64_t tight = 3 * sl->iw;
+  StageScope scope(c, s, ST_H2D, (double)rows * tight);
+  c->raster.alloc((size_t)rows * tight);
+  if (rows > 0)
+    CUDA_CHECK(cudaMemcpy2DAsync(c->raster.p, tight, sl->rgb, sl->row_stride, tight, rows, cudaMemcpyHostToDevice, s));
+  *stride_out = tight;
+  return c->raster.as<uint8_t>();
+}
+
+static void check_tiles(const wsi_slide_desc* sl, const int32_t* xy, int64_t n, int64_t rows) {
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t x = xy[2 * i], y = xy[2 * i + 1];
+    WSI_REQUIRE(x >= 0 && x + sl->pw <= sl->iw, WSI_ERR_INVALID, "tile %lld: x=%lld leaves the raster", (long long)i, (long long)x);
+    WSI_REQUIRE(y >= sl->row0 && y + sl->ph <= sl->row0 + rows, WSI_ERR_INVALID, "tile %lld: y=%lld outside raster rows [%lld,%lld)",
+                (long long)i, (long long)y, (long long)sl->row0, (long long)(sl->row0 + rows));
+  }
+}
+
+static void ensure_lut(wsi_ctx* c) {
+  if (c->lut.p) return;
+  // ToTensor: u8 -> f32, div 255; Normalize: sub mean, div std (utils/preprocessing.py:209-212,
+  // myargs.py:127-130), evaluated in fp32 in that order — 256 possible values per channel.
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  std::vector<float> t(768);
+  for (int ch = 0; ch < 3; ++ch)
+    for (int v = 0; v < 256; ++v) {
+      volatile float a = (float)v / 255.0f;
+      volatile float b = a - mean[ch];
+      volatile float d = b / stdv[ch];
+      t[ch * 256 + v] = d;
+    }
+  upload(c->lut, t);
+  CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+// the hot path ------------------------------------------------------------------------------
+static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles_xy, int64_t T, int head, const wsi_out_desc* out,
+                      cudaStream_t s) {
+  validate_slide(sl);
+  WSI_REQUIRE(out && out->classes && out->heatmap, WSI_ERR_INVALID, "classes and heatmap outputs are required");
+  WSI_REQUIRE(head == WSI_HEAD_SEG || head == WSI_HEAD_CLS, WSI_ERR_INVALID, "wsi_run_slide: head must be SEG or CLS");
+  WSI_REQUIRE(T >= 0 && T < (1LL << 30) && (T == 0 || tiles_xy), WSI_ERR_INVALID, "bad tile list");
+  WSI_REQUIRE(sl->m > 0, WSI_ERR_INVALID, "m must be positive");
+  const int64_t rows_r = (sl->rows == 0 && sl->row0 == 0) ? sl->ih : sl->rows;
+  const int64_t H2 = sl->H2, W2 = sl->W2;
+  WSI_REQUIRE(H2 > 0 && W2 > 0 && W2 < (1LL << 31) && H2 < (1LL << 31), WSI_ERR_INVALID, "bad canvas size");
+  const int64_t own0 = sl->own0, own1 = (sl->own0 == 0 && sl->own1 == 0) ? H2 : sl->own1;
+  WSI_REQUIRE(own0 >= 0 && own1 >= own0 && own1 <= H2, WSI_ERR_INVALID, "bad owned rows");
+  const int64_t orows = own1 - own0, plane = orows * W2;
+  const int ph = sl->ph, pw = sl->pw;
+  const int64_t dx = (int64_t)(sl->m * (double)pw), dy = (int64_t)(sl->m * (double)ph);   // utils/eval.py:186
+  if (head == WSI_HEAD_SEG)
+    WSI_REQUIRE(dx == pw && dy == ph, WSI_ERR_UNSUPPORTED, "SEG needs m == 1 (the reference's slice-add requires equal shapes, utils/eval.py:213-215)");
+  WSI_REQUIRE(dx > 0 && dy > 0, WSI_ERR_DEGENERATE, "tile rectangle is empty on the canvas");
+  check_tiles(sl, tiles_xy, T, rows_r);
+  ensure_lut(c);
+  CUDA_CHECK(cudaMemsetAsync(c->err_flag.p, 0, sizeof(int), s));
+
+  // ---- sort tiles by canvas origin (ty, tx): batches become spatially compact and the stitch
+  //      sums in a fixed order regardless of the order the caller (or a shuffling DataLoader,
+  //      utils/dataset.py:192) presents them in ----
+  std::vector<int32_t> order((size_t)T), tys((size_t)T), txs((size_t)T);
+  for (int64_t i = 0; i < T; ++i) {
+    order[i] = (int32_t)i;
+    txs[i] = (int32_t)(sl->m * (double)tiles_xy[2 * i]);        // int(m * x), utils/eval.py:214
+    tys[i] = (int32_t)(sl->m * (double)tiles_xy[2 * i + 1]);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    if (tys[a] != tys[b]) return tys[a] < tys[b];
+    return txs[a] < txs[b];
+  });
+  std::vector<int32_t> sxy((size_t)2 * T), stx((size_t)T), rowy, rowstart;
+  for (int64_t i = 0; i < T; ++i) {
+    const int32_t o = order[i];
+    sxy[2 * i] = tiles_xy[2 * o];
+    sxy[2 * i + 1] = tiles_xy[2 * o + 1];
+    stx[i] = txs[o];
+    if (i == 0 || tys[o] != rowy.back()) {
+      rowy.push_back(tys[o]);
+      rowstart.push_back((int32_t)i);
+    }
+  }
+  rowstart.push_back((int32_t)T);
+  upload(c->tiles_dev, sxy, s);
+  upload(c->rect_tx, stx, s);
+  upload(c->rect_rowy, rowy, s);
+  upload(c->rect_rowstart, rowstart, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));   // the host vectors above die with this scope
+  RectIndex ri;
+  ri.tx = c->rect_tx.as<int32_t>();
+  ri.row_y = c->rect_rowy.as<int32_t>();
+  ri.row_start = c->rect_rowstart.as<int32_t>();
+  ri.R = (int32_t)rowy.size();
+  ri.dx = (int32_t)dx;
+  ri.dy = (int32_t)dy;
+
+  int64_t rstride = 0;
+  const uint8_t* rgb = stage_raster(c, sl, rows_r, &rstride, s);
+
+  const uint8_t* mask_dev = nullptr;
+  if (sl->mask) {
+    if (sl->mask_mem == WSI_MEM_DEVICE) {
+      mask_dev = sl->mask;
+    } else {
+      StageScope scope(c, s, ST_H2D, (double)plane);
+      c->maskbuf.alloc((size_t)plane);
+      CUDA_CHECK(cudaMemcpyAsync(c->maskbuf.p, sl->mask, (size_t)plane, cudaMemcpyHostToDevice, s));
+      mask_dev = c->maskbuf.as<uint8_t>();
+    }
+  }
+
+  const bool host_out = (out->mem == WSI_MEM_HOST);
+  uint8_t *cls_dev = out->classes, *heat_dev = out->heatmap;
+  float *canvas_out = out->canvas, *probs_out = out->probs;
+  int32_t* counts_out = out->counts;
+  if (host_out) {
+    c->classes.alloc((size_t)plane);
+    c->heatmap.alloc((size_t)plane);
+    cls_dev = c->classes.as<uint8_t>();
+    heat_dev = c->heatmap.as<uint8_t>();
+    const size_t want = ((out->canvas ? 1 : 0) + (out->probs ? 1 : 0)) * (size_t)plane * 4;
+    if (want) c->scratch_f32.alloc(want * sizeof(float));
+    float* p = c->scratch_f32.as<float>();
+    if (out->canvas) { canvas_out = p; p += plane * 4; }
+    if (out->probs) probs_out = p;
+    if (out->counts) { c->counts.alloc((size_t)plane * sizeof(int32_t)); counts_out = c->counts.as<int32_t>(); }
+  }
+
+  FinaliseArgs fa;
+  fa.W2 = W2; fa.own0 = own0; fa.own1 = own1; fa.mask = mask_dev;
+  for (int i = 0; i < 4; ++i) fa.class_probs[i] = c->class_probs[i];
+  fa.heat_mode = (head == WSI_HEAD_CLS) ? 1 : 0;
+  fa.classes = cls_dev; fa.heatmap = heat_dev; fa.canvas_out = canvas_out; fa.probs_out = probs_out;
+
+  const int64_t B = auto_batch(c, ph, pw, std::max<int64_t>(T, 1));
+  NetPlan* plan = (T > 0) ? get_plan(c, head, (int)B, ph, pw) : nullptr;
+  const int cap = plan ? plan->cap : 1;
+  const double tile_px = (double)ph * pw;
+
+  if (head == WSI_HEAD_SEG) {
+    c->canvas.alloc((size_t)plane * sizeof(float4));
+    CUDA_CHECK(cudaMemsetAsync(c->canvas.p, 0, (size_t)plane * sizeof(float4), s));
+  } else {
+    c->tile_logits.alloc((size_t)std::max<int64_t>(T, 1) * 4 * sizeof(float));
+    WSI_REQUIRE(!plan || plan->out_dim == 4, WSI_ERR_UNSUPPORTED, "CLS stitch needs 4 classes (got %d)", plan ? plan->out_dim : 0);
+  }
+
+  for (int64_t t0 = 0; t0 < T; t0 += cap) {
+    const int n = (int)std::min<int64_t>(cap, T - t0);
+    {
+      StageScope scope(c, s, ST_GATHER, 9.0 * n * tile_px);
+      launch_gather(rgb, rstride, sl->row0, c->tiles_dev.as<int32_t>() + 2 * t0, n, ph, pw, c->lut.as<float>(), plan->in_pad.as<bf16>(),
+                    nullptr, s, &c->lc);
+    }
+    plan->run(c, s);
+    if (head == WSI_HEAD_SEG) {
+      // algorithmic bytes: T*P*C*4 logits read + S*C*4 canvas written once
+      StageScope scope(c, s, ST_STITCH, (double)n * tile_px * 16.0 + (t0 == 0 ? (double)plane * 16.0 : 0.0));
+      // one launch per run of tiles sharing a canvas row: box = that row's rectangle union
+      int64_t a = t0;
+      while (a < t0 + n) {
+        const int32_t ty = tys[order[a]];
+        int64_t b = a;
+        int32_t xmin = stx[a], xmax = stx[a];
+        while (b < t0 + n && tys[order[b]] == ty) { xmax = stx[b]; ++b; }
+        launch_stitch_seg_box(c->canvas.as<float4>(), ri, plan->logits.as<float4>(), (int)a, (int)b, (int)t0, W2, own0, own1, ty,
+                              (int)(ty + dy), xmin, (int)(xmax + dx), s, &c->lc);
+        a = b;
+      }
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(c->tile_logits.as<float>() + 4 * t0, plan->logits.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+  }
+
+  {
+    if (head == WSI_HEAD_SEG) {
+      StageScope scope(c, s, ST_FINALISE, (double)plane * 18.0);
+      launch_finalise_seg(c->canvas.as<float4>(), fa, s, &c->lc);
+    } else {
+      StageScope scope(c, s, ST_STITCH, (double)T * 16.0 + (double)plane * 2.0);
+      launch_stitch_finalise_cls(ri, c->tile_logits.as<float4>(), (int)T, fa, s, &c->lc);
+    }
+    if (counts_out) launch_counts(ri, (int)T, W2, own0, own1, counts_out, s, &c->lc);
+  }
+
+  if (host_out) {
+    StageScope scope(c, s, ST_D2H, (double)plane * 2.0);
+    CUDA_CHECK(cudaMemcpyAsync(out->classes, cls_dev, (size_t)plane, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(out->heatmap, heat_dev, (size_t)plane, cudaMemcpyDeviceToHost, s));
+    if (out->canvas) CUDA_CHECK(cudaMemcpyAsync(out->canvas, canvas_out, (size_t)plane * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out->probs) CUDA_CHECK(cudaMemcpyAsync(out->probs, probs_out, (size_t)plane * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (out->counts) CUDA_CHECK(cudaMemcpyAsync(out->counts, counts_out, (size_t)plane * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  if (out->tile_logits) {
+    WSI_REQUIRE(head == WSI_HEAD_CLS, WSI_ERR_UNSUPPORTED, "tile_logits is a CLS-only output");
+    std::vector<float> sorted((size_t)T * 4), orig((size_t)T * 4);
+    CUDA_CHECK(cudaMemcpyAsync(sorted.data(), c->tile_logits.p, (size_t)T * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < T; ++i) memcpy(&orig[(size_t)order[i] * 4], &sorted[(size_t)i * 4], 4 * sizeof(float));
+    CUDA_CHECK(cudaMemcpy(out->tile_logits, orig.data(), (size_t)T * 4 * sizeof(float), host_out ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice));
+  }
+  if (host_out || c->stage_timing) {
+    check_device_flag(c, s);
+    resolve_spans(c);
+  }
+}
+
+// one batch through the network: x f32 NCHW (normalised) or tiles cut from a raster
+static void forward_common(wsi_ctx* c, NetPlan* plan, int n, int head, float* out, int mem, cudaStream_t s) {
+  plan->run(c, s);
+  const int ph = plan->ph, pw = plan->pw;
+  const size_t out_elems = (head == WSI_HEAD_SEG) ? (size_t)n * 4 * ph * pw : (size_t)n * plan->out_dim;
+  float* dst = out;
+  if (mem == WSI_MEM_HOST) {
+    c->scratch_f32.alloc(out_elems * sizeof(float));
+    dst = c->scratch_f32.as<float>();
+  }
+  if (head == WSI_HEAD_SEG) {
+    StageScope scope(c, s, ST_HEAD, (double)out_elems * 8.0);
+    launch_nhwc4_to_nchw(plan->logits.as<float>(), n, ph, pw, dst, s, &c->lc);
+  } else {
+    CUDA_CHECK(cudaMemcpyAsync(dst, plan->logits.p, out_elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  if (mem == WSI_MEM_HOST) CUDA_CHECK(cudaMemcpyAsync(out, dst, out_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+  check_device_flag(c, s);
+  resolve_spans(c);
+}
+
+}  // namespace wsi
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+#define WSI_API_BEGIN try {
+#define WSI_API_END(ctxp)                                  \
+  }                                                        \
+  catch (const ::wsi::Error& e) {                          \
+    if (ctxp) (ctxp)->err = e.msg;                         \
+    ::wsi::set_global_error(e.msg);                        \
+    return e.status;                                       \
+  }                                                        \
+  catch (const std::bad_alloc&) {                          \
+    ::wsi::set_global_error("out of host memory");         \
+    return WSI_ERR_NOMEM;                                  \
+  }                                                        \
+  catch (const std::exception& e) {                        \
+    if (ctxp) (ctxp)->err = e.what();                      \
+    ::wsi::set_global_error(e.what());                     \
+    return WSI_ERR_INVALID;                                \
+  }                                                        \
+  return WSI_OK;
+
+extern "C" {
+
+const char* wsi_version(void) { return "wsi_b200 0.1 (sm_100a)"; }
+
+int wsi_ctx_create(int device, wsi_ctx** out) {
+  wsi_ctx* c = nullptr;
+  WSI_API_BEGIN
+  WSI_REQUIRE(out, WSI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  WSI_REQUIRE(e == cudaSuccess && ndev > 0, WSI_ERR_CUDA, "no CUDA device (%s); libwsi_b200 has no CPU fallback", cudaGetErrorString(e));
+  WSI_REQUIRE(device >= 0 && device < ndev, WSI_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  WSI_REQUIRE(prop.major == 10, WSI_ERR_CUDA, "device %d is sm_%d%d; libwsi_b200 is built for sm_100a only", device, prop.major, prop.minor);
+  std::unique_ptr<wsi_ctx> ctx(new wsi_ctx());
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->err_flag.alloc(sizeof(int));
+  CUDA_CHECK(cudaMemset(ctx->err_flag.p, 0, sizeof(int)));
+  init_tensor_map_api();
+  *out = ctx.release();
+  WSI_API_END(c)
+}
+
+int wsi_ctx_destroy(wsi_ctx* ctx) {
+  if (!ctx) return WSI_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  delete ctx;
+  return WSI_OK;
+}
+
+const char* wsi_last_error(wsi_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && key, WSI_ERR_INVALID, "NULL argument");
+  const std::string k(key);
+  if (k == "batch_tiles") { WSI_REQUIRE(value >= 0 && value <= 4096, WSI_ERR_INVALID, "batch_tiles out of range"); ctx->batch_tiles = value; }
+  else if (k == "stage_timing") ctx->stage_timing = value ? 1 : 0;
+  else WSI_THROW(WSI_ERR_INVALID, "unknown option '%s'", key);
+  WSI_API_END(ctx)
+}
+
+int wsi_set_class_probs(wsi_ctx* ctx, const float* p, int n) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && p && n == 4, WSI_ERR_INVALID, "class_probs must have 4 entries");
+  for (int i = 0; i < 4; ++i) ctx->class_probs[i] = p[i];
+  WSI_API_END(ctx)
+}
+
+int64_t wsi_kernel_launches(wsi_ctx* ctx) { return ctx ? ctx->lc.n : 0; }
+
+int wsi_model_load(wsi_ctx* ctx, int arch, const wsi_tensor_desc* tensors, int n, int num_classes) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && tensors && n > 0, WSI_ERR_INVALID, "NULL argument");
+  WSI_REQUIRE(arch == WSI_ARCH_RESNET18 || arch == WSI_ARCH_UNET_R18, WSI_ERR_INVALID, "unknown arch %d", arch);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->plan.reset();
+  ctx->sd.clear();
+  ctx->arch = -1;
+  for (int i = 0; i < n; ++i) {
+    const wsi_tensor_desc& t = tensors[i];
+    WSI_REQUIRE(t.name && t.data && t.ndim >= 0 && t.ndim <= 4, WSI_ERR_INVALID, "tensor %d is malformed", i);
+    HostTensor h;
+    int64_t numel = 1;
+    for (int d = 0; d < t.ndim; ++d) { WSI_REQUIRE(t.shape[d] >= 0, WSI_ERR_INVALID, "tensor '%s': negative dim", t.name); h.shape.push_back(t.shape[d]); numel *= t.shape[d]; }
+    h.data.assign(t.data, t.data + numel);
+    ctx->sd[t.name] = std::move(h);
+  }
+  ctx->num_classes = num_classes;
+  ctx->arch = arch;
+  // fail early on an incomplete trunk
+  (void)weight(ctx, (arch == WSI_ARCH_UNET_R18 ? std::string("encoder.") : std::string("")) + "conv1.weight");
+  WSI_API_END(ctx)
+}
+
+int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles, int head,
+                  const wsi_out_desc* out, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx, WSI_ERR_INVALID, "ctx is NULL");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  run_slide(ctx, slide, tiles_xy, n_tiles, head, out, (cudaStream_t)stream);
+  WSI_API_END(ctx)
+}
+
+int wsi_forward_batch(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_t w, int head, float* out, int mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && x && out && n > 0 && n < (1 << 20), WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  NetPlan* plan = get_plan(ctx, head, (int)n, h, w);
+  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
+  const float* xd = x;
+  const size_t in_bytes = (size_t)n * 3 * h * w * sizeof(float);
+  DevBuf tmp;
+  if (mem == WSI_MEM_HOST) {
+    tmp.alloc(in_bytes);
+    CUDA_CHECK(cudaMemcpyAsync(tmp.p, x, in_bytes, cudaMemcpyHostToDevice, s));
+    xd = tmp.as<float>();
+  }
+  {
+    StageScope scope(ctx, s, ST_GATHER, (double)n * h * w * 18.0);
+    launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc);
+  }
+  forward_common(ctx, plan, (int)n, head, out, mem, s);
+  WSI_API_END(ctx)
+}
+
+int wsi_forward_tiles(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles, int head, float* out,
+                      int mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && out && tiles_xy && n_tiles > 0 && n_tiles < (1 << 20), WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  validate_slide(slide);
+  const int64_t rows_r = (slide->rows == 0 && slide->row0 == 0) ? slide->ih : slide->rows;
+  check_tiles(slide, tiles_xy, n_tiles, rows_r);
+  ensure_lut(ctx);
+  NetPlan* plan = get_plan(ctx, head, (int)n_tiles, slide->ph, slide->pw);
+  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
+  int64_t rstride = 0;
+  const uint8_t* rgb = stage_raster(ctx, slide, rows_r, &rstride, s);
+  std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * n_tiles);
+  upload(ctx->tiles_dev, xy, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  {
+    StageScope scope(ctx, s, ST_GATHER, 9.0 * n_tiles * slide->ph * slide->pw);
+    launch_gather(rgb, rstride, slide->row0, ctx->tiles_dev.as<int32_t>(), (int)n_tiles, slide->ph, slide->pw, ctx->lut.as<float>(),
+                  plan->in_pad.as<bf16>(), nullptr, s, &ctx->lc);
+  }
+  forward_common(ctx, plan, (int)n_tiles, head, out, mem, s);
+  WSI_API_END(ctx)
+}
+
+int wsi_synth_slide(wsi_ctx* ctx, int64_t ih, int64_t iw, uint32_t seed, int64_t y0, int64_t y1, const uint8_t* lut, uint8_t* rgb_dev,
+                    int64_t row_stride, uint8_t* mask_dev_or_null, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && lut && rgb_dev && y0 >= 0 && y1 >= y0 && y1 <= ih && iw > 0 && row_stride >= 3 * iw, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf l;
+  l.alloc(16 * 8 * 3);
+  CUDA_CHECK(cudaMemcpyAsync(l.p, lut, 16 * 8 * 3, cudaMemcpyHostToDevice, s));
+  launch_synth(ih, iw, seed, y0, y1, l.as<uint8_t>(), rgb_dev, row_stride, mask_dev_or_null, s, &ctx->lc);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  WSI_API_END(ctx)
+}
+
+int wsi_debug_conv(wsi_ctx* ctx, const void* x, int n, int h, int w, int cin, const float* wt, int cout, int ksize, int stride, int pad,
+                   const float* scale, const float* bias, const void* res, int relu, int up2, const void* skip, int cskip, void* y,
+                   void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && x && wt && y, WSI_ERR_INVALID, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
+  std::vector<ConvInputPart> parts;
+  parts.push_back(ConvInputPart{TensorView{x, n, h, w, cin}, up2 != 0});
+  if (skip) parts.push_back(ConvInputPart{TensorView{skip, n, up2 ? 2 * h : h, up2 ? 2 * w : w, cskip}, false});
+  ConvSpec sp;
+  sp.ksize = ksize; sp.stride = stride; sp.pad = pad; sp.cout = cout; sp.relu = relu != 0;
+  ConvOp op;
+  op.build(parts, sp, wt, scale, bias, res, y, nullptr, nullptr, nullptr, ctx->err_flag.as<int>(), ctx->num_sms);
+  op.launch(s, &ctx->lc);
+  check_device_flag(ctx, s);
+  WSI_API_END(ctx)
+}
+
+int wsi_debug_gather(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int n, float* norm_out, void* padded_out,
+                     void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && tiles_xy && n > 0, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  validate_slide(slide);
+  const int64_t rows_r = (slide->rows == 0 && slide->row0 == 0) ? slide->ih : slide->rows;
+  check_tiles(slide, tiles_xy, n, rows_r);
+  ensure_lut(ctx);
+  int64_t rstride = 0;
+  const uint8_t* rgb = stage_raster(ctx, slide, rows_r, &rstride, s);
+  std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * (size_t)n);
+  upload(ctx->tiles_dev, xy, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (padded_out) CUDA_CHECK(cudaMemsetAsync(padded_out, 0, (size_t)n * (slide->ph + 6) * (slide->pw + 8) * 8, s));
+  launch_gather(rgb, rstride, slide->row0, ctx->tiles_dev.as<int32_t>(), n, slide->ph, slide->pw, ctx->lut.as<float>(),
+                static_cast<bf16*>(padded_out), norm_out, s, &ctx->lc);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  WSI_API_END(ctx)
+}
+
+int wsi_debug_stem(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int n, const float* wt, const float* scale,
+                   const float* bias, void* y, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && tiles_xy && n > 0 && wt && y, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  validate_slide(slide);
+  const int64_t rows_r = (slide->rows == 0 && slide->row0 == 0) ? slide->ih : slide->rows;
+  check_tiles(slide, tiles_xy, n, rows_r);
+  ensure_lut(ctx);
+  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
+  int64_t rstride = 0;
+  const uint8_t* rgb = stage_raster(ctx, slide, rows_r, &rstride, s);
+  std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * (size_t)n);
+  upload(ctx->tiles_dev, xy, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  DevBuf pad;
+  pad.alloc((size_t)n * (slide->ph + 6) * (slide->pw + 8) * 8);
+  CUDA_CHECK(cudaMemsetAsync(pad.p, 0, pad.bytes, s));
+  launch_gather(rgb, rstride, slide->row0, ctx->tiles_dev.as<int32_t>(), n, slide->ph, slide->pw, ctx->lut.as<float>(), pad.as<bf16>(),
+                nullptr, s, &ctx->lc);
+  ConvOp op;
+  op.build_stem(pad.p, n, slide->ph, slide->pw, wt, scale, bias, y, ctx->err_flag.as<int>(), ctx->num_sms);
+  op.launch(s, &ctx->lc);
+  check_device_flag(ctx, s);
+  WSI_API_END(ctx)
+}
+
+int wsi_debug_maxpool(wsi_ctx* ctx, const void* x, int n, int h, int w, int c, void* y, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && x && y && c % 8 == 0, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  launch_maxpool(static_cast<const bf16*>(x), n, h, w, c, static_cast<bf16*>(y), (cudaStream_t)stream, &ctx->lc);
+  CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  WSI_API_END(ctx)
+}
+
+int wsi_stage_stats(wsi_ctx* ctx, const char* stage, double* ms_out, int64_t* launches_out, double* work_out) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && stage, WSI_ERR_INVALID, "NULL argument");
+  for (int i = 0; i < ST_COUNT; ++i)
+    if (strcmp(stage, kStageNames[i]) == 0) {
+      if (ms_out) *ms_out = ctx->acc[i].ms;
+      if (launches_out) *launches_out = ctx->acc[i].launches;
+      if (work_out) *work_out = ctx->acc[i].work;
+      return WSI_OK;
+    }
+  WSI_THROW(WSI_ERR_INVALID, "unknown stage '%s'", stage);
+  WSI_API_END(ctx)
+}
+
+int wsi_stage_reset(wsi_ctx* ctx) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx, WSI_ERR_INVALID, "ctx is NULL");
+  resolve_spans(ctx);
+  for (int i = 0; i < ST_COUNT; ++i) ctx->acc[i] = StageAcc();
+  WSI_API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,477 @@
+// kernels.cu — HBM-bound stages (see kernels.cuh).  Reference lines cited per kernel.
+#include "kernels.cuh"
+
+#include <algorithm>
+
+namespace wsi {
+
+// =============================================================================================
+// K0: fused tile gather + normalise + bf16 cast
+//   reference: read_region(...).convert('RGB') (utils/dataset.py:175-178), ToTensor + Normalize
+//   (utils/preprocessing.py:209-212), collate + .cuda() (utils/eval.py:192).
+//   ((u8/255) - mean_c)/std_c has only 256 values per channel: the host builds the table with the
+//   reference's exact fp32 op order and rounds it to bf16 once, so the kernel is a byte gather.
+//   Output is the stem's operand layout: [n][ph+6][pw+8][4] bf16, zero border (3 top/left), ch 3 = 0.
+// =============================================================================================
+__global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t row0,
+                                                      const int32_t* __restrict__ tiles_xy, int ph, int pw,
+                                                      const float* __restrict__ lut, bf16* __restrict__ padded,
+                                                      float* __restrict__ norm_out) {
+  // s_lut: the 3x256 possible outputs of Normalize(ToTensor(u8)) in fp32 (host-built, reference op order)
+  __shared__ float s_f32[768];
+  __shared__ uint16_t s_lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const float v = lut[i];
+    s_f32[i] = v;
+    s_lut[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
+  __syncthreads();
+  const int t = blockIdx.x / ph, r = blockIdx.x % ph;
+  const int x0 = tiles_xy[2 * t], y0 = tiles_xy[2 * t + 1];
+  const uint8_t* src = rgb + (int64_t)(y0 + r - row0) * row_stride + (int64_t)x0 * 3;
+  const int64_t pitch = (int64_t)(pw + 8) * 4;
+  bf16* dst = padded + ((int64_t)t * (ph + 6) + (r + 3)) * pitch + 3 * 4;
+  for (int x = threadIdx.x; x < pw; x += blockDim.x) {
+    const uint8_t c0 = __ldg(src + 3 * x), c1 = __ldg(src + 3 * x + 1), c2 = __ldg(src + 3 * x + 2);
+    const uint16_t v0 = s_lut[c0], v1 = s_lut[256 + c1], v2 = s_lut[512 + c2];
+    if (padded) {
+      uint2 o;
+      o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
+      o.y = (uint32_t)v2;
+      *reinterpret_cast<uint2*>(dst + 4 * x) = o;
+    }
+    if (norm_out) {
+      const int64_t plane = (int64_t)ph * pw;
+      float* q = norm_out + (int64_t)t * 3 * plane + (int64_t)r * pw + x;
+      q[0] = s_f32[c0];
+      q[plane] = s_f32[256 + c1];
+      q[2 * plane] = s_f32[512 + c2];
+    }
+  }
+}
+
+void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n, int ph,
+                   int pw, const float* lut_dev, bf16* padded, float* norm_out, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return;
+  gather_kernel<<<(unsigned)((int64_t)n * ph), 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, ph, pw, lut_dev, padded, norm_out);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ x, int h, int w, bf16* __restrict__ padded) {
+  const int t = blockIdx.x / h, r = blockIdx.x % h;
+  const int64_t plane = (int64_t)h * w;
+  const float* src = x + (int64_t)t * 3 * plane + (int64_t)r * w;
+  const int64_t pitch = (int64_t)(w + 8) * 4;
+  bf16* dst = padded + ((int64_t)t * (h + 6) + (r + 3)) * pitch + 3 * 4;
+  for (int c = threadIdx.x; c < w; c += blockDim.x) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(src[c], src[plane + c]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(src[2 * plane + c], 0.f);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + 4 * c) = o;
+  }
+}
+
+void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return;
+  pack_nchw_kernel<<<(unsigned)((int64_t)n * h), 256, 0, s>>>(x, h, w, padded);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// =============================================================================================
+// max pool 3x3 / s2 / p1 (resnets_shift.py:126), NHWC bf16; one thread = 8 channels of one output px
+// =============================================================================================
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__global__ void __launch_bounds__(256) maxpool_kernel(const bf16* __restrict__ x, int n, int h, int w, int c,
+                                                       bf16* __restrict__ y) {
+  const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1, cg = c / 8;
+  const int64_t total = (int64_t)n * oh * ow * cg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    int64_t r = i / cg;
+    const int ox = (int)(r % ow); r /= ow;
+    const int oy = (int)(r % oh);
+    const int b = (int)(r / oh);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int iy = 2 * oy + dy;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ix = 2 * ox + dx;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)b * h + iy) * w + ix) * c + g * 8));
+        const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          m[2 * t] = fmaxf(m[2 * t], bf_lo(ww[t]));
+          m[2 * t + 1] = fmaxf(m[2 * t + 1], bf_hi(ww[t]));
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(m[2 * t], m[2 * t + 1]);
+      o[t] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(y + (((int64_t)b * oh + oy) * ow + ox) * c + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+void launch_maxpool(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t total = (int64_t)n * ((h - 1) / 2 + 1) * ((w - 1) / 2 + 1) * (c / 8);
+  if (total <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+  maxpool_kernel<<<grid, 256, 0, s>>>(x, n, h, w, c, y);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// =============================================================================================
+// global average pool + head MLP (models/models.py:32-38, :52-58; resnets_shift.py:206-208)
+// one block (512 threads) per tile
+// =============================================================================================
+__global__ void __launch_bounds__(512) pool_head_kernel(const bf16* __restrict__ x4, int hw, int c,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1, int n1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2, int n2,
+                                                         float* __restrict__ feat_out, float* __restrict__ out) {
+  __shared__ float s_feat[512];
+  __shared__ float s_hid[512];
+  const int t = blockIdx.x;
+  const bf16* src = x4 + (int64_t)t * hw * c;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < hw; ++i) s += __bfloat162float(src[(int64_t)i * c + ch]);
+    s = s / (float)hw;
+    s_feat[ch] = s;
+    if (feat_out) feat_out[(int64_t)t * c + ch] = s;
+  }
+  __syncthreads();
+  if (n1 <= 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int j = warp; j < n1; j += nwarp) {
+    float s = 0.f;
+    for (int ch = lane; ch < c; ch += 32) s = fmaf(s_feat[ch], __ldg(w1 + (int64_t)j * c + ch), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s += b1[j];
+      if (n2 > 0) s_hid[j] = fmaxf(s, 0.f);
+      else out[(int64_t)t * n1 + j] = s;
+    }
+  }
+  if (n2 <= 0) return;
+  __syncthreads();
+  for (int j = warp; j < n2; j += nwarp) {
+    float s = 0.f;
+    for (int ch = lane; ch < n1; ch += 32) s = fmaf(s_hid[ch], __ldg(w2 + (int64_t)j * n1 + ch), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[(int64_t)t * n2 + j] = s + b2[j];
+  }
+}
+
+void launch_pool_head(const bf16* x4, int n, int hw, int c, const float* w1, const float* b1, int n1, const float* w2,
+                      const float* b2, int n2, float* feat_out, float* out, cudaStream_t s, LaunchCounter* lc) {
+  WSI_REQUIRE(c <= 512 && n1 <= 512, WSI_ERR_UNSUPPORTED, "pool_head: c=%d n1=%d", c, n1);
+  if (n <= 0) return;
+  pool_head_kernel<<<n, 512, 0, s>>>(x4, hw, c, w1, b1, n1, w2, b2, n2, feat_out, out);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+__global__ void __launch_bounds__(256) nhwc4_to_nchw_kernel(const float4* __restrict__ x, int64_t plane, int64_t total, float* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / plane, r = i % plane;
+    const float4 v = x[i];
+    float* o = y + b * 4 * plane + r;
+    o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
+  }
+}
+void launch_nhwc4_to_nchw(const float* x, int n, int h, int w, float* y, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t plane = (int64_t)h * w, total = plane * n;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+  nhwc4_to_nchw_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(x), plane, total, y);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// =============================================================================================
+// rect lookup shared by the stitch kernels: visit every sorted rect in [t0, t1) covering (X, Y)
+// in a fixed (row, x) order -> deterministic sums, no atomics (each pixel has one owner thread).
+// =============================================================================================
+template <class F>
+__device__ __forceinline__ void for_each_cover(const RectIndex& ri, int t0, int t1, int X, int Y, F&& f) {
+  // rows with row_y in (Y - dy, Y]
+  int lo = 0, hi = ri.R;
+  while (lo < hi) {  // first row with row_y > Y - dy
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(ri.row_y + mid) > Y - ri.dy) hi = mid; else lo = mid + 1;
+  }
+  for (int r = lo; r < ri.R; ++r) {
+    const int ry = __ldg(ri.row_y + r);
+    if (ry > Y) break;
+    int a = max(__ldg(ri.row_start + r), t0), b = min(__ldg(ri.row_start + r + 1), t1);
+    if (a >= b) continue;
+    int l2 = a, h2 = b;
+    while (l2 < h2) {  // first rect with tx > X - dx
+      const int mid = (l2 + h2) >> 1;
+      if (__ldg(ri.tx + mid) > X - ri.dx) h2 = mid; else l2 = mid + 1;
+    }
+    for (int i = l2; i < b; ++i) {
+      const int tx = __ldg(ri.tx + i);
+      if (tx > X) break;
+      f(i, X - tx, Y - ry);
+    }
+  }
+}
+
+// =============================================================================================
+// K6 (seg): overlap-accumulate, reference pred[:, ty:ty+dy, tx:tx+dx] += pred_src[bj]
+// (utils/eval.py:213-215), gather formulation.
+// =============================================================================================
+__global__ void __launch_bounds__(256) stitch_seg_kernel(float4* __restrict__ canvas, RectIndex ri, const float4* __restrict__ logits,
+                                                          int t0, int t1, int logit_base, int64_t W2, int64_t own0, int y_lo, int x_lo, int x_hi) {
+  const int Y = y_lo + blockIdx.y;
+  const int X = x_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (X >= x_hi) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool any = false;
+  const int64_t plane = (int64_t)ri.dx * ri.dy;
+  for_each_cover(ri, t0, t1, X, Y, [&](int i, int ox, int oy) {
+    const float4 v = __ldg(logits + (int64_t)(i - logit_base) * plane + (int64_t)oy * ri.dx + ox);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    any = true;
+  });
+  if (any) {
+    float4* c = canvas + (int64_t)(Y - own0) * W2 + X;
+    float4 o = *c;
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    *c = o;
+  }
+}
+
+void launch_stitch_seg_box(float4* canvas, const RectIndex& ri, const float4* logits, int t0, int t1, int logit_base,
+                           int64_t W2, int64_t own0, int64_t own1, int y_lo, int y_hi, int x_lo, int x_hi,
+                           cudaStream_t s, LaunchCounter* lc) {
+  y_lo = (int)std::max<int64_t>(y_lo, own0);
+  y_hi = (int)std::min<int64_t>(y_hi, own1);
+  x_lo = std::max(x_lo, 0);
+  x_hi = (int)std::min<int64_t>(x_hi, W2);
+  if (y_hi <= y_lo || x_hi <= x_lo) return;
+  dim3 grid((unsigned)ceil_div(x_hi - x_lo, 256), (unsigned)(y_hi - y_lo));
+  stitch_seg_kernel<<<grid, 256, 0, s>>>(canvas, ri, logits, t0, t1, logit_base, W2, own0, y_lo, x_lo, x_hi);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// =============================================================================================
+// K7: threshold_probs (utils/preprocessing.py:156-172) + heatmap (utils/eval.py:220-228)
+//   softmax over the SUMMED logits, per-class floor, first-max argmax, heat = p[2]+p[3] | p[1],
+//   x mask, uint8(255*h) truncation.
+// =============================================================================================
+struct PixelOut { uint8_t cls, heat; float p[4]; };
+
+__device__ __forceinline__ PixelOut finalise_pixel(const float4 l, float maskv, const float* cp, int heat_mode) {
+  PixelOut o;
+  const float mx = fmaxf(fmaxf(l.x, l.y), fmaxf(l.z, l.w));
+  float e0 = expf(l.x - mx), e1 = expf(l.y - mx), e2 = expf(l.z - mx), e3 = expf(l.w - mx);
+  const float inv = 1.f / (e0 + e1 + e2 + e3);
+  float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv, p3 = e3 * inv;
+  if (p0 < cp[0]) p0 = 0.f;
+  if (p1 < cp[1]) p1 = 0.f;
+  if (p2 < cp[2]) p2 = 0.f;
+  if (p3 < cp[3]) p3 = 0.f;
+  int am = 0; float best = p0;
+  if (p1 > best) { best = p1; am = 1; }
+  if (p2 > best) { best = p2; am = 2; }
+  if (p3 > best) { best = p3; am = 3; }
+  const float h = (heat_mode == 1) ? p1 : (p2 + p3);
+  const float hv = 255.f * (maskv * h);
+  o.cls = (uint8_t)am;
+  o.heat = (uint8_t)(int)fminf(hv, 255.f);
+  o.p[0] = p0; o.p[1] = p1; o.p[2] = p2; o.p[3] = p3;
+  return o;
+}
+
+__device__ __forceinline__ void write_pixel(const FinaliseArgs& a, int64_t idx, int64_t plane, const float4 l, const PixelOut& o) {
+  a.classes[idx] = o.cls;
+  a.heatmap[idx] = o.heat;
+  if (a.canvas_out) {
+    a.canvas_out[idx] = l.x; a.canvas_out[plane + idx] = l.y; a.canvas_out[2 * plane + idx] = l.z; a.canvas_out[3 * plane + idx] = l.w;
+  }
+  if (a.probs_out) {
+    a.probs_out[idx] = o.p[0]; a.probs_out[plane + idx] = o.p[1]; a.probs_out[2 * plane + idx] = o.p[2]; a.probs_out[3 * plane + idx] = o.p[3];
+  }
+}
+
+// 4 pixels per thread: 64 B canvas read, 4 B + 4 B output
+__global__ void __launch_bounds__(256) finalise_seg_kernel(const float4* __restrict__ canvas, FinaliseArgs a) {
+  const int64_t rows = a.own1 - a.own0, plane = rows * a.W2;
+  const int64_t quads = (plane + 3) / 4;
+  for (int64_t qd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t base = qd * 4;
+    if (base + 3 < plane && !a.canvas_out && !a.probs_out) {
+      uint32_t cw = 0, hw = 0;
+      uint32_t mk = 0x01010101u;
+      if (a.mask) mk = *reinterpret_cast<const uint32_t*>(a.mask + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 l = __ldg(canvas + base + j);
+        const PixelOut o = finalise_pixel(l, (float)((mk >> (8 * j)) & 0xffu), a.class_probs, a.heat_mode);
+        cw |= (uint32_t)o.cls << (8 * j);
+        hw |= (uint32_t)o.heat << (8 * j);
+      }
+      *reinterpret_cast<uint32_t*>(a.classes + base) = cw;
+      *reinterpret_cast<uint32_t*>(a.heatmap + base) = hw;
+    } else {
+      for (int64_t idx = base; idx < base + 4 && idx < plane; ++idx) {
+        const float4 l = canvas[idx];
+        const float mv = a.mask ? (float)a.mask[idx] : 1.f;
+        const PixelOut o = finalise_pixel(l, mv, a.class_probs, a.heat_mode);
+        write_pixel(a, idx, plane, l, o);
+      }
+    }
+  }
+}
+
+void launch_finalise_seg(const float4* canvas, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t plane = (a.own1 - a.own0) * a.W2;
+  if (plane <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(ceil_div(plane, 4), 256), 148 * 32);
+  finalise_seg_kernel<<<grid, 256, 0, s>>>(canvas, a);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// K6+K7 (cls): pred_src [C] broadcast over the rectangle (utils/eval.py:210-215), canvas never materialised
+__global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, const float4* __restrict__ tile_logits, int T, FinaliseArgs a) {
+  const int64_t rows = a.own1 - a.own0, plane = rows * a.W2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int Y = (int)(a.own0 + idx / a.W2), X = (int)(idx % a.W2);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for_each_cover(ri, 0, T, X, Y, [&](int i, int, int) {
+      const float4 v = __ldg(tile_logits + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    });
+    const float mv = a.mask ? (float)a.mask[idx] : 1.f;
+    const PixelOut o = finalise_pixel(acc, mv, a.class_probs, a.heat_mode);
+    write_pixel(a, idx, plane, acc, o);
+  }
+}
+
+void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t plane = (a.own1 - a.own0) * a.W2;
+  if (plane <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(plane, 256), 148 * 32);
+  stitch_finalise_cls_kernel<<<grid, 256, 0, s>>>(ri, tile_logits, T, a);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+__global__ void __launch_bounds__(256) counts_kernel(RectIndex ri, int T, int64_t W2, int64_t own0, int64_t own1, int32_t* __restrict__ counts) {
+  const int64_t plane = (own1 - own0) * W2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int Y = (int)(own0 + idx / W2), X = (int)(idx % W2);
+    int n = 0;
+    for_each_cover(ri, 0, T, X, Y, [&](int, int, int) { ++n; });
+    counts[idx] = n;
+  }
+}
+
+void launch_counts(const RectIndex& ri, int T, int64_t W2, int64_t own0, int64_t own1, int32_t* counts, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t plane = (own1 - own0) * W2;
+  if (plane <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(plane, 256), 148 * 32);
+  counts_kernel<<<grid, 256, 0, s>>>(ri, T, W2, own0, own1, counts);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// =============================================================================================
+// synthetic H&E slide (integer-only twin of wsi_segmentation_pipeline_b200/synth.py)
+// =============================================================================================
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t hash2(uint32_t seed, uint32_t a, uint32_t b, uint32_t salt) {
+  const uint32_t k = seed * 0xC2B2AE3Du + salt * 0x27D4EB2Fu;
+  return mix32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ k);
+}
+__device__ __forceinline__ uint32_t value_noise(uint32_t seed, int64_t y, int64_t x, int shift, uint32_t salt) {
+  const uint32_t cell = 1u << shift;
+  const uint32_t gy = (uint32_t)(y >> shift), gx = (uint32_t)(x >> shift);
+  const uint32_t fy = (uint32_t)(y & (cell - 1)), fx = (uint32_t)(x & (cell - 1));
+  const uint32_t v00 = hash2(seed, gx, gy, salt) & 255u, v10 = hash2(seed, gx + 1, gy, salt) & 255u;
+  const uint32_t v01 = hash2(seed, gx, gy + 1, salt) & 255u, v11 = hash2(seed, gx + 1, gy + 1, salt) & 255u;
+  const uint32_t top = v00 * (cell - fx) + v10 * fx, bot = v01 * (cell - fx) + v11 * fx;
+  const uint32_t val = top * (cell - fy) + bot * fy;
+  return val >> (2 * shift - 8);
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(int64_t iw, uint32_t seed, int64_t y0, int64_t y1, const uint8_t* __restrict__ lut,
+                                                     uint8_t* __restrict__ rgb, int64_t row_stride, uint8_t* __restrict__ mask) {
+  __shared__ uint8_t s_lut[16 * 8 * 3];
+  for (int i = threadIdx.x; i < 16 * 8 * 3; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int64_t total = (y1 - y0) * iw;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t y = y0 + idx / iw, x = idx % iw;
+    const uint32_t f1 = value_noise(seed, y, x, 9, 11), f2 = value_noise(seed, y, x, 7, 23);
+    const bool tissue = ((f1 * 3u + f2) >> 2) > 30200u;
+    const uint32_t hp = hash2(seed, (uint32_t)x, (uint32_t)y, 37);
+    uint8_t* o = rgb + (y - y0) * row_stride + x * 3;
+    if (mask) mask[(y - y0) * iw + x] = tissue ? 1 : 0;
+    int out[3];
+    if (tissue) {
+      const uint32_t ef = value_noise(seed, y, x, 6, 41);
+      const uint32_t e_lvl = min((ef >> 12) + ((hp >> 28) & 3u), 15u);
+      const int64_t cy = y / 12, cx = x / 12;
+      uint32_t h_lvl = 0;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int64_t gy = cy + dy, gx = cx + dx;
+          const uint32_t hc = hash2(seed, (uint32_t)gx, (uint32_t)gy, 53);
+          if ((hc & 7u) >= 5u) continue;
+          const int64_t ox = (hc >> 3) % 12u, oy = (hc >> 9) % 12u;
+          const int64_t r = 3 + ((hc >> 15) & 3u);
+          const int64_t ddx = x - (gx * 12 + ox), ddy = y - (gy * 12 + oy);
+          if (ddx * ddx + ddy * ddy <= r * r) h_lvl = max(h_lvl, 1u + ((hc >> 17) % 7u));
+        }
+      const uint8_t* base = s_lut + (e_lvl * 8 + h_lvl) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t bits = (hp >> (6 * c)) & 63u;
+        out[c] = (int)base[c] + (int)((bits & 7u) + (bits >> 3)) - 7;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[c] = 240 + (int)((hp >> (4 * c + 8)) % 9u) - 4;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = (uint8_t)min(max(out[c], 0), 255);
+  }
+}
+
+void launch_synth(int64_t ih, int64_t iw, uint32_t seed, int64_t y0, int64_t y1, const uint8_t* lut_dev, uint8_t* rgb,
+                  int64_t row_stride, uint8_t* mask, cudaStream_t s, LaunchCounter* lc) {
+  (void)ih;
+  const int64_t total = (y1 - y0) * iw;
+  if (total <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
+  synth_kernel<<<grid, 256, 0, s>>>(iw, seed, y0, y1, lut_dev, rgb, row_stride, mask);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+}  // namespace wsi

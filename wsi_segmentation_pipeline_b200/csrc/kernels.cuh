@@ -1,0 +1,65 @@
+// kernels.cuh — the HBM-bound stages of the path: tile gather + normalise (K0), max-pool, global
+// average pool + heads (K4), overlap-accumulate stitch (K6), softmax/argmax/heatmap finalise (K7),
+// and the synthetic-slide generator.  Launch wrappers; kernels live in kernels.cu.
+#pragma once
+#include "common.cuh"
+
+namespace wsi {
+
+// Rectangles (tiles mapped to canvas coordinates) sorted by (ty, tx) with a row index, the
+// lookup structure of the atomic-free gather-formulated stitch.
+struct RectIndex {
+  const int32_t* tx;        // [T] canvas x origin of sorted rect i
+  const int32_t* row_y;     // [R] distinct canvas y origins, ascending
+  const int32_t* row_start; // [R+1] first sorted rect of each row
+  int32_t R;
+  int32_t dx, dy;           // rectangle size on the canvas
+};
+
+struct FinaliseArgs {
+  int64_t W2;               // canvas width
+  int64_t own0, own1;       // canvas rows handled
+  const uint8_t* mask;      // [own1-own0, W2] or nullptr (= ones)
+  float class_probs[4];
+  int heat_mode;            // 0: p[2]+p[3] (seg), 1: p[1] (cls)
+  uint8_t* classes;         // [rows, W2]
+  uint8_t* heatmap;         // [rows, W2]
+  float* canvas_out;        // [4, rows, W2] or nullptr
+  float* probs_out;         // [4, rows, W2] or nullptr
+};
+
+// K0: raster u8 [rows, iw, 3] -> zero-padded normalised bf16 tiles [n][ph+6][pw+8][4] (interior only)
+void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n,
+                   int ph, int pw, const float* lut_dev /*f32 [3][256]*/, bf16* padded_or_null, float* norm_out_or_null,
+                   cudaStream_t s, LaunchCounter* lc);
+// normalised f32 NCHW -> padded bf16 tiles (nn.Module shim forward)
+void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc);
+// 3x3/s2/p1 max pool, NHWC bf16, C multiple of 8
+void launch_maxpool(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc);
+// global average pool + up to two Linear layers: feat[512] -> (W1,b1)[n1] (-> ReLU -> (W2,b2)[n2])
+void launch_pool_head(const bf16* x4, int n, int hw, int c, const float* w1, const float* b1, int n1,
+                      const float* w2, const float* b2, int n2, float* feat_out_or_null, float* out,
+                      cudaStream_t s, LaunchCounter* lc);
+// logits f32 NHWC4 [n,h,w,4] -> NCHW [n,4,h,w]
+void launch_nhwc4_to_nchw(const float* x, int n, int h, int w, float* y, cudaStream_t s, LaunchCounter* lc);
+
+// K6 (seg): canvas[own rows][W2] (float4) += sum over the sorted tiles [t0, t1) covering each pixel
+// of the box [y_lo, y_hi) x [x_lo, x_hi) (clipped to the owned rows and the canvas width).
+// logits: f32 [..][ph][pw][4], tile i at index (i - logit_base).  One owner thread per pixel.
+void launch_stitch_seg_box(float4* canvas, const RectIndex& ri, const float4* logits, int t0, int t1, int logit_base,
+                           int64_t W2, int64_t own0, int64_t own1, int y_lo, int y_hi, int x_lo, int x_hi,
+                           cudaStream_t s, LaunchCounter* lc);
+// K7 (seg): canvas -> classes/heatmap (+ optional planar canvas / probs)
+void launch_finalise_seg(const float4* canvas, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc);
+// K6+K7 (cls): per-tile logits [T][4] (sorted order) broadcast over rectangles, summed per pixel and finalised
+void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const FinaliseArgs& a,
+                                cudaStream_t s, LaunchCounter* lc);
+// coverage counts from the rect index
+void launch_counts(const RectIndex& ri, int T, int64_t W2, int64_t own0, int64_t own1, int32_t* counts,
+                   cudaStream_t s, LaunchCounter* lc);
+
+// synthetic slide rows [y0, y1) (twin of synth.py)
+void launch_synth(int64_t ih, int64_t iw, uint32_t seed, int64_t y0, int64_t y1, const uint8_t* lut_dev,
+                  uint8_t* rgb, int64_t row_stride, uint8_t* mask_or_null, cudaStream_t s, LaunchCounter* lc);
+
+}  // namespace wsi
