@@ -184,6 +184,15 @@ struct NetPlan {
   Act* x4 = nullptr;
   double conv_flops = 0, stem_flops = 0;   // per batch of `cap` tiles (algorithmic: 2*MAC, no padding)
   std::vector<Act*> feats;                 // [x4, x3, x2, x1, x0]
+  // WSI_CONV_TRACE=1: per-op device time (dev tool; events around every conv launch)
+  struct OpStat { std::string desc; double ms = 0, flops = 0; int64_t count = 0; };
+  std::vector<OpStat> op_stats;
+  struct OpSpan { cudaEvent_t a, b; int idx; };
+  std::vector<OpSpan> op_spans;
+  bool trace = false;
+  void resolve_trace();
+  void print_trace();
+  ~NetPlan() { if (trace) { resolve_trace(); print_trace(); } }
 
   Act* new_act(int N, int H, int W, int C) {
     acts.emplace_back(new Act());
@@ -226,6 +235,8 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
     op->build_stem(in_pad.p, cap, ph, pw, w.data.data(), f.scale.data(), f.bias.data(), x0->buf.p, ef, sms);
     steps.push_back(Step{0, ST_STEM, op, nullptr, x0});
     stem_flops = op->flops();
+    op_stats.push_back(OpStat{"stem 7x7/s2 3->64", 0, op->flops(), 0});
+    trace = getenv("WSI_CONV_TRACE") != nullptr;
   }
   // ---- maxpool 3x3/s2/p1 (:199) ----
   Act* p0 = new_act(cap, (x0->H - 1) / 2 + 1, (x0->W - 1) / 2 + 1, 64);
@@ -238,6 +249,13 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
               out ? out->buf.p : nullptr, hw, hb, hout, ef, sms);
     steps.push_back(Step{0, ST_CONV, op, nullptr, out});
     conv_flops += op->flops();
+    char d[160];
+    int cin_t = 0;
+    for (auto& q : parts) cin_t += q.t.C;
+    snprintf(d, sizeof(d), "conv%dx%d/s%d %4d->%-4d @%dx%d%s%s BN%d BK%d", spec.ksize, spec.ksize, spec.stride, cin_t, spec.cout,
+             parts[0].up2 ? 2 * parts[0].t.H : parts[0].t.H, parts[0].up2 ? 2 * parts[0].t.W : parts[0].t.W, parts[0].up2 ? " up2" : "",
+             res ? " +res" : "", op->block_n(), op->block_k());
+    op_stats.push_back(OpStat{d, 0, op->flops(), 0});
   };
 
   // ---- layer1..layer4, BasicBlock (resnets_shift.py:49-65) ----
@@ -356,7 +374,32 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
   CUDA_CHECK(cudaDeviceSynchronize());
 }
 
+void NetPlan::resolve_trace() {
+  for (auto& sp : op_spans) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+      op_stats[sp.idx].ms += ms;
+      op_stats[sp.idx].count++;
+    }
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  op_spans.clear();
+}
+
+void NetPlan::print_trace() {
+  double tot = 0;
+  for (auto& o : op_stats) tot += o.ms;
+  fprintf(stderr, "[wsi conv trace] cap=%d tile=%dx%d, %.2f ms total\n", cap, ph, pw, tot);
+  for (auto& o : op_stats)
+    if (o.count)
+      fprintf(stderr, "  %-58s %8.3f ms/launch %7.1f TFLOP/s %5.1f%%\n", o.desc.c_str(), o.ms / o.count,
+              o.flops / (o.ms / o.count * 1e-3) / 1e12, 100.0 * o.ms / tot);
+}
+
 void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
+  if (trace && op_spans.size() > 20000) resolve_trace();
+  int conv_idx = 0;
   size_t i = 0;
   while (i < steps.size()) {
     const int stage = steps[i].stage;
@@ -372,7 +415,19 @@ void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
     for (; i < j; ++i) {
       const Step& st = steps[i];
       if (st.kind == 0) {
-        st.op->launch(s, &c->lc);
+        if (trace) {
+          OpSpan sp;
+          cudaEventCreate(&sp.a);
+          cudaEventCreate(&sp.b);
+          sp.idx = conv_idx;
+          cudaEventRecord(sp.a, s);
+          st.op->launch(s, &c->lc);
+          cudaEventRecord(sp.b, s);
+          op_spans.push_back(sp);
+        } else {
+          st.op->launch(s, &c->lc);
+        }
+        ++conv_idx;
       } else if (st.kind == 1) {
         launch_maxpool(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
       } else {
