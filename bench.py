@@ -99,6 +99,8 @@ def cpu_sample(threads: int, sample_hw=(1024, 1536)):
     from oracle import wsi_oracle as O
     from wsi_segmentation_pipeline_b200 import synth
     torch.set_num_threads(threads)
+    if os.environ.get("WSI_BENCH_TINY"):        # tests/test_host_cpu.py: contract check only
+        sample_hw = (640, 768)
     h, w = sample_hw
     raster = synth.synth_slide(h, w, SEED)
     mask = np.ones((h, w), np.uint8)

@@ -1,0 +1,115 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/wsi_b200.h declares, the
+host-only planner is bit-exact with the reference enumeration, and device entry points fail loudly
+without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import wsi_oracle as O
+from wsi_segmentation_pipeline_b200 import capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "wsi_b200.h")).read()
+    declared = set(re.findall(r"WSI_API\s+[\w\s\*]+?\b(wsi_\w+)\s*\(", header))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    L = capi.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in L.wsi_version()
+
+
+def test_plan_tiles_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "plan.npz"))
+    for ci in range(int(g["n_cases"])):
+        ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g[f"case{ci}_geom"])
+        m = 1.0 if lvl == 2 else 0.25
+        np.testing.assert_array_equal(capi.plan_tiles(ih, iw, ph, pw, sh, sw, g[f"case{ci}_mask"], m), g[f"case{ci}_tiles"])
+
+
+@settings(max_examples=150, deadline=None)
+@given(ih=st.integers(40, 400), iw=st.integers(40, 400), ph=st.integers(8, 96), pw=st.integers(8, 96),
+       sh=st.integers(4, 128), sw=st.integers(4, 128), lvl=st.sampled_from([2, 1]), seed=st.integers(0, 5),
+       kind=st.sampled_from(["ones", "synth", "sparse"]))
+def test_plan_tiles_matches_oracle_property(ih, iw, ph, pw, sh, sw, lvl, seed, kind):
+    m = 1.0 if lvl == 2 else 0.25
+    mh, mw = (ih, iw) if lvl == 2 else (max(ih // 4, 1), max(iw // 4, 1))
+    if kind == "ones":
+        mask = np.ones((mh, mw), np.uint8)
+    elif kind == "synth":
+        mask = np.ascontiguousarray(synth.synth_mask(mh * 8, mw * 8, 100 + seed)[::8, ::8])
+    else:
+        mask = (np.random.default_rng(seed).random((mh, mw)) < 0.04).astype(np.uint8)
+    try:
+        ref = O.plan_tiles(ih, iw, ph, pw, sh, sw, mask, m)
+        ref_err = None
+    except ZeroDivisionError:
+        ref_err = True
+    # a tile with a negative origin would be tested (python negative indexing): rejected explicitly
+    n_ys, n_xs = len(range(1, ih - 1 - ph, sh)), len(range(1, iw - 1 - pw, sw))
+    degenerate = (iw - 1 - pw < 0 and n_ys > 0) or (ih - 1 - ph < 0 and n_xs > 0)
+    if ref_err or degenerate:
+        with pytest.raises(capi.WsiError) as e:
+            capi.plan_tiles(ih, iw, ph, pw, sh, sw, mask, m)
+        assert e.value.status == -4
+        return
+    got = capi.plan_tiles(ih, iw, ph, pw, sh, sw, mask, m)
+    np.testing.assert_array_equal(got, np.array(ref, np.int32).reshape(-1, 2))
+
+
+def test_plan_tiles_full_size_counts():
+    assert len(capi.plan_tiles(2048, 2048, 256, 256, 128, 128)) == 224
+    assert len(capi.plan_tiles(20000, 20000, 512, 512, 128, 128)) == 23715        # config 2
+    t = capi.plan_tiles(80000, 100000, 512, 512, 128, 128)                        # config 3
+    assert len(t) == 484537
+    assert t[:, 0].min() == 1 and t[:, 1].min() == 1 and t[:, 0].max() == 100000 - 1 - 512 and t[:, 1].max() == 80000 - 1 - 512
+
+
+@pytest.mark.parametrize("ih,ph,sh,n", [(20000, 512, 128, 1), (20000, 512, 128, 2), (80000, 512, 128, 8), (2048, 256, 128, 4),
+                                        (352, 64, 32, 3), (700, 64, 96, 5)])
+def test_band_partition_covers_and_tiles_are_complete(ih, ph, sh, n):
+    iw = 1000
+    bands = capi.band_partition(ih, ph, sh, n)
+    assert bands[0, 0] == 0 and bands[-1, 1] == ih
+    assert (bands[1:, 0] == bands[:-1, 1]).all() and (bands[:, 1] >= bands[:, 0]).all()
+    tiles = capi.plan_tiles(ih, iw, ph, ph, sh, sh)
+    seen = np.zeros(len(tiles), bool)
+    for own0, own1, row0, row1 in bands:
+        idx = capi.band_tiles(tiles, ph, 1.0, own0, own1)
+        ys = tiles[idx, 1]
+        # exactly the tiles intersecting the band, and their rows are all inside [row0, row1)
+        want = np.nonzero((tiles[:, 1] < own1) & (tiles[:, 1] + ph > own0))[0]
+        np.testing.assert_array_equal(idx, want)
+        if len(idx):
+            assert ys.min() >= row0 and ys.max() + ph <= row1
+        seen[idx] = True
+    assert seen.all()
+
+
+def test_device_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.WsiError) as e:
+        capi.Context(0)
+    assert e.value.status == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_models_refuse_cpu_forward():
+    import torch
+    from wsi_segmentation_pipeline_b200 import models
+    net = models.unet_resnet18()
+    sd = O.random_state_dict("unet", 0)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 64, 64))
+    r = models.resnet18()
+    sd = O.random_state_dict("resnet18", 0, with_fc=True)
+    missing, unexpected = r.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("fc1.", "fc2.")) for k in missing), (missing, unexpected)

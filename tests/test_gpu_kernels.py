@@ -112,6 +112,11 @@ CONV_CASES = [
     (2, 20, 28, 64, 64, 3, 1, 1, False, False),      # extents that are not powers of two
     (1, 64, 64, 64, 64, 3, 1, 1, True, True),        # many M tiles per CTA (persistent loop, 2 TMEM buffers)
     (2, 2, 2, 512, 512, 3, 1, 1, False, True),       # 2x2 feature map (64 px tiles at /32)
+    # row-tile kernel (cout 16/32, <=64 channels per operand): halo-resident taps, cp.async producers
+    (2, 40, 300, 32, 32, 3, 1, 1, False, True),      # 3 x-tiles per row, ragged last tile
+    (1, 24, 136, 16, 16, 3, 1, 1, False, False),     # 1 slab, no relu
+    (3, 8, 8, 64, 32, 3, 1, 1, False, True),         # 4 slabs, rows shorter than the tile
+    (1, 70, 128, 48, 16, 3, 1, 1, False, True),      # 3 slabs, exactly one tile per row, many rows per CTA
 ]
 
 
@@ -143,6 +148,11 @@ UP_CASES = [
     (2, 16, 16, 64, 64, 32),      # decoder level 4 shape (128 -> 32)
     (1, 16, 16, 32, 0, 16),       # decoder level 5: no skip, BLOCK_K 32
     (3, 1, 1, 512, 256, 256),     # 1x1 low-res map (64 px tiles)
+    # row-tile kernel, upsample (+ skip) variants
+    (1, 20, 150, 32, 0, 16),      # output 40x300: two 256-px parity tiles per row, ragged
+    (2, 12, 70, 64, 64, 32),      # decoder level 4 shape: x2(64) + skip(64) -> 32, 8 slabs
+    (1, 6, 6, 16, 16, 16),        # tiny
+    (1, 33, 129, 32, 32, 32),     # odd low-res extents
 ]
 
 

@@ -2,9 +2,17 @@
 #include "conv_igemm.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
+#include "conv_rowtile.cuh"
+
 namespace wsi {
+
+ConvOp::ConvOp() = default;
+ConvOp::~ConvOp() = default;
+ConvOp::ConvOp(ConvOp&&) noexcept = default;
+ConvOp& ConvOp::operator=(ConvOp&&) noexcept = default;
 
 // ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda) ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -87,6 +95,15 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
                    const float* scale, const float* bias, const void* residual, void* out,
                    const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms) {
   WSI_REQUIRE(!parts.empty() && parts.size() <= 2, WSI_ERR_INVALID, "conv: 1 or 2 input parts");
+  if (RowConvOp::eligible(parts, spec, residual) && getenv("WSI_NO_ROWTILE") == nullptr) {
+    row_.reset(new RowConvOp());
+    row_->build(parts, spec, w_oihw, scale, bias, out, head_w, head_b, head_out, error_flag, num_sms);
+    flops_ = row_->flops();
+    block_n_ = spec.cout;
+    block_k_ = 16;
+    return;
+  }
+  row_.reset();
   bool any_up = false;
   for (auto& q : parts) any_up |= q.up2;
   const int k = spec.ksize;
@@ -276,6 +293,7 @@ static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams
 }
 
 void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
+  if (row_) { row_->launch(stream, lc); return; }
 #define WSI_CASE(BN, BK) \
   if (block_n_ == BN && block_k_ == BK) { launch_inst<BN, BK>(amaps_, bmap_, p_, grid_, stream); if (lc) lc->n++; return; }
   WSI_CASE(128, 64) WSI_CASE(64, 64) WSI_CASE(32, 64) WSI_CASE(16, 64)

@@ -27,6 +27,8 @@
 //   Persistent CTAs (grid = min(tiles, #SM)), static round-robin tile schedule, N-tile fastest so
 //   CTAs sharing an A tile run together and hit L2.
 #pragma once
+#include <memory>
+
 #include "common.cuh"
 
 namespace wsi {
@@ -436,12 +438,17 @@ struct ConvSpec {
   bool head = false;         // fused final 1x1 conv (cout must be 16)
 };
 
+class RowConvOp;   // conv_rowtile.cuh: halo-resident kernel for the small-channel 3x3 layers
+
 // A fully prepared conv launch: tensor maps, K-block table, packed weights, epilogue params.
+// build() routes small-channel 3x3/s1 convs to the row-tile kernel (conv_rowtile.cuh) and
+// everything else to the TMA implicit-GEMM kernel below.
 class ConvOp {
  public:
-  ConvOp() = default;
-  ConvOp(ConvOp&&) = default;
-  ConvOp& operator=(ConvOp&&) = default;
+  ConvOp();
+  ~ConvOp();
+  ConvOp(ConvOp&&) noexcept;
+  ConvOp& operator=(ConvOp&&) noexcept;
 
   // weights: fp32 OIHW [cout][cin_total][k][k]; scale/bias may be nullptr (1 / 0).
   void build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
@@ -462,6 +469,7 @@ class ConvOp {
   CUtensorMap bmap_{};
   ConvParams p_{};
   DevBuf w_, scale_, bias_, tbl_, headw_, headb_;
+  std::unique_ptr<RowConvOp> row_;
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
   double flops_ = 0;
 };

@@ -71,8 +71,8 @@ extern "C" int wsi_plan_tiles(int64_t ih, int64_t iw, int32_t ph, int32_t pw, in
   RowCounter rc{mask, mh, mw};
 
   auto test = [&](int64_t xpos, int64_t ypos) -> int {
+    if (xpos < 0 || ypos < 0) return -1;   // the reference would index the mask with a negative origin
     if (!mask) return 1;
-    if (xpos < 0 || ypos < 0) return -1;
     const int64_t yp = (int64_t)((double)ypos * m), xp = (int64_t)((double)xpos * m);
     rc.set_row(yp, dy);
     return rc.foreground(xp, dx);

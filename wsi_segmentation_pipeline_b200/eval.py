@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's inference entry points (utils/eval.py).
+
+``predict_tumorbed(model, dataset, ep, mode)`` keeps the reference's signature and side effects
+(heatmap / overlay PNGs under ``{val_save_pth}/{ep}/``, ``dataset.wsis[key] = None`` when done,
+``model.train()`` on exit) but the loop body — DataLoader, ``model.encoder``/``decoder``,
+``.cpu().numpy()``, the per-tile numpy ``+=`` and ``threshold_probs`` (utils/eval.py:190-228) —
+is ONE call into libwsi_b200 per slide (``wsi_run_slide``).  No CPU fallback.
+
+Multi-GPU: ``predict_tumorbed_banded`` partitions a slide into row bands (one per rank, halo =
+tile overlap), runs each band locally and gathers the u8 band outputs on rank 0 — the only
+collective on the path.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .dataset import DotDict
+
+DEFAULT_ARGS = DotDict(num_classes=4, class_probs=[0.0, 0.0, 0.0, 0.0], scan_level=2, scan_resize=1, val_save_pth=None,
+                       tile_stride_w=128, save_overlay=True)
+
+
+def _engine_of(model) -> capi.Context:
+    if isinstance(model, capi.Context):
+        return model
+    if hasattr(model, "_engine"):
+        return model._engine()
+    raise TypeError("model must be a wsi_segmentation_pipeline_b200.models module (or a capi.Context with weights loaded)")
+
+
+def _merge_args(args):
+    a = DotDict(DEFAULT_ARGS)
+    if args is not None:
+        for k in DEFAULT_ARGS:
+            v = args.get(k) if isinstance(args, dict) else getattr(args, k, None)
+            if v is not None:
+                a[k] = v
+    return a
+
+
+def run_slide(ctx: capi.Context, entry: dict, params, mode: str, **kw) -> dict:
+    """One slide through the CUDA path.  entry: a ``Dataset_wsis.wsis[key]`` dict."""
+    it = entry["iterator"]
+    scan = entry["scan"]
+    raster = it.raster()
+    ih, iw = raster.shape[:2]
+    W2, H2 = scan.level_dimensions[2]                          # utils/eval.py:182
+    mask = entry.get("mask")
+    mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    sl = ctx.slide_desc(raster, ih, iw, params.ph, params.pw, m=it.m, H2=H2, W2=W2, mask=mask)
+    return ctx.run_slide(sl, it.tiles, capi.HEAD_SEG if mode == "seg" else capi.HEAD_CLS, **kw)
+
+
+def predict_tumorbed(model, dataset, ep, mode: str = "seg", args=None, return_outputs: bool = True):
+    """utils/eval.py:155-286.  Returns {key: {'classes': u8 [H2,W2], 'heatmap': u8 [H2,W2]}}."""
+    assert mode in ("seg", "cls")
+    a = _merge_args(args)
+    if a.scan_resize != 1:
+        raise NotImplementedError("scan_resize != 1 (nearest re-interpolation of tiles, utils/eval.py:202-206) is not on the CUDA path")
+    ctx = _engine_of(model)
+    ctx.set_class_probs(a.class_probs)
+    if hasattr(model, "eval"):
+        model.eval()
+    save = a.val_save_pth is not None
+    if save:
+        os.makedirs(f"{a.val_save_pth}/{ep}", exist_ok=True)
+    outputs = {}
+    for key in list(dataset.wsis):
+        entry = dataset.wsis[key]
+        if entry is None:
+            continue
+        r = run_slide(ctx, entry, dataset.params, mode)
+        heat, classes = r["heatmap"].numpy(), r["classes"].numpy()
+        if save:
+            from PIL import Image
+            Image.fromarray(heat).save(f"{a.val_save_pth}/{ep}/{key}_{a.tile_stride_w}_heatmap.png")     # :229
+            if a.save_overlay:                                                                            # :262-267
+                scan = entry["scan"]
+                img = np.asarray(scan.read_region((0, 0), 2, scan.level_dimensions[2]).convert("RGB")).astype(np.uint8)
+                img = img * 0.75 + 255 * np.repeat(np.expand_dims(heat > 255 * 0.99, -1), repeats=3, axis=-1) * 0.25
+                Image.fromarray(np.uint8(img)).save(f"{a.val_save_pth}/{ep}/{key}_{a.tile_stride_w}_overlay.png")
+        if return_outputs:
+            outputs[key] = {"classes": classes, "heatmap": heat}
+        dataset.wsis[key] = None                                                                          # :282
+    if hasattr(model, "train"):
+        model.train()                                                                                     # :286
+    return outputs
+
+
+def band_plan(ih: int, ph: int, sh: int, tiles: np.ndarray, m: float, world: int):
+    """Per rank: (own0, own1, row0, row1, tile indices).  SURVEY 8e: boundaries on the tile grid;
+    a rank evaluates every tile intersecting its band, so nothing is exchanged during compute."""
+    bands = capi.band_partition(ih, ph, sh, world)
+    return [(int(o0), int(o1), int(r0), int(r1), capi.band_tiles(tiles, ph, m, int(o0), int(o1))) for o0, o1, r0, r1 in bands]
+
+
+def gather_bands(parts, rows_per_rank, W2: int, rank: int, world: int, device=None):
+    """The path's only collective: gather u8 [2, rows_k, W2] (classes, heatmap) band outputs on
+    rank 0.  ``parts``: this rank's (classes, heatmap) tensors.  Backend-agnostic (NCCL over NVLink
+    on the GPU box, gloo in CPU tests); bands are ragged, so they are padded to the tallest band."""
+    import torch
+    import torch.distributed as dist
+    max_rows = int(max(rows_per_rank))
+    cls, heat = parts
+    dev = device if device is not None else cls.device
+    send = torch.zeros((2, max_rows, W2), dtype=torch.uint8, device=dev)
+    send[0, :cls.shape[0]].copy_(cls)
+    send[1, :heat.shape[0]].copy_(heat)
+    if world == 1:
+        return send[0, :rows_per_rank[0]], send[1, :rows_per_rank[0]]
+    bufs = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, bufs, dst=0)
+    if rank != 0:
+        return None
+    classes = torch.cat([bufs[k][0, :rows_per_rank[k]] for k in range(world)])
+    heatmap = torch.cat([bufs[k][1, :rows_per_rank[k]] for k in range(world)])
+    return classes, heatmap
+
+
+def predict_tumorbed_banded(model, raster_rows_fn, ih: int, iw: int, params, mask: Optional[np.ndarray], rank: int, world: int,
+                            mode: str = "seg"):
+    """Row-band sharded slide (m == 1).  ``raster_rows_fn(row0, row1)`` returns the u8 [row1-row0, iw, 3]
+    raster rows this rank needs (numpy or torch, host or device).  Returns (classes, heatmap) on
+    rank 0, None elsewhere."""
+    ctx = _engine_of(model)
+    tiles = capi.plan_tiles(ih, iw, params.ph, params.pw, params.sh, params.sw, mask, 1.0)
+    plan = band_plan(ih, params.ph, params.sh, tiles, 1.0, world)
+    own0, own1, row0, row1, idx = plan[rank]
+    band = raster_rows_fn(row0, row1)
+    bmask = None if mask is None else np.ascontiguousarray(mask[own0:own1])
+    sl = ctx.slide_desc(band, ih, iw, params.ph, params.pw, mask=bmask, row0=row0, rows=row1 - row0, own0=own0, own1=own1)
+    r = ctx.run_slide(sl, tiles[idx], capi.HEAD_SEG if mode == "seg" else capi.HEAD_CLS, device_out=True)
+    rows = [p[1] - p[0] for p in plan]
+    return gather_bands((r["classes"], r["heatmap"]), rows, iw, rank, world)
