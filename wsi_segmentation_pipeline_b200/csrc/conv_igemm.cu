@@ -91,19 +91,25 @@ static void map_parity(CUtensorMap* m, const TensorView& t, int hp, int wp, int 
 
 static inline int floor_div2(int t) { return (t >= 0) ? t / 2 : -((-t + 1) / 2); }
 
+bool ConvOp::routes_to_rowtile(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual) {
+  return RowConvOp::eligible(parts, spec, residual) && getenv("WSI_NO_ROWTILE") == nullptr;
+}
+
 void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
                    const float* scale, const float* bias, const void* residual, void* out,
-                   const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms) {
+                   const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms, int out_layout) {
   WSI_REQUIRE(!parts.empty() && parts.size() <= 2, WSI_ERR_INVALID, "conv: 1 or 2 input parts");
-  if (RowConvOp::eligible(parts, spec, residual) && getenv("WSI_NO_ROWTILE") == nullptr) {
+  if (routes_to_rowtile(parts, spec, residual)) {
     row_.reset(new RowConvOp());
-    row_->build(parts, spec, w_oihw, scale, bias, out, head_w, head_b, head_out, error_flag, num_sms);
+    row_->build(parts, spec, w_oihw, scale, bias, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
     flops_ = row_->flops();
     block_n_ = spec.cout;
     block_k_ = 16;
     return;
   }
   row_.reset();
+  WSI_REQUIRE(out_layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: only the row-tile kernel writes planar outputs");
+  for (auto& q : parts) WSI_REQUIRE(q.t.layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC operands");
   bool any_up = false;
   for (auto& q : parts) any_up |= q.up2;
   const int k = spec.ksize;

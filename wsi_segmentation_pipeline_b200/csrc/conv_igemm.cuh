@@ -74,6 +74,18 @@ struct AMaps {
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of the (converged) warp; the compiler treats code under it as single-threaded, so operands of
+// tcgen05 / TMA instructions move to uniform registers without a per-instruction waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -242,7 +254,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -276,7 +288,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16<BLOCK_N>();
       int stage = 0;
       uint32_t phase = 0;
@@ -420,9 +432,14 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct TensorView {          // bf16 NHWC activation tensor in HBM
+// Activation layouts in HBM (bf16).  NHWC everywhere except around the row-tile kernel, whose
+// operands are zero-padded channel-chunk-planar (conv_rowtile.cuh).
+enum ActLayout { LAYOUT_NHWC = 0, LAYOUT_PLANAR = 1, LAYOUT_PLANAR_PARITY = 2 };
+
+struct TensorView {          // bf16 activation tensor in HBM
   const void* ptr = nullptr;
   int N = 0, H = 0, W = 0, C = 0;
+  int layout = LAYOUT_NHWC;
 };
 
 // One operand part of a conv input (the input is the channel concat of its parts).
@@ -451,9 +468,14 @@ class ConvOp {
   ConvOp& operator=(ConvOp&&) noexcept;
 
   // weights: fp32 OIHW [cout][cin_total][k][k]; scale/bias may be nullptr (1 / 0).
+  // out_layout: LAYOUT_NHWC, or LAYOUT_PLANAR when the consumer is a row-tile conv (row-tile producers only).
   void build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
              const float* scale, const float* bias, const void* residual, void* out,
-             const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms);
+             const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms,
+             int out_layout = LAYOUT_NHWC);
+  bool is_rowtile() const { return (bool)row_; }
+  // would build() route this conv to the row-tile kernel?  (lets the caller chain planar layouts)
+  static bool routes_to_rowtile(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual);
   // stem: x = gather output, zero-padded tiles [n][ph+6][pw+8][4] bf16; 7x7/s2/p3, cout 64.
   void build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw /*[64,3,7,7]*/,
                   const float* scale, const float* bias, void* out, int* error_flag, int num_sms);

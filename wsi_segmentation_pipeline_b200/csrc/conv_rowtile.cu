@@ -7,11 +7,11 @@
 namespace wsi {
 
 namespace ptx {
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// contiguous global -> shared bulk copy on the TMA engine, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace ptx
@@ -44,9 +44,8 @@ struct TileCoord {
 };
 
 template <int BN, bool HEAD, int G>
-__global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowParams p) {
+__global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __grid_constant__ RowParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint32_t s_adelta[3][2][G][9];     // [mode][row parity][column parity group][tap] in 16-byte units
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int w_bytes = p.nslabs * 9 * 2 * BN * 16;
   uint8_t* s_w = smem;
@@ -64,8 +63,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S + 2 * kRowAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // accumulator ring: kRowAccStages tiles in flight between the MMA issuer and the epilogue (the tiles are
-  // short, so commit -> wait -> drain -> release latency would otherwise idle the tensor pipe)
+  // accumulator ring: kRowAccStages tiles in flight between the MMA issuer and the epilogue
   constexpr uint32_t kTmemCols = kRowAccStages * G * BN;
   static_assert(kTmemCols >= 32 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
 
@@ -77,27 +75,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
     for (int i = threadIdx.x; i < BN; i += blockDim.x) { s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i]; }
     if (HEAD)
       for (int i = threadIdx.x; i < 68; i += blockDim.x) s_hw[i] = (i < 64) ? p.head_w[i] : p.head_b[i - 64];
+    // stage planes are only partially overwritten for ragged tiles: start from zeros (no NaN garbage)
+    uint4* st = reinterpret_cast<uint4*>(s_stage);
+    for (int i = threadIdx.x; i < S * p.stage_bytes / 16; i += blockDim.x) st[i] = make_uint4(0, 0, 0, 0);
     ptx::fence_proxy_async();
-  }
-  // A-operand start offsets (16-byte units) of every tap, relative to the stage base
-  for (int i = threadIdx.x; i < 3 * 2 * G * 9; i += blockDim.x) {
-    const int tap = i % 9, g = (i / 9) % G, py = (i / (9 * G)) % 2, mode = i / (18 * G);
-    const int r = tap / 3, sft = tap % 3;
-    int par = 0, poff;
-    if (mode == 0) {
-      poff = r * kRowHaloCols + sft;
-    } else if (mode == 1) {
-      poff = (((py + r - 1) >> 1) + 1) * kRowHaloCols + (((g + sft - 1) >> 1) + 1);
-    } else {
-      const int qq = g + sft - 1;
-      par = qq & 1;
-      poff = r * kRowHaloCols + ((qq >> 1) + 1);
-    }
-    s_adelta[mode][py][g][tap] = (uint32_t)((par * 2 * kRowPlaneBytes + poff * 16) >> 4);
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
-      ptx::mbar_init(&full[i], kRowProducers);
+      ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < kRowAccStages; ++i) {
@@ -106,76 +91,59 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
     }
     ptx::fence_barrier_init();
   }
-  if (warp == kRowProducerWarps) ptx::tmem_alloc(tmem_holder, kTmemCols);
+  if (warp == 1) ptx::tmem_alloc(tmem_holder, kTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
 
   // contiguous tile range per CTA: coordinates advance incrementally (no divisions in the loops) and a
   // CTA walks down consecutive rows, so two of its three halo rows were just read by itself (L2 hits)
   const int t_begin = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
   const int t_end = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp < kRowProducerWarps) {
-    // ================================ cp.async producers ================================
-    // lanes = (8-channel chunk kc, 16 consecutive halo columns): 8 consecutive lanes write 128
-    // contiguous smem bytes (no bank conflicts) and read whole 32-byte sectors from L2.
-    // Everything that depends only on (tile, operand part) is computed once per part; a 16-channel
-    // slab then costs one wait, <= 9 cp.async with one IMAD + one compare each, and one arrive.
-    const int kc = lane >> 4, cxl = lane & 15;
-    const int ry = warp % 3, hi = warp / 3;          // this warp's halo row; parity (mode 2) or column half
+  if (warp == 0) {
+    // ================================ bulk-copy producer ================================
+    // One 16-channel slab = 2 chunk planes x 3 halo rows (x 2 column parities for the skip operand):
+    // lane l issues copy l, all lanes at once; lane 0 arms the barrier with the byte total.
+    const int ry = lane % 3, kc = (lane / 3) & 1, par = lane / 6;
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t stage0 = ptx::smem_u32(s_stage);
-    const uint32_t lane_dst = (uint32_t)(kc * kRowPlaneBytes + cxl * 16);
     TileCoord tc;
     tc.init(t_begin, p.tiles_x, p.OH);
     for (int tile = t_begin; tile < t_end; ++tile, tc.next(p.tiles_x, p.OH)) {
-      int sl = 0;
+      const int b0 = tc.xb * 128;
+#pragma unroll 1
       for (int pi = 0; pi < p.nparts; ++pi) {
-        const bf16* ptr = p.part[pi].ptr;
-        const int H = p.part[pi].H, W = p.part[pi].W, C = p.part[pi].C, mode = p.part[pi].mode;
-        const int nsl = C >> 4;
-        const int par = (mode == 2) ? hi : 0;
-        const int col0 = (mode == 2) ? 0 : hi * 65;
-        const int sy = ((mode == 1) ? (tc.y >> 1) : tc.y) - 1 + ry;
-        const bool row_ok = (sy >= 0) && (sy < H);
-        const int c0 = tc.xb * 128 - 1 + col0 + cxl;
-        const int sx0 = (mode == 2) ? (2 * c0 + par) : c0;
-        const int xstep = (mode == 2) ? 32 : 16;     // source columns per unrolled step
-        // this lane's 9 (5) chunks: validity mask and byte offsets are the same for every slab of the part
-        uint32_t okmask = 0;
-#pragma unroll
-        for (int it = 0; it < 9; ++it) {
-          const int sx = sx0 + it * xstep;
-          const bool in_task = (mode == 2) ? (cxl + 16 * it < kRowHaloCols) : (it < 5 && cxl + 16 * it < 65);
-          if (in_task) okmask |= 1u << (16 + it);
-          if (in_task && row_ok && (unsigned)sx < (unsigned)W) okmask |= 1u << it;
-        }
-        const bf16* rowp = ptr + ((size_t)tc.n * H + (row_ok ? sy : 0)) * W * C + kc * 8;
-        const int off0 = sx0 * C, offstep = xstep * C;       // element offsets (fit 32 bits: one image row)
-        const uint32_t dst_part = lane_dst + (uint32_t)(par * 2 * kRowPlaneBytes + (ry * kRowHaloCols + col0) * 16);
-        for (int j = 0; j < nsl; ++j, ++sl) {
-          const bf16* srcb = rowp + j * 16;
-          const uint32_t dst = stage0 + (uint32_t)stage * p.stage_bytes + dst_part;
+        const RowPart& pt = p.part[pi];
+        const int mode = pt.mode;
+        const int ncopies = (mode == 2) ? 12 : 6;
+        const int sy = ((mode == 1) ? (tc.y >> 1) : tc.y) - 1 + ry;            // in [-1, H]: the padded layout holds it
+        // entries: plain / x2 source: columns b0-1 .. b0+128 = indices b0 .. b0+129; skip even plane: indices
+        // b0 .. b0+128 into halo cols 1..129; skip odd plane: indices b0 .. b0+128 into halo cols 0..128
+        const int want = (mode == 2) ? 129 : 130;
+        const int n_ent = min(want, pt.d.Wrow - b0);
+        const uint32_t bytes = (uint32_t)n_ent * 16u;
+        const uint32_t dcol = (mode == 2 && par == 0) ? 16u : 0u;
+        const uint32_t dst_l = (uint32_t)((par * 2 + kc) * kRowPlaneBytes + ry * (kRowHaloCols * 16)) + dcol;
+        const bool active = lane < ncopies;
+        const uint8_t* src_l = pt.base + pt.d.row_off(tc.n, active ? sy : 0, kc, (mode == 2 && active) ? par : 0) + (size_t)b0 * 16;
+        const size_t slab_step = (size_t)2 * pt.d.P * pt.d.Wrow * 16;            // two 8-channel chunks further
+        for (int j = 0; j < pt.nslabs; ++j) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 11);
-#pragma unroll
-          for (int it = 0; it < 9; ++it) {
-            if (okmask & (1u << (16 + it))) {
-              const bool ok = (okmask >> it) & 1u;
-              ptx::cp_async16_zfill(dst + 256u * it, srcb + (ok ? off0 + it * offstep : 0), ok ? 16u : 0u);
-            }
-          }
-          ptx::cp_async_arrive_noinc(&full[stage]);
+          if (lane == 0) ptx::mbar_expect_tx(&full[stage], bytes * (uint32_t)ncopies);
+          __syncwarp();
+          if (active) ptx::bulk_g2s(stage0 + (uint32_t)stage * p.stage_bytes + dst_l, src_l + j * slab_step, bytes, &full[stage]);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == kRowProducerWarps) {
+  } else if (warp == 1) {
     // ================================ MMA issuer ========================================
-    if (lane == 0) {
+    // every operand of the issue loop comes from kernel parameters / constants (uniform datapath); the
+    // TMEM base read from smem is made warp-uniform with a redux so no per-MMA R2UR waterfall is needed
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_holder);
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16<BN>();
       const uint64_t a_desc0 = make_nosw_desc(ptx::smem_u32(s_stage), kRowPlaneBytes, 128);
       const uint64_t b_desc0 = make_nosw_desc(ptx::smem_u32(s_w), BN * 16, 128);
@@ -191,24 +159,20 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 12);
         ptx::tc_fence_after();
         int sl = 0;
+#pragma unroll 1
         for (int pi = 0; pi < p.nparts; ++pi) {
-          const int nsl = p.part[pi].C >> 4;
-          const uint32_t* dl = &s_adelta[p.part[pi].mode][py][0][0];
-          uint32_t delta[G * 9];
-#pragma unroll
-          for (int i = 0; i < G * 9; ++i) delta[i] = dl[i];
-          for (int j = 0; j < nsl; ++j, ++sl) {
+          const int mode = p.part[pi].mode;
+          for (int j = 0; j < p.part[pi].nslabs; ++j, ++sl) {
             const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)stage * stage_units);
             const uint64_t b_sl = b_desc0 + (uint64_t)(sl * 9 * 2 * BN);
             ptx::mbar_wait(&full[stage], phase, p.error_flag, 13);
-            ptx::fence_proxy_async();
             ptx::tc_fence_after();
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
               for (int g = 0; g < G; ++g) {
-                ptx::umma_bf16(tmem_base + (uint32_t)((acc * G + g) * BN), a_st + delta[g * 9 + tap], b_sl + (uint64_t)(tap * 2 * BN), idesc,
-                               (uint32_t)((sl | tap) != 0));
+                ptx::umma_bf16(tmem_base + (uint32_t)((acc * G + g) * BN), a_st + (uint64_t)p.adelta[mode][py][g][tap],
+                               b_sl + (uint64_t)(tap * 2 * BN), idesc, (uint32_t)((sl | tap) != 0));
               }
             }
             ptx::umma_commit(&empty[stage]);
@@ -221,8 +185,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
     }
   } else {
     // ================================ epilogue (4 warps) ================================
-    // Tiles here are only 9..144 small MMAs long, so the per-tile epilogue is on the critical path:
-    // folded-BN constants and the fused 1x1 head live in registers for the life of the CTA.
+    // folded-BN constants and the fused 1x1 head live in registers for the life of the CTA
+    const uint32_t tmem_base = *tmem_holder;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     float r_scale[BN], r_bias[BN];
@@ -236,6 +200,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
       for (int j = 0; j < 4; ++j) r_hb[HEAD ? j : 0] = s_hb[j];
     }
     const float lo = p.relu ? 0.f : -INFINITY;
+    const bool planar_out = (p.out_layout == LAYOUT_PLANAR);
+    const size_t chunk_step = (size_t)p.od.Wrow * 16;
     int acc = 0;
     uint32_t acc_phase = 0;
     TileCoord tc;
@@ -274,7 +240,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
           if (valid) reinterpret_cast<float4*>(p.head_out)[pix] = o;
         }
         if (valid && p.out != nullptr) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * BN);
+          uint4 w4[BN / 8];
 #pragma unroll
           for (int j = 0; j < BN / 8; ++j) {
             uint32_t w[4];
@@ -283,7 +249,17 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
               __nv_bfloat162 h2 = __floats2bfloat162_rn(yv[8 * j + 2 * t], yv[8 * j + 2 * t + 1]);
               w[t] = *reinterpret_cast<uint32_t*>(&h2);
             }
-            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            w4[j] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if (planar_out) {
+            // chunk rows are contiguous along x: consecutive lanes write consecutive 16-byte entries
+            uint8_t* o = p.out + p.od.row_off(tc.n, tc.y, 0, 0) + (size_t)(x + 1) * 16;
+#pragma unroll
+            for (int j = 0; j < BN / 8; ++j) *reinterpret_cast<uint4*>(o + j * chunk_step) = w4[j];
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(p.out + pix * (size_t)(BN * 2));
+#pragma unroll
+            for (int j = 0; j < BN / 8; ++j) o[j] = w4[j];
           }
         }
       }
@@ -295,10 +271,41 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const RowP
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kRowProducerWarps) {
+  if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    ptx::tmem_dealloc(*tmem_holder, kTmemCols);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NHWC -> planar relayout (one thread per 16-byte chunk, chunk index fastest: reads are fully
+// coalesced, writes are 16-byte entries of C/8 planar rows)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relayout_planar_kernel(const uint4* __restrict__ src, uint8_t* __restrict__ dst, int N, int H,
+                                                               int W, int KC, int layout) {
+  const PlanarDims d = PlanarDims::make(H, W, KC * 8, layout);
+  const int64_t total = (int64_t)N * H * KC * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % KC);
+    int64_t r = i / KC;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    const uint4 v = __ldg(src + i);
+    size_t off;
+    if (layout == LAYOUT_PLANAR_PARITY) off = d.row_off(n, y, kc, x & 1) + (size_t)((x + 1) >> 1) * 16;   // even x -> x/2, odd x -> (x+1)/2
+    else off = d.row_off(n, y, kc, 0) + (size_t)(x + 1) * 16;
+    *reinterpret_cast<uint4*>(dst + off) = v;
+  }
+}
+
+void launch_relayout_planar(const void* src_nhwc, void* dst, int N, int H, int W, int C, int layout, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t total = (int64_t)N * H * (C / 8) * W;
+  if (total <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
+  relayout_planar_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(src_nhwc), static_cast<uint8_t*>(dst), N, H, W, C / 8, layout);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,16 +322,20 @@ bool RowConvOp::eligible(const std::vector<ConvInputPart>& parts, const ConvSpec
     slabs += q.t.C / 16;
   }
   if (slabs > kRowMaxSlabs) return false;
-  if (parts[0].up2) return parts.size() == 1 || !parts[1].up2;
+  if (parts[0].up2) {
+    if (parts.size() == 2 && (parts[1].up2 || parts[1].t.W % 2 != 0)) return false;
+    return true;
+  }
   return parts.size() == 1;
 }
 
 void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw, const float* scale,
-                      const float* bias, void* out, const float* head_w, const float* head_b, float* head_out, int* error_flag,
-                      int num_sms) {
+                      const float* bias, void* out, int out_layout, const float* head_w, const float* head_b, float* head_out,
+                      int* error_flag, int num_sms) {
   WSI_REQUIRE(eligible(parts, spec, nullptr), WSI_ERR_UNSUPPORTED, "conv is not eligible for the row-tile kernel");
   RowParams& p = p_;
   p = RowParams{};
+  relayouts_.clear();
   const bool up2 = parts[0].up2;
   const int N = parts[0].t.N;
   const int OH = up2 ? 2 * parts[0].t.H : parts[0].t.H, OW = up2 ? 2 * parts[0].t.W : parts[0].t.W;
@@ -336,18 +347,25 @@ void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& s
   for (size_t i = 0; i < parts.size(); ++i) {
     const auto& q = parts[i];
     RowPart& rp = p.part[i];
-    rp.ptr = static_cast<const bf16*>(q.t.ptr);
-    rp.H = q.t.H; rp.W = q.t.W; rp.C = q.t.C;
     rp.mode = up2 ? (q.up2 ? 1 : 2) : 0;
+    const int want_layout = (rp.mode == 2) ? LAYOUT_PLANAR_PARITY : LAYOUT_PLANAR;
+    rp.d = PlanarDims::make(q.t.H, q.t.W, q.t.C, want_layout);
+    if (q.t.layout == LAYOUT_NHWC) {
+      // operand produced by an NHWC kernel: converted before every launch into a private planar buffer
+      stage_in_[i].alloc(rp.d.bytes(N));
+      CUDA_CHECK(cudaMemset(stage_in_[i].p, 0, stage_in_[i].bytes));
+      relayouts_.push_back(Relayout{q.t.ptr, stage_in_[i].p, N, q.t.H, q.t.W, q.t.C, want_layout});
+      rp.base = stage_in_[i].as<uint8_t>();
+    } else {
+      WSI_REQUIRE(q.t.layout == want_layout, WSI_ERR_INVALID, "row conv: operand %zu has layout %d, needs %d", i, q.t.layout, want_layout);
+      rp.base = static_cast<const uint8_t*>(q.t.ptr);
+    }
     if (rp.mode == 2) {
       WSI_REQUIRE(q.t.H == OH && q.t.W == OW && q.t.N == N, WSI_ERR_INVALID, "row conv: skip shape mismatch");
       has_skip = true;
     }
-    for (int kc0 = 0; kc0 < q.t.C / 8; kc0 += 2) {
-      p.slab_part[p.nslabs] = (int8_t)i;
-      p.slab_kc0[p.nslabs] = (int16_t)kc0;
-      ++p.nslabs;
-    }
+    rp.nslabs = q.t.C / 16;
+    p.nslabs += rp.nslabs;
     cin += q.t.C;
   }
   p.N = N; p.OH = OH; p.OW = OW; p.Cout = BN; p.up2 = up2 ? 1 : 0;
@@ -356,18 +374,40 @@ void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& s
   WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "row conv: too many tiles");
   p.total_tiles = (int)total;
   p.relu = spec.relu ? 1 : 0;
-  p.out = static_cast<bf16*>(out);
+  p.out = static_cast<uint8_t*>(out);
+  p.out_layout = out_layout;
+  WSI_REQUIRE(out_layout == LAYOUT_NHWC || out_layout == LAYOUT_PLANAR, WSI_ERR_INVALID, "row conv: bad output layout");
+  p.od = PlanarDims::make(OH, OW, BN, LAYOUT_PLANAR);
   p.error_flag = error_flag;
 
-  // weights: [slab][tap][2 chunks][BN][8]
+  // A-operand start offsets of every tap relative to the stage base, in 16-byte units
+  auto fl2 = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };
+  for (int mode = 0; mode < 3; ++mode)
+    for (int py = 0; py < 2; ++py)
+      for (int g = 0; g < 2; ++g)
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, s = tap % 3;
+          int par = 0, poff;
+          if (mode == 0) {
+            poff = r * kRowHaloCols + s;
+          } else if (mode == 1) {
+            poff = (fl2(py + r - 1) + 1) * kRowHaloCols + (fl2(g + s - 1) + 1);
+          } else {
+            const int q = g + s - 1;
+            par = q & 1;
+            poff = r * kRowHaloCols + (fl2(q) + 1);
+          }
+          p.adelta[mode][py][g][tap] = (uint16_t)((par * 2 * kRowPlaneBytes + poff * 16) >> 4);
+        }
+
+  // weights: [slab][tap][2 chunks][BN][8]; slabs enumerate the concatenated input channels in order
   std::vector<uint16_t> wp((size_t)p.nslabs * 9 * 2 * BN * 8);
-  int part_off[2] = {0, parts[0].t.C};
   for (int sl = 0; sl < p.nslabs; ++sl)
     for (int tap = 0; tap < 9; ++tap)
       for (int j = 0; j < 2; ++j)
         for (int n = 0; n < BN; ++n)
           for (int e = 0; e < 8; ++e) {
-            const int ci = part_off[p.slab_part[sl]] + (p.slab_kc0[sl] + j) * 8 + e;
+            const int ci = sl * 16 + j * 8 + e;
             const float v = w_oihw[(((size_t)n * cin + ci) * 3 + tap / 3) * 3 + tap % 3];
             wp[((((size_t)sl * 9 + tap) * 2 + j) * BN + n) * 8 + e] = f32_to_bf16_bits(v);
           }
@@ -390,7 +430,7 @@ void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& s
   p.stage_bytes = (has_skip ? 4 : 2) * kRowPlaneBytes;
   const int w_bytes = p.nslabs * 9 * 2 * BN * 16;
   const int fixed = 128 + ((w_bytes + (2 * BN + 68) * 4 + 127) & ~127) + 512;
-  p.stages = std::min(8, (224 * 1024 - fixed) / p.stage_bytes);   // 3 KB left for the static tables
+  p.stages = std::min(8, (226 * 1024 - fixed) / p.stage_bytes);
   WSI_REQUIRE(p.stages >= 2, WSI_ERR_UNSUPPORTED, "row conv: not enough shared memory for 2 stages");
   smem_ = fixed + p.stages * p.stage_bytes;
   grid_ = (int)std::min<long long>(total, num_sms);
@@ -401,7 +441,7 @@ template <int BN, bool HEAD, int G>
 static void launch_row(const RowParams& p, int grid, int smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_rowtile_kernel<BN, HEAD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_rowtile_kernel<BN, HEAD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
   conv_rowtile_kernel<BN, HEAD, G><<<grid, kRowThreads, smem, s>>>(p);
@@ -409,6 +449,7 @@ static void launch_row(const RowParams& p, int grid, int smem, cudaStream_t s) {
 }
 
 void RowConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
+  for (auto& r : relayouts_) launch_relayout_planar(r.src, r.dst, r.N, r.H, r.W, r.C, r.layout, stream, lc);
   const bool head = p_.head_out != nullptr;
   if (p_.Cout == 16) {
     if (p_.up2) { if (head) launch_row<16, true, 2>(p_, grid_, smem_, stream); else launch_row<16, false, 2>(p_, grid_, smem_, stream); }

@@ -1,38 +1,59 @@
 // conv_rowtile.cuh — 3x3/s1 convolution for the high-resolution, small-channel layers (sm_100a).
 //
 // The decoder's last levels (smp Unet: 128->32->32 @ H/2, 32->16->16 @ H) have
-// 16..64 channels per operand and 16/32 output channels.  Per-tap TMA boxes would move one
-// 32..128-byte row per pixel per tap (9x re-reads, TMA box-row rate bound: measured 4 cycles/row).
-// Here a tile is 128 consecutive pixels of ONE output row and its 3 x 130 pixel halo is loaded
-// ONCE with 16-byte cp.async (LDGSTS, zero-fill = conv padding) into channel-chunk planes
-//     plane[kc][row 0..2][col 0..129][16 B]            (kc = 8-channel chunk)
-// which is the canonical NO-SWIZZLE K-major UMMA layout with SBO = 128 B (rows are linear at 16 B
-// pitch) and LBO = plane stride.  Every filter tap (r,s) is then just a different descriptor START
-// ADDRESS (+ (r*130+s)*16 B) into the same smem — no data is re-read or re-arranged.
-//   * nearest x2 upsample: output pixels are processed per column parity; the source planes hold
-//     the half-resolution rows, tap offsets become floor((parity+tap-1)/2).
-//   * the skip operand of an upsample+concat conv is de-interleaved into even/odd column planes.
+// 16..64 channels per operand and 16/32 output channels.  Per-tap TMA boxes move one 32..128-byte
+// row per pixel per tap (9x re-reads, bound by the TMA box-row rate: measured ~4 cycles/row), and
+// 16-byte cp.async producers starve for memory-level parallelism (measured 2 TB/s).  Instead:
+//
+//   * these activations live in HBM in a zero-padded CHANNEL-CHUNK-PLANAR layout
+//         [N][H+2][C/8][W+2][8 ch]                                  (LAYOUT_PLANAR)
+//     so that a halo row of one 8-channel chunk is ONE contiguous run, and the conv zero padding is
+//     simply there.  The skip operand of an upsample+concat conv is additionally de-interleaved by
+//     column parity: [N][H+2][C/8][2][W/2+1][8]                      (LAYOUT_PLANAR_PARITY)
+//   * a tile = 128 consecutive pixels of ONE output row (x2-upsampling convs: 256 pixels = two column
+//     parity groups).  Its 3 x 130 pixel halo is fetched ONCE per 16-channel slab by 6 (12) bulk
+//     copies (cp.async.bulk, TMA engine, mbarrier complete_tx) issued by the lanes of one warp into
+//         plane[kc][row 0..2][col 0..129][16 B]
+//     — the canonical NO-SWIZZLE K-major UMMA layout with SBO = 128 B (rows linear at 16 B pitch),
+//     LBO = plane stride.  Every filter tap (r,s) is then only a different descriptor START ADDRESS
+//     (+ (r*130+s)*16 B): nothing is re-read or re-arranged.  For x2-nearest sources the planes hold
+//     the half-resolution rows and tap offsets become floor((parity+tap-1)/2).
 //   * the whole weight tensor (<= 74 KB) stays resident in smem for the life of the persistent CTA.
-//   * warps 0-5: cp.async producers (one halo-row task each); warp 6: MMA issuer (+TMEM alloc); warps 7-10: epilogue
-//     (folded BN + ReLU + bf16 store, or the fused 1x1 `final_conv` head -> fp32 logits).
+//   * warp 0: bulk-copy producer; warp 1: MMA issuer (+TMEM alloc); warps 2-5: epilogue (folded BN +
+//     ReLU + bf16 store in planar or NHWC layout, or the fused 1x1 `final_conv` head -> fp32 logits).
 #pragma once
 #include "conv_igemm.cuh"
 
 namespace wsi {
 
 constexpr int kRowHaloCols = 130;
-constexpr int kRowPlanePx = 3 * kRowHaloCols;            // 390 pixels
-constexpr int kRowPlaneBytes = 6304;                     // 390*16 = 6240, padded so planes land 32 B apart mod 128 (banks)
-constexpr int kRowProducerWarps = 6;
-constexpr int kRowProducers = kRowProducerWarps * 32;
-constexpr int kRowThreads = (kRowProducerWarps + 1 + 4) * 32;
+constexpr int kRowPlaneBytes = 3 * kRowHaloCols * 16;    // 6240: [3 rows][130 cols][16 B]
+constexpr int kRowThreads = 6 * 32;
 constexpr int kRowMaxSlabs = 8;
-constexpr int kRowAccStages = 4;                        // TMEM accumulator ring depth
+constexpr int kRowAccStages = 4;                         // TMEM accumulator ring depth
+
+// geometry of the planar layouts (host + device)
+struct PlanarDims {
+  int H, W, KC, P, Wrow;   // P = 1 (plain) or 2 (column-parity planes); Wrow = entries per chunk row
+  __host__ __device__ static PlanarDims make(int H_, int W_, int C_, int layout) {
+    PlanarDims d;
+    d.H = H_; d.W = W_; d.KC = C_ / 8;
+    d.P = (layout == LAYOUT_PLANAR_PARITY) ? 2 : 1;
+    d.Wrow = (layout == LAYOUT_PLANAR_PARITY) ? (W_ / 2 + 1) : (W_ + 2);
+    return d;
+  }
+  // byte offset of entry 0 of chunk row (n, y in [-1,H], kc, par)
+  __host__ __device__ size_t row_off(int n, int y, int kc, int par) const {
+    return (((((size_t)n * (H + 2) + (size_t)(y + 1)) * KC + kc) * P + par) * (size_t)Wrow) * 16;
+  }
+  __host__ __device__ size_t bytes(int N_) const { return (size_t)N_ * (H + 2) * KC * P * Wrow * 16; }
+};
 
 struct RowPart {
-  const bf16* ptr;   // NHWC source
-  int H, W, C;       // source extents (half resolution for mode 1)
-  int mode;          // 0 plain, 1 nearest-x2 source, 2 skip operand of an x2 conv (parity planes)
+  const uint8_t* base;   // planar tensor
+  PlanarDims d;
+  int mode;              // 0 plain, 1 nearest-x2 source (half res), 2 skip operand of an x2 conv (parity planes)
+  int nslabs;            // C / 16
 };
 
 struct RowParams {
@@ -41,15 +62,16 @@ struct RowParams {
   int N, OH, OW, Cout;
   int up2;                       // output tile = 256 px (two column parities) instead of 128
   int tiles_x, total_tiles;
-  int nslabs;                    // 16-channel slabs per tile
-  int8_t slab_part[kRowMaxSlabs];
-  int16_t slab_kc0[kRowMaxSlabs];   // first 8-channel chunk of the slab inside its part
+  int nslabs;                    // 16-channel slabs per tile (all parts)
   int stages, stage_bytes;
+  uint16_t adelta[3][2][2][9];   // [mode][output row parity][column parity group][tap]: A start offset, 16-byte units
   const bf16* w;                 // [slab][tap][2][BN][8] bf16
   const float* scale;            // [BN]
   const float* bias;             // [BN]
   int relu;
-  bf16* out;                     // NHWC [N,OH,OW,BN] or nullptr
+  uint8_t* out;                  // bf16 output, or nullptr
+  int out_layout;                // LAYOUT_NHWC or LAYOUT_PLANAR
+  PlanarDims od;                 // geometry of a planar output
   const float* head_w;           // [4][16] or nullptr
   const float* head_b;
   float* head_out;               // [N,OH,OW,4] fp32
@@ -60,17 +82,25 @@ class RowConvOp {
  public:
   // true if this conv can run on the row-tile kernel
   static bool eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual);
+  // parts / out may be NHWC (converted by an internal relayout launch; output written NHWC) or planar.
   void build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw, const float* scale,
-             const float* bias, void* out, const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms);
+             const float* bias, void* out, int out_layout, const float* head_w, const float* head_b, float* head_out,
+             int* error_flag, int num_sms);
   void launch(cudaStream_t stream, LaunchCounter* lc) const;
   double flops() const { return flops_; }
   int block_n() const { return p_.Cout; }
 
  private:
+  struct Relayout { const void* src; void* dst; int N, H, W, C, layout; };
   RowParams p_{};
-  DevBuf w_, scale_, bias_, headw_, headb_;
+  DevBuf w_, scale_, bias_, headw_, headb_, stage_in_[2];
+  std::vector<Relayout> relayouts_;
   int grid_ = 0, smem_ = 0;
   double flops_ = 0;
 };
+
+// NHWC bf16 -> padded planar (interior only; the zero border is written once at allocation)
+void launch_relayout_planar(const void* src_nhwc, void* dst, int N, int H, int W, int C, int layout, cudaStream_t s,
+                            LaunchCounter* lc);
 
 }  // namespace wsi

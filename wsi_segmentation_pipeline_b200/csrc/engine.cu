@@ -12,6 +12,7 @@
 #include <numeric>
 
 #include "conv_igemm.cuh"
+#include "conv_rowtile.cuh"
 #include "kernels.cuh"
 
 namespace wsi {
@@ -29,11 +30,15 @@ struct HostTensor {
   }
 };
 
-struct Act {  // bf16 NHWC activation in HBM
+struct Act {  // bf16 activation in HBM: NHWC, or zero-padded channel-chunk-planar around the row-tile kernel
   DevBuf buf;
   int N = 0, H = 0, W = 0, C = 0;
-  TensorView view() const { return TensorView{buf.p, N, H, W, C}; }
-  size_t bytes() const { return (size_t)N * H * W * C * 2; }
+  int layout = LAYOUT_NHWC;
+  TensorView view() const { return TensorView{buf.p, N, H, W, C, layout}; }
+  size_t bytes() const {
+    if (layout == LAYOUT_NHWC) return (size_t)N * H * W * C * 2;
+    return PlanarDims::make(H, W, C, layout).bytes(N);
+  }
 };
 
 enum StageId { ST_GATHER = 0, ST_STEM, ST_MAXPOOL, ST_CONV, ST_HEAD, ST_STITCH, ST_FINALISE, ST_H2D, ST_D2H, ST_COUNT };
@@ -194,11 +199,12 @@ struct NetPlan {
   void print_trace();
   ~NetPlan() { if (trace) { resolve_trace(); print_trace(); } }
 
-  Act* new_act(int N, int H, int W, int C) {
+  Act* new_act(int N, int H, int W, int C, int layout = LAYOUT_NHWC) {
     acts.emplace_back(new Act());
     Act* a = acts.back().get();
-    a->N = N; a->H = H; a->W = W; a->C = C;
+    a->N = N; a->H = H; a->W = W; a->C = C; a->layout = layout;
     a->buf.alloc(a->bytes());
+    if (layout != LAYOUT_NHWC) CUDA_CHECK(cudaMemset(a->buf.p, 0, a->buf.bytes));   // the zero border IS the conv padding
     return a;
   }
   ConvOp* new_op() {
@@ -246,7 +252,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
                       const Act* res, Act* out, const float* hw = nullptr, const float* hb = nullptr, float* hout = nullptr) {
     ConvOp* op = new_op();
     op->build(parts, spec, w, f ? f->scale.data() : nullptr, f ? f->bias.data() : nullptr, res ? res->buf.p : nullptr,
-              out ? out->buf.p : nullptr, hw, hb, hout, ef, sms);
+              out ? out->buf.p : nullptr, hw, hb, hout, ef, sms, out ? out->layout : LAYOUT_NHWC);
     steps.push_back(Step{0, ST_CONV, op, nullptr, out});
     conv_flops += op->flops();
     char d[160];
@@ -307,6 +313,29 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
   if (head == WSI_HEAD_SEG) {
     // ---- smp Unet decoder: 5 x {nearest x2, concat skip, 2 x (conv3x3 + BN + ReLU)}, final 1x1 (+bias) ----
     const int outs[5] = {256, 128, 64, 32, 16};
+    // The ten decoder convs form a chain; a conv writes the planar layout iff it and its consumer both run
+    // on the row-tile kernel (the small-channel, high-resolution end of the decoder).
+    struct DConv { std::vector<ConvInputPart> parts; ConvSpec sp; bool row; };
+    auto probe_part = [](int N, int H, int W, int C, bool up2) { return ConvInputPart{TensorView{nullptr, N, H, W, C, LAYOUT_NHWC}, up2}; };
+    std::vector<DConv> plan;
+    {
+      int xh = x4->H, xw = x4->W, xc = x4->C;
+      for (int i = 1; i <= 5; ++i) {
+        Act* skip = (i <= 4) ? feats[i] : nullptr;
+        const int co = outs[i - 1];
+        if (skip) WSI_REQUIRE(skip->H == 2 * xh && skip->W == 2 * xw, WSI_ERR_UNSUPPORTED, "decoder level %d: skip shape mismatch", i);
+        DConv a, b;
+        a.parts.push_back(probe_part(cap, xh, xw, xc, true));
+        if (skip) a.parts.push_back(probe_part(cap, skip->H, skip->W, skip->C, false));
+        a.sp.ksize = 3; a.sp.stride = 1; a.sp.pad = 1; a.sp.cout = co; a.sp.relu = true;
+        b.parts.push_back(probe_part(cap, 2 * xh, 2 * xw, co, false));
+        b.sp = a.sp; b.sp.head = (i == 5);
+        a.row = ConvOp::routes_to_rowtile(a.parts, a.sp, nullptr);
+        b.row = ConvOp::routes_to_rowtile(b.parts, b.sp, nullptr);
+        plan.push_back(a); plan.push_back(b);
+        xh *= 2; xw *= 2; xc = co;
+      }
+    }
     Act* x = x4;
     logits.alloc((size_t)cap * ph * pw * 4 * sizeof(float));
     for (int i = 1; i <= 5; ++i) {
@@ -314,29 +343,28 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
       const int co = outs[i - 1];
       const int ci = x->C + (skip ? skip->C : 0);
       const std::string q = "decoder.layer" + std::to_string(i) + ".block.";
-      if (skip) WSI_REQUIRE(skip->H == 2 * x->H && skip->W == 2 * x->W, WSI_ERR_UNSUPPORTED, "decoder level %d: skip shape mismatch", i);
-      Act* a = new_act(cap, 2 * x->H, 2 * x->W, co);
+      const size_t ia = 2 * (size_t)(i - 1), ib = ia + 1;
+      const bool a_planar = plan[ia].row && plan[ib].row;
+      const bool b_planar = (ib + 1 < plan.size()) && plan[ib].row && plan[ib + 1].row;
+      Act* a = new_act(cap, 2 * x->H, 2 * x->W, co, a_planar ? LAYOUT_PLANAR : LAYOUT_NHWC);
       {
         const HostTensor& w = conv_weight(c, q + "0.block.0.weight", co, ci, 3);
         const Folded f = fold_bn(c, q + "0.block.1", co);
-        ConvSpec sp; sp.ksize = 3; sp.stride = 1; sp.pad = 1; sp.cout = co; sp.relu = true;
         std::vector<ConvInputPart> parts{ConvInputPart{x->view(), true}};
         if (skip) parts.push_back(ConvInputPart{skip->view(), false});
-        add_conv(parts, sp, w.data.data(), &f, nullptr, a);
+        add_conv(parts, plan[ia].sp, w.data.data(), &f, nullptr, a);
       }
       const HostTensor& w = conv_weight(c, q + "1.block.0.weight", co, co, 3);
       const Folded f = fold_bn(c, q + "1.block.1", co);
-      ConvSpec sp; sp.ksize = 3; sp.stride = 1; sp.pad = 1; sp.cout = co; sp.relu = true;
       if (i < 5) {
-        Act* b = new_act(cap, a->H, a->W, co);
-        add_conv({ConvInputPart{a->view(), false}}, sp, w.data.data(), &f, nullptr, b);
+        Act* b = new_act(cap, a->H, a->W, co, b_planar ? LAYOUT_PLANAR : LAYOUT_NHWC);
+        add_conv({ConvInputPart{a->view(), false}}, plan[ib].sp, w.data.data(), &f, nullptr, b);
         x = b;
       } else {
         const HostTensor& fw = conv_weight(c, "decoder.final_conv.weight", 4, 16, 1);
         const HostTensor& fb = weight(c, "decoder.final_conv.bias");
         WSI_REQUIRE(fb.numel() == 4, WSI_ERR_NOMODEL, "decoder.final_conv.bias must have 4 entries");
-        sp.head = true;
-        add_conv({ConvInputPart{a->view(), false}}, sp, w.data.data(), &f, nullptr, nullptr, fw.data.data(), fb.data.data(),
+        add_conv({ConvInputPart{a->view(), false}}, plan[ib].sp, w.data.data(), &f, nullptr, nullptr, fw.data.data(), fb.data.data(),
                  logits.as<float>());
       }
     }
