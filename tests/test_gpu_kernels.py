@@ -171,8 +171,19 @@ def test_conv_upsample_concat(ctx, case):
     xin = F.interpolate(_bf16_round(x), scale_factor=2, mode="nearest")
     if cskip:
         xin = torch.cat([xin, _bf16_round(skip)], 1)
-    ref = F.relu(F.conv2d(xin, _bf16_round(wt).cuda(), None, 1, 1) * scale.cuda().view(1, -1, 1, 1) + bias.cuda().view(1, -1, 1, 1))
-    _assert_close_bf16(_nchw_f32(y), ref, f"up conv {case}")
+    sc, bi = scale.cuda().view(1, -1, 1, 1), bias.cuda().view(1, -1, 1, 1)
+    # The row-tile kernel sums the taps that read the same half-resolution pixel BEFORE rounding the weight to
+    # bf16, so the reference uses the fp32 weights and the tolerance carries the rigorous weight-rounding bound
+    # 2^-8 * (|x| conv |w|) next to the one-ulp output rounding.
+    ref = F.relu(F.conv2d(xin, wt.cuda(), None, 1, 1) * sc + bi)
+    wbound = F.conv2d(xin.abs(), wt.abs().cuda(), None, 1, 1) * sc.abs() * 2.0 ** -8
+    got = _nchw_f32(y)
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -7 + wbound + 1e-3
+    assert not (err > tol).any(), f"up conv {case}: {int((err > tol).sum())} mismatches, max err {err.max().item():.4g}"
+    # and statistically it must be as good as a faithful bf16 evaluation
+    ref16 = F.relu(F.conv2d(xin, _bf16_round(wt).cuda(), None, 1, 1) * sc + bi)
+    assert (got - ref).abs().mean() <= 1.5 * (_bf16_round(ref16) - ref).abs().mean() + 1e-4
 
 
 @pytest.mark.parametrize("ph,pw,n", [(64, 64, 5), (256, 256, 2), (32, 96, 3)])

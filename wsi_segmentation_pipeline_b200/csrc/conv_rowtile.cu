@@ -41,13 +41,16 @@ struct TileCoord {
       if (++y == OH) { y = 0; ++n; }
     }
   }
+  __device__ __forceinline__ void advance(int k, int tiles_x, int OH) {
+    for (int i = 0; i < k; ++i) next(tiles_x, OH);
+  }
 };
 
 template <int BN, bool HEAD, int G>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __grid_constant__ RowParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  const int w_bytes = p.nslabs * 9 * 2 * BN * 16;
+  const int w_bytes = p.w_blocks * 2 * BN * 16;
   uint8_t* s_w = smem;
   float* s_scale = reinterpret_cast<float*>(smem + w_bytes);
   float* s_bias = s_scale + BN;
@@ -63,8 +66,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S + 2 * kRowAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // accumulator ring: kRowAccStages tiles in flight between the MMA issuer and the epilogue
-  constexpr uint32_t kTmemCols = kRowAccStages * G * BN;
+  // accumulator ring: kRowAccStages tiles in flight between the MMA issuer and the epilogue.  Back-to-back
+  // MMAs into the same TMEM columns serialise on the accumulate dependency (~120 vs ~60 cycles per small
+  // MMA, measured), so consecutive issues always alternate accumulators: the two column-parity groups
+  // when G == 2, two partial sums (added in the epilogue) when G == 1.
+  constexpr int NA = (G == 1) ? 2 : 1;
+  static_assert(G * NA == 2, "two accumulators per tile, one per MMA warp");
+  constexpr uint32_t kTmemCols = kRowAccStages * G * NA * BN;
   static_assert(kTmemCols >= 32 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
 
   // resident weights + epilogue constants (generic-proxy writes, read by the async proxy -> fence)
@@ -82,16 +90,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
-      ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], 1);
+      ptx::mbar_init(&full[i], kRowProducerWarps);   // one arrive.expect_tx per producer warp
+      ptx::mbar_init(&empty[i], kRowMmaWarps);       // one tcgen05.commit per MMA warp
     }
     for (int i = 0; i < kRowAccStages; ++i) {
-      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_full[i], kRowMmaWarps);
       ptx::mbar_init(&tmem_empty[i], 128);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_holder, kTmemCols);
+  if (warp == kRowProducerWarps) ptx::tmem_alloc(tmem_holder, kTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -101,11 +109,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
   const int t_begin = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
   const int t_end = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp == 0) {
-    // ================================ bulk-copy producer ================================
-    // One 16-channel slab = 2 chunk planes x 3 halo rows (x 2 column parities for the skip operand):
-    // lane l issues copy l, all lanes at once; lane 0 arms the barrier with the byte total.
-    const int ry = lane % 3, kc = (lane / 3) & 1, par = lane / 6;
+  if (warp < kRowProducerWarps) {
+    // ================================ bulk-copy producers ================================
+    // A lone warp issues ~1 dependent instruction per 8-10 cycles, so the roles are spread: producer warp w
+    // owns halo row w of every slab; its lanes (chunk kc, column parity) issue the row's 2 (4) bulk copies.
+    const int ry = warp, kc = lane & 1, par = lane >> 1;
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t stage0 = ptx::smem_u32(s_stage);
@@ -117,17 +125,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
       for (int pi = 0; pi < p.nparts; ++pi) {
         const RowPart& pt = p.part[pi];
         const int mode = pt.mode;
-        const int ncopies = (mode == 2) ? 12 : 6;
+        const int ncopies = (mode == 2) ? 4 : 2;
         const int sy = ((mode == 1) ? (tc.y >> 1) : tc.y) - 1 + ry;            // in [-1, H]: the padded layout holds it
-        // entries: plain / x2 source: columns b0-1 .. b0+128 = indices b0 .. b0+129; skip even plane: indices
-        // b0 .. b0+128 into halo cols 1..129; skip odd plane: indices b0 .. b0+128 into halo cols 0..128
-        const int want = (mode == 2) ? 129 : 130;
-        const int n_ent = min(want, pt.d.Wrow - b0);
+        // halo col c <-> source column b0 - 8 + c = entry b0 + c of the padded row: source and destination
+        // are both 128-byte aligned and the length is a multiple of 128 B (Wrow is a multiple of 8)
+        const int n_ent = min(kRowHaloCols, pt.d.Wrow - b0);
         const uint32_t bytes = (uint32_t)n_ent * 16u;
-        const uint32_t dcol = (mode == 2 && par == 0) ? 16u : 0u;
-        const uint32_t dst_l = (uint32_t)((par * 2 + kc) * kRowPlaneBytes + ry * (kRowHaloCols * 16)) + dcol;
         const bool active = lane < ncopies;
-        const uint8_t* src_l = pt.base + pt.d.row_off(tc.n, active ? sy : 0, kc, (mode == 2 && active) ? par : 0) + (size_t)b0 * 16;
+        const uint32_t dst_l = (uint32_t)(((active ? par : 0) * 2 + kc) * kRowPlaneBytes + ry * (kRowHaloCols * 16));
+        const uint8_t* src_l = pt.base + pt.d.row_off(tc.n, sy, kc, (mode == 2 && active) ? par : 0) + (size_t)b0 * 16;
         const size_t slab_step = (size_t)2 * pt.d.P * pt.d.Wrow * 16;            // two 8-channel chunks further
         for (int j = 0; j < pt.nslabs; ++j) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 11);
@@ -138,16 +144,20 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ========================================
-    // every operand of the issue loop comes from kernel parameters / constants (uniform datapath); the
-    // TMEM base read from smem is made warp-uniform with a redux so no per-MMA R2UR waterfall is needed
+  } else if (warp < kRowProducerWarps + kRowMmaWarps) {
+    // ================================ MMA issuers (2 warps) =============================
+    // MMA warp m owns accumulator m of every tile: the column-parity group g = m when G == 2, the partial
+    // sum over taps of parity m when G == 1 (the epilogue adds the two partials).  Consecutive MMAs into one
+    // accumulator serialise, two issuing threads interleave naturally.  All operands come from kernel
+    // parameters / constants (uniform datapath); the TMEM base is made warp-uniform with a redux.
+    const int m = warp - kRowProducerWarps;
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_holder);
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16<BN>();
       const uint64_t a_desc0 = make_nosw_desc(ptx::smem_u32(s_stage), kRowPlaneBytes, 128);
       const uint64_t b_desc0 = make_nosw_desc(ptx::smem_u32(s_w), BN * 16, 128);
       const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+      const int g = (G == 2) ? m : 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -158,22 +168,34 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
         const int py = tc.y & 1;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 12);
         ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 2 + m) * BN);
         int sl = 0;
 #pragma unroll 1
         for (int pi = 0; pi < p.nparts; ++pi) {
           const int mode = p.part[pi].mode;
           for (int j = 0; j < p.part[pi].nslabs; ++j, ++sl) {
             const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)stage * stage_units);
-            const uint64_t b_sl = b_desc0 + (uint64_t)(sl * 9 * 2 * BN);
+            const uint64_t b_sl = b_desc0 + (uint64_t)(p.slab_wblock[sl] * 2 * BN);
             ptx::mbar_wait(&full[stage], phase, p.error_flag, 13);
             ptx::tc_fence_after();
+            if (mode == 1) {
+              // nearest x2 source (G == 2): the 9 taps touch only 2 x 2 distinct half-resolution positions; their
+              // weights were summed per (row parity, column parity) on the host -> 4 MMAs instead of 9
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
+              for (int pos = 0; pos < 4; ++pos)
+                ptx::umma_bf16(d_tmem, a_st + (uint64_t)p.adelta_up[py][g][pos], b_sl + (uint64_t)((((py * 2 + g) * 4) + pos) * 2 * BN), idesc,
+                               (uint32_t)((sl | pos) != 0));
+            } else if (G == 2) {
 #pragma unroll
-              for (int g = 0; g < G; ++g) {
-                ptx::umma_bf16(tmem_base + (uint32_t)((acc * G + g) * BN), a_st + (uint64_t)p.adelta[mode][py][g][tap],
-                               b_sl + (uint64_t)(tap * 2 * BN), idesc, (uint32_t)((sl | tap) != 0));
-              }
+              for (int tap = 0; tap < 9; ++tap)
+                ptx::umma_bf16(d_tmem, a_st + (uint64_t)p.adelta[mode][py][g][tap], b_sl + (uint64_t)(tap * 2 * BN), idesc,
+                               (uint32_t)((sl | tap) != 0));
+            } else {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap)
+                if ((tap & 1) == m)
+                  ptx::umma_bf16(d_tmem, a_st + (uint64_t)p.adelta[mode][py][0][tap], b_sl + (uint64_t)(tap * 2 * BN), idesc,
+                                 (uint32_t)(sl != 0 || tap >= 2));
             }
             ptx::umma_commit(&empty[stage]);
             if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -186,8 +208,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
   } else {
     // ================================ epilogue (4 warps) ================================
     // folded-BN constants and the fused 1x1 head live in registers for the life of the CTA
+    // two groups of 4 warps alternate tiles (group e drains accumulator stages e, e+2), so the epilogue of
+    // tile t overlaps the epilogue of tile t+1 as well as the MMAs of t+2..
     const uint32_t tmem_base = *tmem_holder;
     const int q = warp & 3;
+    const int egrp = (warp - kRowProducerWarps - kRowMmaWarps) >> 2;
     const int row = q * 32 + lane;
     float r_scale[BN], r_bias[BN];
 #pragma unroll
@@ -202,11 +227,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
     const float lo = p.relu ? 0.f : -INFINITY;
     const bool planar_out = (p.out_layout == LAYOUT_PLANAR);
     const size_t chunk_step = (size_t)p.od.Wrow * 16;
-    int acc = 0;
+    int acc = egrp;
     uint32_t acc_phase = 0;
     TileCoord tc;
-    tc.init(t_begin, p.tiles_x, p.OH);
-    for (int tile = t_begin; tile < t_end; ++tile, tc.next(p.tiles_x, p.OH)) {
+    tc.init(t_begin + egrp, p.tiles_x, p.OH);
+    for (int tile = t_begin + egrp; tile < t_end; tile += kRowEpiGroups, tc.advance(kRowEpiGroups, p.tiles_x, p.OH)) {
       const size_t rowpix = ((size_t)tc.n * p.OH + tc.y) * p.OW;
       ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 14);
       ptx::tc_fence_after();
@@ -215,14 +240,17 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
         const int x = (G == 2) ? (2 * (tc.xb * 128 + row) + g) : (tc.xb * 128 + row);
         const bool valid = x < p.OW;
         const size_t pix = rowpix + x;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * G + g) * BN);
-        uint32_t v[BN];
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * G + g) * NA * BN);
+        uint32_t v[NA * BN];
 #pragma unroll
-        for (int c = 0; c < BN; c += 16) ptx::tmem_ld16(t_row + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+        for (int c = 0; c < NA * BN; c += 16) ptx::tmem_ld16(t_row + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
         ptx::tmem_ld_wait();
         float yv[BN];
 #pragma unroll
-        for (int j = 0; j < BN; ++j) yv[j] = fmaxf(fmaf(__uint_as_float(v[j]), r_scale[j], r_bias[j]), lo);
+        for (int j = 0; j < BN; ++j) {
+          const float a = (NA == 2) ? (__uint_as_float(v[j]) + __uint_as_float(v[BN + j])) : __uint_as_float(v[j]);
+          yv[j] = fmaxf(fmaf(a, r_scale[j], r_bias[j]), lo);
+        }
         if (HEAD) {
           float4 o;
           float* op = reinterpret_cast<float*>(&o);
@@ -253,7 +281,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
           }
           if (planar_out) {
             // chunk rows are contiguous along x: consecutive lanes write consecutive 16-byte entries
-            uint8_t* o = p.out + p.od.row_off(tc.n, tc.y, 0, 0) + (size_t)(x + 1) * 16;
+            uint8_t* o = p.out + p.od.row_off(tc.n, tc.y, 0, 0) + (size_t)(x + kRowPad) * 16;
 #pragma unroll
             for (int j = 0; j < BN / 8; ++j) *reinterpret_cast<uint4*>(o + j * chunk_step) = w4[j];
           } else {
@@ -265,13 +293,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
-      if (++acc == kRowAccStages) { acc = 0; acc_phase ^= 1u; }
+      acc += kRowEpiGroups;
+      if (acc >= kRowAccStages) { acc -= kRowAccStages; acc_phase ^= 1u; }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kRowProducerWarps) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(*tmem_holder, kTmemCols);
   }
@@ -293,8 +322,8 @@ __global__ void __launch_bounds__(256) relayout_planar_kernel(const uint4* __res
     const int n = (int)(r / H);
     const uint4 v = __ldg(src + i);
     size_t off;
-    if (layout == LAYOUT_PLANAR_PARITY) off = d.row_off(n, y, kc, x & 1) + (size_t)((x + 1) >> 1) * 16;   // even x -> x/2, odd x -> (x+1)/2
-    else off = d.row_off(n, y, kc, 0) + (size_t)(x + 1) * 16;
+    if (layout == LAYOUT_PLANAR_PARITY) off = d.row_off(n, y, kc, x & 1) + (size_t)((x >> 1) + kRowPad) * 16;
+    else off = d.row_off(n, y, kc, 0) + (size_t)(x + kRowPad) * 16;
     *reinterpret_cast<uint4*>(dst + off) = v;
   }
 }
@@ -388,29 +417,60 @@ void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& s
         for (int tap = 0; tap < 9; ++tap) {
           const int r = tap / 3, s = tap % 3;
           int par = 0, poff;
+          // halo col c holds source column b0 - kRowPad + c (parity planes: half-index b0 - kRowPad + c)
           if (mode == 0) {
-            poff = r * kRowHaloCols + s;
+            poff = r * kRowHaloCols + (s - 1 + kRowPad);
           } else if (mode == 1) {
-            poff = (fl2(py + r - 1) + 1) * kRowHaloCols + (fl2(g + s - 1) + 1);
+            poff = (fl2(py + r - 1) + 1) * kRowHaloCols + (fl2(g + s - 1) + kRowPad);
           } else {
-            const int q = g + s - 1;
+            const int q = g + s - 1;          // source column 2(b0+i) + q: parity q&1, half-index b0 + i + floor(q/2)
             par = q & 1;
-            poff = r * kRowHaloCols + (fl2(q) + 1);
+            poff = r * kRowHaloCols + (fl2(q) + kRowPad);
           }
           p.adelta[mode][py][g][tap] = (uint16_t)((par * 2 * kRowPlaneBytes + poff * 16) >> 4);
         }
 
-  // weights: [slab][tap][2 chunks][BN][8]; slabs enumerate the concatenated input channels in order
-  std::vector<uint16_t> wp((size_t)p.nslabs * 9 * 2 * BN * 8);
-  for (int sl = 0; sl < p.nslabs; ++sl)
-    for (int tap = 0; tap < 9; ++tap)
-      for (int j = 0; j < 2; ++j)
-        for (int n = 0; n < BN; ++n)
-          for (int e = 0; e < 8; ++e) {
-            const int ci = sl * 16 + j * 8 + e;
-            const float v = w_oihw[(((size_t)n * cin + ci) * 3 + tap / 3) * 3 + tap % 3];
-            wp[((((size_t)sl * 9 + tap) * 2 + j) * BN + n) * 8 + e] = f32_to_bf16_bits(v);
-          }
+  // weights: per slab a run of [block][2 chunks][BN][8] bf16; slabs enumerate the concatenated input channels in
+  // order.  Plain / skip slabs: 9 blocks = the 9 taps.  Nearest-x2 slabs: 16 blocks = (row parity, column
+  // parity) x the 4 distinct half-resolution positions, each the fp32 sum of the taps that read that position.
+  std::vector<uint16_t> wp;
+  int wblock = 0;
+  {
+    int sl = 0;
+    for (int pi = 0; pi < p.nparts; ++pi)
+      for (int j = 0; j < p.part[pi].nslabs; ++j, ++sl) {
+        p.slab_wblock[sl] = wblock;
+        const int nblk = (p.part[pi].mode == 1) ? 16 : 9;
+        wp.resize((size_t)(wblock + nblk) * 2 * BN * 8);
+        for (int b = 0; b < nblk; ++b)
+          for (int ch = 0; ch < 2; ++ch)
+            for (int n = 0; n < BN; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = sl * 16 + ch * 8 + e;
+                float v = 0.f;
+                if (p.part[pi].mode != 1) {
+                  v = w_oihw[(((size_t)n * cin + ci) * 3 + b / 3) * 3 + b % 3];
+                } else {
+                  const int py = b >> 3, g = (b >> 2) & 1, pos = b & 3;
+                  for (int tap = 0; tap < 9; ++tap) {
+                    const int r = tap / 3, sft = tap % 3;
+                    const int dy = fl2(py + r - 1) - fl2(py - 1), dx = fl2(g + sft - 1) - fl2(g - 1);
+                    if (dy * 2 + dx == pos) v += w_oihw[(((size_t)n * cin + ci) * 3 + r) * 3 + sft];
+                  }
+                }
+                wp[((((size_t)(wblock + b)) * 2 + ch) * BN + n) * 8 + e] = f32_to_bf16_bits(v);
+              }
+        wblock += nblk;
+      }
+  }
+  p.w_blocks = wblock;
+  // A start offsets of the 4 collapsed positions of a nearest-x2 slab
+  for (int py = 0; py < 2; ++py)
+    for (int g = 0; g < 2; ++g)
+      for (int pos = 0; pos < 4; ++pos) {
+        const int ry = fl2(py - 1) + (pos >> 1) + 1, cx = fl2(g - 1) + (pos & 1) + kRowPad;
+        p.adelta_up[py][g][pos] = (uint16_t)(ry * kRowHaloCols + cx);
+      }
   upload(w_, wp);
   std::vector<float> sc(BN, 1.f), bi(BN, 0.f);
   if (scale) sc.assign(scale, scale + BN);
@@ -428,9 +488,11 @@ void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& s
     flops_ += 2.0 * N * OH * OW * 16 * 4;
   }
   p.stage_bytes = (has_skip ? 4 : 2) * kRowPlaneBytes;
-  const int w_bytes = p.nslabs * 9 * 2 * BN * 16;
+  const int w_bytes = p.w_blocks * 2 * BN * 16;
   const int fixed = 128 + ((w_bytes + (2 * BN + 68) * 4 + 127) & ~127) + 512;
-  p.stages = std::min(8, (226 * 1024 - fixed) / p.stage_bytes);
+  int max_stages = 8;
+  if (const char* e = getenv("WSI_ROW_STAGES")) max_stages = std::max(2, atoi(e));
+  p.stages = std::min(max_stages, (226 * 1024 - fixed) / p.stage_bytes);
   WSI_REQUIRE(p.stages >= 2, WSI_ERR_UNSUPPORTED, "row conv: not enough shared memory for 2 stages");
   smem_ = fixed + p.stages * p.stage_bytes;
   grid_ = (int)std::min<long long>(total, num_sms);

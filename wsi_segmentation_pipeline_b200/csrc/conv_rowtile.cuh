@@ -6,29 +6,35 @@
 // 16-byte cp.async producers starve for memory-level parallelism (measured 2 TB/s).  Instead:
 //
 //   * these activations live in HBM in a zero-padded CHANNEL-CHUNK-PLANAR layout
-//         [N][H+2][C/8][W+2][8 ch]                                  (LAYOUT_PLANAR)
-//     so that a halo row of one 8-channel chunk is ONE contiguous run, and the conv zero padding is
-//     simply there.  The skip operand of an upsample+concat conv is additionally de-interleaved by
-//     column parity: [N][H+2][C/8][2][W/2+1][8]                      (LAYOUT_PLANAR_PARITY)
+//         [N][H+2][C/8][Wrow][8 ch],  entry index = x + 8,  Wrow = roundup8(W + 9)     (LAYOUT_PLANAR)
+//     so that a halo row of one 8-channel chunk is ONE contiguous, 128-byte aligned run, and the conv
+//     zero padding is simply there.  The skip operand of an upsample+concat conv is additionally
+//     de-interleaved by column parity: [N][H+2][C/8][2][Wq][8], index = floor(x/2) + 8  (LAYOUT_PLANAR_PARITY)
 //   * a tile = 128 consecutive pixels of ONE output row (x2-upsampling convs: 256 pixels = two column
-//     parity groups).  Its 3 x 130 pixel halo is fetched ONCE per 16-channel slab by 6 (12) bulk
-//     copies (cp.async.bulk, TMA engine, mbarrier complete_tx) issued by the lanes of one warp into
-//         plane[kc][row 0..2][col 0..129][16 B]
+//     parity groups).  Its 3-row halo (144 entries per row: x in [x0-8, x0+136), 128-byte aligned at both
+//     ends — misaligned bulk copies run at ~14 B/cycle) is fetched ONCE per 16-channel slab by 6 (12)
+//     bulk copies (cp.async.bulk, TMA engine, mbarrier complete_tx) issued by the lanes of one warp into
+//         plane[kc][row 0..2][col 0..143][16 B]
 //     — the canonical NO-SWIZZLE K-major UMMA layout with SBO = 128 B (rows linear at 16 B pitch),
 //     LBO = plane stride.  Every filter tap (r,s) is then only a different descriptor START ADDRESS
-//     (+ (r*130+s)*16 B): nothing is re-read or re-arranged.  For x2-nearest sources the planes hold
-//     the half-resolution rows and tap offsets become floor((parity+tap-1)/2).
+//     (+ (r*144+s+7)*16 B): nothing is re-read or re-arranged.  For x2-nearest sources the planes hold
+//     the half-resolution rows and the 9 taps collapse to the 4 distinct source positions.
 //   * the whole weight tensor (<= 74 KB) stays resident in smem for the life of the persistent CTA.
-//   * warp 0: bulk-copy producer; warp 1: MMA issuer (+TMEM alloc); warps 2-5: epilogue (folded BN +
+//   * warps 0-2: bulk-copy producers (one halo row each); warps 3-4: MMA issuers (one accumulator each; warp 3
+//     owns the TMEM allocation); then 4 epilogue warps (folded BN +
 //     ReLU + bf16 store in planar or NHWC layout, or the fused 1x1 `final_conv` head -> fp32 logits).
 #pragma once
 #include "conv_igemm.cuh"
 
 namespace wsi {
 
-constexpr int kRowHaloCols = 130;
-constexpr int kRowPlaneBytes = 3 * kRowHaloCols * 16;    // 6240: [3 rows][130 cols][16 B]
-constexpr int kRowThreads = 6 * 32;
+constexpr int kRowPad = 8;                               // left padding entries of a planar row (128 B)
+constexpr int kRowHaloCols = 144;                        // halo entries per row: x in [x0-8, x0+136)
+constexpr int kRowPlaneBytes = 3 * kRowHaloCols * 16;    // 6912: [3 rows][144 cols][16 B], a multiple of 128
+constexpr int kRowProducerWarps = 3;                     // one per halo row
+constexpr int kRowMmaWarps = 2;                          // one per accumulator of a tile
+constexpr int kRowEpiGroups = 2;                         // epilogue warp-groups (4 warps each) alternating tiles
+constexpr int kRowThreads = (kRowProducerWarps + kRowMmaWarps + 4 * kRowEpiGroups) * 32;
 constexpr int kRowMaxSlabs = 8;
 constexpr int kRowAccStages = 4;                         // TMEM accumulator ring depth
 
@@ -39,10 +45,11 @@ struct PlanarDims {
     PlanarDims d;
     d.H = H_; d.W = W_; d.KC = C_ / 8;
     d.P = (layout == LAYOUT_PLANAR_PARITY) ? 2 : 1;
-    d.Wrow = (layout == LAYOUT_PLANAR_PARITY) ? (W_ / 2 + 1) : (W_ + 2);
+    d.Wrow = (((layout == LAYOUT_PLANAR_PARITY) ? (W_ / 2) : W_) + kRowPad + 1 + 7) & ~7;   // x = -1 .. W, rows 128 B aligned
     return d;
   }
-  // byte offset of entry 0 of chunk row (n, y in [-1,H], kc, par)
+  // byte offset of entry 0 of chunk row (n, y in [-1,H], kc, par); pixel x sits at entry x + kRowPad
+  // (parity planes: floor(x/2) + kRowPad, with x = -1 at entry kRowPad - 1 of the odd plane)
   __host__ __device__ size_t row_off(int n, int y, int kc, int par) const {
     return (((((size_t)n * (H + 2) + (size_t)(y + 1)) * KC + kc) * P + par) * (size_t)Wrow) * 16;
   }
@@ -65,7 +72,10 @@ struct RowParams {
   int nslabs;                    // 16-channel slabs per tile (all parts)
   int stages, stage_bytes;
   uint16_t adelta[3][2][2][9];   // [mode][output row parity][column parity group][tap]: A start offset, 16-byte units
-  const bf16* w;                 // [slab][tap][2][BN][8] bf16
+  uint16_t adelta_up[2][2][4];   // nearest-x2 slabs: [row parity][column parity][collapsed 2x2 position]
+  int slab_wblock[kRowMaxSlabs]; // first weight block of each slab
+  int w_blocks;                  // total weight blocks (each [2][BN][8] bf16)
+  const bf16* w;                 // per slab: 9 tap blocks, or 16 = (parities) x 4 collapsed positions for x2 slabs
   const float* scale;            // [BN]
   const float* bias;             // [BN]
   int relu;
