@@ -124,7 +124,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   int bk = 64;
   for (auto& q : parts) while (q.t.C % bk) bk /= 2;
   const int OH = (Hin + 2 * spec.pad - k) / spec.stride + 1, OW = (Win + 2 * spec.pad - k) / spec.stride + 1;
-  WSI_REQUIRE(spec.cout % 16 == 0, WSI_ERR_UNSUPPORTED, "conv: cout (%d) must be a multiple of 16", spec.cout);
+  WSI_REQUIRE(spec.cout % 16 == 0 && spec.cout <= 512, WSI_ERR_UNSUPPORTED, "conv: cout (%d) must be a multiple of 16, at most 512", spec.cout);
   int bn_out = 128;
   while (spec.cout % bn_out) bn_out /= 2;
   block_n_ = bn_out;

@@ -35,7 +35,7 @@ namespace wsi {
 
 constexpr int kMaxAMaps = 5;
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;     // TMA producer warp, MMA issuer warp, 8 epilogue warps
 
 struct KBlock {      // one K block of the implicit GEMM
   int8_t map;        // which A tensor map
@@ -204,7 +204,8 @@ struct ConvSmem {
   static constexpr int kStages = kStagesWanted > 8 ? 8 : (kStagesWanted < 2 ? 2 : kStagesWanted);
   static constexpr int kTableBytes = 4 * 128 * (int)sizeof(KBlock);   // up to 4 parities x 128 K blocks
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = 1024 /*align slack*/ + kStages * kStageBytes + kTableBytes + kBarBytes;
+  static constexpr int kScaleBytes = 2 * 512 * (int)sizeof(float);    // folded-BN scale + bias of up to 512 channels
+  static constexpr int kTotal = 1024 /*align slack*/ + kStages * kStageBytes + kTableBytes + kBarBytes + kScaleBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
 };
 
@@ -222,13 +223,16 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
   uint64_t* tmem_full = bars + 2 * S::kStages;     // [2]
   uint64_t* tmem_empty = bars + 2 * S::kStages + 2;  // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 4);
+  float* s_scale = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kTableBytes + S::kBarBytes);
+  float* s_bias = s_scale + 512;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = p.num_kb;
 
-  // K-block table -> smem
+  // K-block table and epilogue constants -> smem
   for (int i = threadIdx.x; i < p.num_parity * num_kb; i += blockDim.x) tbl[i] = p.kblocks[i];
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) { s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i]; }
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < S::kStages; ++i) {
@@ -237,7 +241,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 128);
+      ptx::mbar_init(&tmem_empty[i], 256);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&bmap);
@@ -319,9 +323,17 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
       }
     }
   } else {
-    // ================================ epilogue (4 warps) ==========================
+    // ================================ epilogue (8 warps) ==========================
+    // Two warps per TMEM lane quadrant, each draining half of the tile's columns (BLOCK_N >= 32), so
+    // the per-tile drain latency halves.  Folded-BN constants come from smem (loaded once per CTA),
+    // columns are processed 16/32 at a time with the residual for the NEXT chunk already in flight.
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int hsel = (warp - 2) >> 2;          // which half of the columns
     const int row = q * 32 + lane;             // M index inside the tile == TMEM lane
+    constexpr int CH = (BLOCK_N >= 32) ? BLOCK_N / 2 : BLOCK_N;      // columns per warp
+    constexpr int STEP = (CH >= 32) ? 32 : 16;                       // columns per iteration
+    const bool idle = (BLOCK_N < 32) && (hsel == 1);
+    const int c_lo = (BLOCK_N >= 32) ? hsel * CH : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -337,64 +349,77 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
       const int hl = (row / p.bw) % p.bh;
       const int nl = row / (p.bw * p.bh);
       const int n = tn * p.bn + nl, a = th * p.bh + hl, b = tw * p.bw + wl;
-      const bool valid = (n < p.N) && (a < p.A_h) && (b < p.A_w);
+      const bool valid = (n < p.N) && (a < p.A_h) && (b < p.A_w) && !idle;
       const int oh = p.sigma * a + (par >> 1), ow = p.sigma * b + (par & 1);
       const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
+      const size_t off0 = pix * p.Cout + co0 + c_lo;
+      const bool has_res = (p.res != nullptr) && valid;
+
+      // residual of the first chunk: issued before waiting for the accumulator
+      uint4 rcur[STEP / 8], rnext[STEP / 8];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < STEP / 8; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0) + j);
+      }
 
       ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 4);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c_lo);
 
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!idle) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(t_row + (uint32_t)c, v);
-        ptx::tmem_ld_wait();
-        float y[16];
-        const float4* sc4 = reinterpret_cast<const float4*>(p.scale + co0 + c);
-        const float4* bi4 = reinterpret_cast<const float4*>(p.bias + co0 + c);
+        for (int c = 0; c < CH; c += STEP) {
+          uint32_t v[STEP];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 s = __ldg(sc4 + j), bb = __ldg(bi4 + j);
-          y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), s.x, bb.x);
-          y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), s.y, bb.y);
-          y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), s.z, bb.z);
-          y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), s.w, bb.w);
-        }
-        if (valid) {
-          const size_t off = pix * p.Cout + co0 + c;
-          if (p.res != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+          for (int j = 0; j < STEP; j += 16) ptx::tmem_ld16(t_row + (uint32_t)(c + j), *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
+          if (has_res && c + STEP < CH) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 rv = __ldg(rp + j);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+            for (int j = 0; j < STEP / 8; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0 + c + STEP) + j);
+          }
+          ptx::tmem_ld_wait();
+          float y[STEP];
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + co0 + c_lo + c);
+          const float4* bi4 = reinterpret_cast<const float4*>(s_bias + co0 + c_lo + c);
+#pragma unroll
+          for (int j = 0; j < STEP / 4; ++j) {
+            const float4 sc = sc4[j], bb = bi4[j];
+            y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, bb.x);
+            y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, bb.y);
+            y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, bb.z);
+            y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, bb.w);
+          }
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < STEP / 8; ++j) {
+              const uint32_t w[4] = {rcur[j].x, rcur[j].y, rcur[j].z, rcur[j].w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 y[8 * j + 2 * t + 0] += __uint_as_float(w[t] << 16);
                 y[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
               }
             }
+#pragma unroll
+            for (int j = 0; j < STEP / 8; ++j) rcur[j] = rnext[j];
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+            for (int j = 0; j < STEP; ++j) y[j] = fmaxf(y[j], 0.f);
           }
           if (p.head_out != nullptr) {
             // fused final 1x1 conv (Cout == BLOCK_N == 16): logits = W[4x16] y + b
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              float s = 0.f;
+              float sacc = 0.f;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) s = fmaf(y[j], __ldg(p.head_w + k * 16 + j), s);
-              head_acc[k] += s;
+              for (int j = 0; j < 16; ++j) sacc = fmaf(y[j], __ldg(p.head_w + k * 16 + j), sacc);
+              head_acc[k] += sacc;
             }
           }
-          if (p.out != nullptr) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + off);
+          if (valid && p.out != nullptr) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < STEP / 8; ++j) {
               uint32_t w[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -405,14 +430,14 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             }
           }
         }
-      }
-      if (valid && p.head_out != nullptr) {
-        float4 o;
-        o.x = head_acc[0] + __ldg(p.head_b + 0);
-        o.y = head_acc[1] + __ldg(p.head_b + 1);
-        o.z = head_acc[2] + __ldg(p.head_b + 2);
-        o.w = head_acc[3] + __ldg(p.head_b + 3);
-        reinterpret_cast<float4*>(p.head_out)[pix] = o;
+        if (valid && p.head_out != nullptr) {
+          float4 o;
+          o.x = head_acc[0] + __ldg(p.head_b + 0);
+          o.y = head_acc[1] + __ldg(p.head_b + 1);
+          o.z = head_acc[2] + __ldg(p.head_b + 2);
+          o.w = head_acc[3] + __ldg(p.head_b + 3);
+          reinterpret_cast<float4*>(p.head_out)[pix] = o;
+        }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
