@@ -1,0 +1,86 @@
+"""GPU tests of the host-side mirror: nn.Module drop-ins (models.py) and predict_tumorbed (eval.py)
+against the oracle / the reference goldens, through the same C-ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wsi_oracle as O
+from wsi_segmentation_pipeline_b200 import capi, dataset as ds, eval as ev, models, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_unet_module_protocol_matches_oracle():
+    """The duck-typed protocol predict_tumorbed relies on (utils/eval.py:196-200)."""
+    sd = O.random_state_dict("unet", 2)
+    net = models.unet_resnet18()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x = O.gather_tiles(synth.synth_slide(200, 300, 5), [(0, 0), (100, 60), (200, 120)], 64, 64)
+    with torch.no_grad():
+        enc = net.encoder(x.cuda())
+        seg = net.decoder(enc).cpu()
+        cls = net.classifier(enc[0]).cpu()
+        reg = net.regressor(enc[0]).cpu()
+        seg2 = net(x.cuda()).cpu()
+    assert seg.shape == (3, 4, 64, 64) and cls.shape == (3, 4) and reg.shape == (3, 1)
+    assert torch.equal(seg, seg2)
+    for got, arch in ((seg, "unet_seg"), (cls, "unet_cls"), (reg, "unet_reg")):
+        ref = O.model_forward(sd, arch, x)
+        with O.bf16_emulation():
+            emu = O.model_forward(sd, arch, x)
+        err = (got - ref).abs().max().item()
+        noise = (emu - ref).abs().max().item()
+        assert err <= 1.5 * noise + 0.02 * ref.abs().max().item(), (arch, err, noise)
+    # weights changed in place -> the engine must pick them up
+    with torch.no_grad():
+        net.decoder.final_conv.bias.add_(1.0)
+        seg3 = net(x.cuda()).cpu()
+    assert torch.allclose(seg3, seg + 1.0, atol=1e-4)
+
+
+def test_resnet_multipatch_forward_matches_reference_golden(golden_dir):
+    """resnets_shift.ResNet.forward (:189-217): (cat(y_list,0) [P*B,4] patch-major, fc(features) [B,4])."""
+    g = np.load(os.path.join(golden_dir, "resnet_fwd.npz"))
+    sd = O.random_state_dict("resnet18", 3, with_fc=True)
+    net = models.resnet18()
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("fc1.", "fc2.")) for k in missing)
+    net = net.cuda().eval()
+    xs = torch.randn(2, 16, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        y, out = net(xs.cuda())
+    y, out = y.cpu().numpy(), out.cpu().numpy()
+    assert y.shape == g["y"].shape and out.shape == g["out"].shape
+    scale = np.abs(g["y"]).max()
+    assert np.abs(y - g["y"]).max() <= 0.05 * scale            # bf16 trunk vs the fp32 reference
+    assert np.abs(out - g["out"]).max() <= 0.05 * max(np.abs(g["out"]).max(), 1e-3) + 5e-3
+
+
+@pytest.mark.parametrize("name,arch,mode", [("cls_m4", "resnet18", "cls"), ("seg_small", "unet", "seg")])
+def test_predict_tumorbed_mirror(golden_dir, tmp_path, name, arch, mode):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g["geom"])
+    sd = O.random_state_dict(arch, int(g["seed"]))
+    net = models.resnet18() if arch == "resnet18" else models.unet_resnet18()
+    net.load_state_dict(sd, strict=False)
+    net = net.cuda()
+    raster = synth.synth_slide(ih, iw, 1234)
+    levels = {lvl: raster}
+    if lvl != 2:
+        levels[2] = np.zeros((ih // 4, iw // 4, 3), np.uint8)
+    scan = ds.ArraySlide(levels)
+    data = ds.Dataset_wsis({"slide0.svs": scan}, {"ph": ph, "pw": pw, "sh": sh, "sw": sw}, scan_level=lvl, masks={"slide0.svs": g["mask"]})
+    np.testing.assert_array_equal(data.wsis["slide0.svs"]["iterator"].tiles, g["tiles"])
+    args = ds.DotDict(val_save_pth=str(tmp_path), tile_stride_w=sw, class_probs=[0.0] * 4)
+    out = ev.predict_tumorbed(net, data, 0, mode, args=args)
+    assert data.wsis["slide0.svs"] is None and net.training           # reference side effects (utils/eval.py:282,286)
+    r = out["slide0.svs"]
+    assert (r["classes"] == g["classes"]).mean() >= 0.98
+    assert np.abs(r["heatmap"].astype(int) - g["heatmap"].astype(int)).max() <= 28
+    from PIL import Image
+    png = np.array(Image.open(tmp_path / "0" / f"slide0.svs_{sw}_heatmap.png"))
+    np.testing.assert_array_equal(png, r["heatmap"])
+    assert (tmp_path / "0" / f"slide0.svs_{sw}_overlay.png").exists()
