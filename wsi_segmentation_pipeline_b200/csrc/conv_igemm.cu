@@ -105,9 +105,11 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
     flops_ = row_->flops();
     block_n_ = spec.cout;
     block_k_ = 16;
+    stem_.reset();
     return;
   }
   row_.reset();
+  stem_.reset();
   WSI_REQUIRE(out_layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: only the row-tile kernel writes planar outputs");
   for (auto& q : parts) WSI_REQUIRE(q.t.layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC operands");
   bool any_up = false;
@@ -227,9 +229,21 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   finish(table, num_parity, wp, K, scale, bias, num_sms);
 }
 
+bool ConvOp::stem_routes_to_rowtile() { return getenv("WSI_NO_ROWTILE") == nullptr; }
+
 void ConvOp::build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw, const float* scale,
-                        const float* bias, void* out, int* error_flag, int num_sms) {
+                        const float* bias, void* out, int* error_flag, int num_sms, int out_layout) {
   WSI_REQUIRE(ph % 2 == 0 && pw % 2 == 0, WSI_ERR_UNSUPPORTED, "stem: tile size must be even");
+  row_.reset();
+  if (stem_routes_to_rowtile()) {
+    stem_.reset(new RowStemOp());
+    stem_->build(padded_tiles, n, ph, pw, w_oihw, scale, bias, out, out_layout, error_flag, num_sms);
+    flops_ = stem_->flops();
+    block_n_ = 64; block_k_ = 16;
+    return;
+  }
+  stem_.reset();
+  WSI_REQUIRE(out_layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "stem: only the row-tile stem writes the planar layout");
   block_n_ = 64; block_k_ = 32;
   ConvParams& p = p_;
   p = ConvParams{};
@@ -300,6 +314,7 @@ static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams
 
 void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (row_) { row_->launch(stream, lc); return; }
+  if (stem_) { stem_->launch(stream, lc); return; }
 #define WSI_CASE(BN, BK) \
   if (block_n_ == BN && block_k_ == BK) { launch_inst<BN, BK>(amaps_, bmap_, p_, grid_, stream); if (lc) lc->n++; return; }
   WSI_CASE(128, 64) WSI_CASE(64, 64) WSI_CASE(32, 64) WSI_CASE(16, 64)

@@ -481,6 +481,7 @@ struct ConvSpec {
 };
 
 class RowConvOp;   // conv_rowtile.cuh: halo-resident kernel for the small-channel 3x3 layers
+class RowStemOp;   // conv_rowtile.cuh: the stem in the same style
 
 // A fully prepared conv launch: tensor maps, K-block table, packed weights, epilogue params.
 // build() routes small-channel 3x3/s1 convs to the row-tile kernel (conv_rowtile.cuh) and
@@ -502,8 +503,11 @@ class ConvOp {
   // would build() route this conv to the row-tile kernel?  (lets the caller chain planar layouts)
   static bool routes_to_rowtile(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual);
   // stem: x = gather output, zero-padded tiles [n][ph+6][pw+8][4] bf16; 7x7/s2/p3, cout 64.
+  // out_layout: LAYOUT_NHWC or LAYOUT_PLANAR_PARITY (row-tile stem only; see stem_routes_to_rowtile)
   void build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw /*[64,3,7,7]*/,
-                  const float* scale, const float* bias, void* out, int* error_flag, int num_sms);
+                  const float* scale, const float* bias, void* out, int* error_flag, int num_sms,
+                  int out_layout = LAYOUT_NHWC);
+  static bool stem_routes_to_rowtile();
   void launch(cudaStream_t stream, LaunchCounter* lc) const;
   double flops() const { return flops_; }
   int block_n() const { return block_n_; }
@@ -517,6 +521,7 @@ class ConvOp {
   ConvParams p_{};
   DevBuf w_, scale_, bias_, tbl_, headw_, headb_;
   std::unique_ptr<RowConvOp> row_;
+  std::unique_ptr<RowStemOp> stem_;
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
   double flops_ = 0;
 };

@@ -307,6 +307,285 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------------------
+// stem kernel (see conv_rowtile.cuh)
+// ---------------------------------------------------------------------------------------------
+constexpr int kStemThreads = (1 + 2 + 8) * 32;   // producer warp, 2 MMA warps, 2 x 4 epilogue warps
+
+__global__ void __launch_bounds__(kStemThreads, 1) stem_rowtile_kernel(const __grid_constant__ StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int kWBytes = 28 * 64 * 16;           // 28 672
+  uint8_t* s_w = smem;
+  float* s_scale = reinterpret_cast<float*>(smem + kWBytes);
+  float* s_bias = s_scale + 64;
+  uint8_t* s_stage = smem + kWBytes + 512;
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + (size_t)S * kStemStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* tmem_full = bars + 2 * S;
+  uint64_t* tmem_empty = bars + 2 * S + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+  constexpr int kAcc = 4;                          // accumulator ring (tiles in flight)
+  constexpr uint32_t kTmemCols = kAcc * 2 * 64;    // 512: two partial accumulators of 64 columns per tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    for (int i = threadIdx.x; i < kWBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i]; }
+    uint4* st = reinterpret_cast<uint4*>(s_stage);
+    for (int i = threadIdx.x; i < S * kStemStageBytes / 16; i += blockDim.x) st[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 2);
+    }
+    for (int i = 0; i < kAcc; ++i) {
+      ptx::mbar_init(&tmem_full[i], 2);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_holder, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  const int t_begin = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
+  const size_t in_pitch = (size_t)(p.PW + 8) * 8;
+  const int row_chunks = (p.PW + 8) / 2;
+
+  if (warp == 0) {
+    // ---- producer: lane r copies input row r of the tile (7 bulk copies per tile) ----
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t stage0 = ptx::smem_u32(s_stage);
+    TileCoord tc;
+    tc.init(t_begin, p.tiles_x, p.OH);
+    for (int tile = t_begin; tile < t_end; ++tile, tc.next(p.tiles_x, p.OH)) {
+      const int b0 = tc.xb * 128;
+      const int n_chunks = min(131, row_chunks - b0);
+      const uint32_t bytes = (uint32_t)n_chunks * 16u;
+      const bool active = lane < 7;
+      const uint8_t* src = p.in + ((size_t)tc.n * (p.PH + 6) + (size_t)(2 * tc.y + (active ? lane : 0))) * in_pitch + (size_t)b0 * 16;
+      ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 21);
+      if (lane == 0) ptx::mbar_expect_tx(&full[stage], bytes * 7u);
+      __syncwarp();
+      if (active) ptx::bulk_g2s(stage0 + (uint32_t)(stage * kStemStageBytes + lane * kStemRowBytes), src, bytes, &full[stage]);
+      if (++stage == S) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp < 3) {
+    // ---- MMA warps: warp m issues the k-steps of parity m into partial accumulator m ----
+    const int m = warp - 1;
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_holder);
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16<64>();
+      const uint64_t a_desc0 = make_nosw_desc(ptx::smem_u32(s_stage), 16, 128);          // K chunks 16 B apart: overlapping windows
+      const uint64_t b_desc0 = make_nosw_desc(ptx::smem_u32(s_w), 64 * 16, 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 22);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 2 + m) * 64);
+        const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)(stage * kStemStageBytes) >> 4);
+        ptx::mbar_wait(&full[stage], phase, p.error_flag, 23);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 14; ++ks) {
+          if ((ks & 1) != m) continue;
+          const int r = ks >> 1, j = ks & 1;
+          ptx::umma_bf16(d_tmem, a_st + (uint64_t)((r * kStemRowBytes + 2 * j * 16) >> 4), b_desc0 + (uint64_t)((r * 4 + 2 * j) * 64), idesc,
+                         (uint32_t)(ks >= 2));
+        }
+        ptx::umma_commit(&empty[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        ptx::umma_commit(&tmem_full[acc]);
+        if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ---- epilogue: two groups of 4 warps alternate tiles ----
+    const uint32_t tmem_base = *tmem_holder;
+    const int q = warp & 3;
+    const int egrp = (warp - 3) >> 2;
+    const int row = q * 32 + lane;
+    const bool planar = (p.out_layout == LAYOUT_PLANAR_PARITY);
+    int acc = egrp;
+    uint32_t acc_phase = 0;
+    TileCoord tc;
+    tc.init(t_begin + egrp, p.tiles_x, p.OH);
+    for (int tile = t_begin + egrp; tile < t_end; tile += 2, tc.advance(2, p.tiles_x, p.OH)) {
+      const int x = tc.xb * 128 + row;
+      const bool valid = x < p.OW;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 24);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * 64);
+      uint8_t* obase;
+      size_t cstep;
+      if (planar) {
+        obase = p.out + p.od.row_off(tc.n, tc.y, 0, x & 1) + (size_t)((x >> 1) + kRowPad) * 16;
+        cstep = (size_t)2 * p.od.Wrow * 16;                    // next 8-channel chunk (both parity runs)
+      } else {
+        obase = p.out + (((size_t)tc.n * p.OH + tc.y) * p.OW + x) * 128;
+        cstep = 16;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                              // 32 output channels at a time
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld16(t_row + (uint32_t)(h * 32), *reinterpret_cast<uint32_t(*)[16]>(&v0[0]));
+        ptx::tmem_ld16(t_row + (uint32_t)(h * 32 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v0[16]));
+        ptx::tmem_ld16(t_row + (uint32_t)(64 + h * 32), *reinterpret_cast<uint32_t(*)[16]>(&v1[0]));
+        ptx::tmem_ld16(t_row + (uint32_t)(64 + h * 32 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v1[16]));
+        ptx::tmem_ld_wait();
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          y[j] = fmaxf(fmaf(__uint_as_float(v0[j]) + __uint_as_float(v1[j]), s_scale[h * 32 + j], s_bias[h * 32 + j]), 0.f);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+              w[t] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(obase + (size_t)(h * 4 + j) * cstep) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+      acc += 2;
+      if (acc >= kAcc) { acc -= kAcc; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(*tmem_holder, kTmemCols);
+  }
+}
+
+void RowStemOp::build(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw, const float* scale, const float* bias,
+                      void* out, int out_layout, int* error_flag, int num_sms) {
+  WSI_REQUIRE(ph % 2 == 0 && pw % 2 == 0, WSI_ERR_UNSUPPORTED, "stem: tile size must be even");
+  WSI_REQUIRE(out_layout == LAYOUT_NHWC || out_layout == LAYOUT_PLANAR_PARITY, WSI_ERR_INVALID, "stem: bad output layout");
+  StemParams& p = p_;
+  p = StemParams{};
+  p.in = static_cast<const uint8_t*>(padded_tiles);
+  p.N = n; p.PH = ph; p.PW = pw; p.OH = ph / 2; p.OW = pw / 2;
+  p.tiles_x = (int)ceil_div(p.OW, 128);
+  const long long total = (long long)n * p.OH * p.tiles_x;
+  WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "stem: too many tiles");
+  p.total_tiles = (int)total;
+  p.out = static_cast<uint8_t*>(out);
+  p.out_layout = out_layout;
+  p.od = PlanarDims::make(p.OH, p.OW, 64, LAYOUT_PLANAR_PARITY);
+  p.error_flag = error_flag;
+  // weights: k-chunk kc = r*4 + (pixel pair), element e = (pixel in pair)*4 + channel; [kc][cout][8]
+  std::vector<uint16_t> wp((size_t)28 * 64 * 8, 0);
+  for (int r = 0; r < 7; ++r)
+    for (int s = 0; s < 7; ++s)
+      for (int c = 0; c < 3; ++c)
+        for (int co = 0; co < 64; ++co) {
+          const int kc = r * 4 + s / 2, e = (s & 1) * 4 + c;
+          wp[((size_t)kc * 64 + co) * 8 + e] = f32_to_bf16_bits(w_oihw[(((size_t)co * 3 + c) * 7 + r) * 7 + s]);
+        }
+  upload(w_, wp);
+  std::vector<float> sc(64, 1.f), bi(64, 0.f);
+  if (scale) sc.assign(scale, scale + 64);
+  if (bias) bi.assign(bias, bias + 64);
+  upload(scale_, sc);
+  upload(bias_, bi);
+  p.w = w_.as<bf16>(); p.scale = scale_.as<float>(); p.bias = bias_.as<float>();
+  flops_ = 2.0 * n * p.OH * p.OW * 64.0 * 147.0;
+  p.stages = 8;
+  smem_ = 128 + 28 * 64 * 16 + 512 + p.stages * kStemStageBytes + 256;
+  grid_ = (int)std::min<long long>(total, num_sms);
+  CUDA_CHECK(cudaStreamSynchronize(0));
+}
+
+void RowStemOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(stem_rowtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  stem_rowtile_kernel<<<grid_, kStemThreads, smem_, stream>>>(p_);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// max pool 3x3/s2/p1 over the parity-planar stem output -> NHWC (resnets_shift.py:126)
+// one thread = 8 channels of one output pixel; all nine taps are in range thanks to the zero border
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_planar_kernel(const uint8_t* __restrict__ x, int n, int h, int w, int kcs,
+                                                              bf16* __restrict__ y) {
+  const PlanarDims d = PlanarDims::make(h, w, kcs * 8, LAYOUT_PLANAR_PARITY);
+  const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+  const int64_t total = (int64_t)n * oh * ow * kcs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // ox fastest: consecutive lanes read consecutive 16-byte entries of the same planar runs
+    const int ox = (int)(i % ow);
+    int64_t r = i / ow;
+    const int g = (int)(r % kcs); r /= kcs;
+    const int oy = (int)(r % oh);
+    const int b = (int)(r / oh);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;        // inputs are post-ReLU (>= 0): 0 is the identity of this max
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int iy = 2 * oy + dy;
+      if (iy >= h) continue;                        // the layout pads one row below only when h is even-sized input; guard anyway
+      const uint8_t* even = x + d.row_off(b, iy, g, 0);
+      const uint8_t* odd = x + d.row_off(b, iy, g, 1);
+      // columns 2ox-1 (odd run, half-index ox-1), 2ox (even run, ox), 2ox+1 (odd run, ox)
+      const uint4 v[3] = {__ldg(reinterpret_cast<const uint4*>(odd + (size_t)(ox - 1 + kRowPad) * 16)),
+                          __ldg(reinterpret_cast<const uint4*>(even + (size_t)(ox + kRowPad) * 16)),
+                          __ldg(reinterpret_cast<const uint4*>(odd + (size_t)(ox + kRowPad) * 16))};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t ww[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          m[2 * t] = fmaxf(m[2 * t], __uint_as_float(ww[t] << 16));
+          m[2 * t + 1] = fmaxf(m[2 * t + 1], __uint_as_float(ww[t] & 0xffff0000u));
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(m[2 * t], m[2 * t + 1]);
+      o[t] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(y + (((int64_t)b * oh + oy) * ow + ox) * (kcs * 8) + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+void launch_maxpool_planar(const void* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t total = (int64_t)n * ((h - 1) / 2 + 1) * ((w - 1) / 2 + 1) * (c / 8);
+  if (total <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+  maxpool_planar_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(x), n, h, w, c / 8, y);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// ---------------------------------------------------------------------------------------------
 // NHWC -> planar relayout (one thread per 16-byte chunk, chunk index fastest: reads are fully
 // coalesced, writes are 16-byte entries of C/8 planar rows)
 // ---------------------------------------------------------------------------------------------

@@ -109,6 +109,50 @@ class RowConvOp {
   double flops_ = 0;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Stem (conv1 7x7/s2/p3, 3 -> 64, + bn1 + relu; resnets_shift.py:196-198) in the same style.
+// Input: the gather kernel's zero-padded tiles [n][ph+6][pw+8][4] bf16 (8 B per pixel).  A tile = 128
+// output pixels of one output row; its 7 input rows (131 16-byte chunks of 2 pixels each) are fetched
+// once by 7 bulk copies.  Output pixel i, filter row r reads padded pixels 2i..2i+7 = chunks i..i+3 of
+// row r: consecutive output pixels advance by ONE chunk, so the A operand of (r, k-step j) is the
+// no-swizzle descriptor {start = row r + 2j chunks, row pitch 16 B (SBO 128), LBO 16 B} — an
+// overlapping (Hankel) view, nothing is im2col'ed.  K = 7 x 32 (8th pixel and 4th channel: zero
+// weights), 14 MMAs of 128x64x16 per tile, alternating two partial accumulators.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStemRowBytes = 132 * 16;                  // 131 chunks needed, padded to 132
+constexpr int kStemStageBytes = 7 * kStemRowBytes;       // 14 784
+
+struct StemParams {
+  const uint8_t* in;             // padded tiles
+  int N, PH, PW, OH, OW;
+  int tiles_x, total_tiles, stages;
+  const bf16* w;                 // [28 k-chunks][64][8] bf16
+  const float* scale;            // [64]
+  const float* bias;             // [64]
+  uint8_t* out;                  // bf16, NHWC [N,OH,OW,64] or parity-planar
+  int out_layout;                // LAYOUT_NHWC or LAYOUT_PLANAR_PARITY
+  PlanarDims od;
+  int* error_flag;
+};
+
+class RowStemOp {
+ public:
+  void build(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw, const float* scale, const float* bias,
+             void* out, int out_layout, int* error_flag, int num_sms);
+  void launch(cudaStream_t stream, LaunchCounter* lc) const;
+  double flops() const { return flops_; }
+
+ private:
+  StemParams p_{};
+  DevBuf w_, scale_, bias_;
+  int grid_ = 0, smem_ = 0;
+  double flops_ = 0;
+};
+
+// 3x3/s2/p1 max pool reading the stem's parity-planar output (values are post-ReLU >= 0, so the layout's
+// zero border is equivalent to the reference's -inf padding), writing NHWC
+void launch_maxpool_planar(const void* x_parity_planar, int n, int h, int w, int c, bf16* y_nhwc, cudaStream_t s, LaunchCounter* lc);
+
 // NHWC bf16 -> padded planar (interior only; the zero border is written once at allocation)
 void launch_relayout_planar(const void* src_nhwc, void* dst, int N, int H, int W, int C, int layout, cudaStream_t s,
                             LaunchCounter* lc);

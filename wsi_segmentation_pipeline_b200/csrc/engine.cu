@@ -233,12 +233,15 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
   CUDA_CHECK(cudaMemset(in_pad.p, 0, in_pad.bytes));
 
   // ---- stem: conv1 7x7/s2/p3 + bn1 + relu (resnets_shift.py:196-198) ----
-  Act* x0 = new_act(cap, ph / 2, pw / 2, 64);
+  // the row-tile stem writes x0 column-parity-planar: the max-pool reads it directly and the decoder's level-4
+  // conv takes it as its skip operand without a relayout
+  const int x0_layout = ConvOp::stem_routes_to_rowtile() ? LAYOUT_PLANAR_PARITY : LAYOUT_NHWC;
+  Act* x0 = new_act(cap, ph / 2, pw / 2, 64, x0_layout);
   {
     const HostTensor& w = conv_weight(c, tp + "conv1.weight", 64, 3, 7);
     const Folded f = fold_bn(c, tp + "bn1", 64);
     ConvOp* op = new_op();
-    op->build_stem(in_pad.p, cap, ph, pw, w.data.data(), f.scale.data(), f.bias.data(), x0->buf.p, ef, sms);
+    op->build_stem(in_pad.p, cap, ph, pw, w.data.data(), f.scale.data(), f.bias.data(), x0->buf.p, ef, sms, x0_layout);
     steps.push_back(Step{0, ST_STEM, op, nullptr, x0});
     stem_flops = op->flops();
     op_stats.push_back(OpStat{"stem 7x7/s2 3->64", 0, op->flops(), 0});
@@ -457,7 +460,10 @@ void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
         }
         ++conv_idx;
       } else if (st.kind == 1) {
-        launch_maxpool(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
+        if (st.in->layout == LAYOUT_PLANAR_PARITY)
+          launch_maxpool_planar(st.in->buf.p, st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
+        else
+          launch_maxpool(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
       } else {
         const bool feat = (head == WSI_HEAD_FEATURES);
         launch_pool_head(x4->buf.as<bf16>(), cap, x4->H * x4->W, x4->C, hw1.as<float>(), hb1.as<float>(), n1, hw2.as<float>(),
