@@ -297,24 +297,36 @@ void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std:
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co * num_parity;
   WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "conv: too many tiles");
   grid_ = (int)std::min<long long>(total, num_sms);
+  {
+    const int bbytes = (block_n_ * block_k_ * 2 + 1023) / 1024 * 1024;
+    resb_ = (p.tiles_co == 1) && (block_k_ == 64) && (block_n_ == 64 || block_n_ == 128) &&
+            ((long long)p.num_kb * bbytes <= kResidentBBytes) && getenv("WSI_NO_RESB") == nullptr;
+  }
   CUDA_CHECK(cudaStreamSynchronize(0));   // uploads above used the default stream
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool RESB = false>
 static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
-  using S = ConvSmem<BN, BK>;
+  using S = ConvSmem<BN, BK, RESB>;
+  static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  conv_igemm_kernel<BN, BK><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);
+  conv_igemm_kernel<BN, BK, RESB><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (row_) { row_->launch(stream, lc); return; }
   if (stem_) { stem_->launch(stream, lc); return; }
+  if (resb_) {
+    if (block_n_ == 64) launch_inst<64, 64, true>(amaps_, bmap_, p_, grid_, stream);
+    else launch_inst<128, 64, true>(amaps_, bmap_, p_, grid_, stream);
+    if (lc) lc->n++;
+    return;
+  }
 #define WSI_CASE(BN, BK) \
   if (block_n_ == BN && block_k_ == BK) { launch_inst<BN, BK>(amaps_, bmap_, p_, grid_, stream); if (lc) lc->n++; return; }
   WSI_CASE(128, 64) WSI_CASE(64, 64) WSI_CASE(32, 64) WSI_CASE(16, 64)

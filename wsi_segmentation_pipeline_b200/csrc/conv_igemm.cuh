@@ -194,36 +194,45 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16() {
          | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
-template <int BLOCK_N, int BLOCK_K>
+constexpr int kResidentBBytes = 96 * 1024;   // RESB: the whole weight tensor of the conv stays in smem
+
+template <int BLOCK_N, int BLOCK_K, bool RESB = false>
 struct ConvSmem {
   static constexpr int kABytes = kBlockM * BLOCK_K * 2;
   static constexpr int kBBytesRaw = BLOCK_N * BLOCK_K * 2;
   static constexpr int kBBytes = (kBBytesRaw + 1023) / 1024 * 1024;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesWanted = (160 * 1024) / kStageBytes;
+  static constexpr int kStageBytes = RESB ? kABytes : kABytes + kBBytes;
+  static constexpr int kResBytes = RESB ? kResidentBBytes : 0;
+  static constexpr int kStagesWanted = ((RESB ? 112 : 160) * 1024) / kStageBytes;
   static constexpr int kStages = kStagesWanted > 8 ? 8 : (kStagesWanted < 2 ? 2 : kStagesWanted);
   static constexpr int kTableBytes = 4 * 128 * (int)sizeof(KBlock);   // up to 4 parities x 128 K blocks
   static constexpr int kBarBytes = 256;
   static constexpr int kScaleBytes = 2 * 512 * (int)sizeof(float);    // folded-BN scale + bias of up to 512 channels
-  static constexpr int kTotal = 1024 /*align slack*/ + kStages * kStageBytes + kTableBytes + kBarBytes + kScaleBytes;
+  static constexpr int kRing = kStages * kStageBytes + kResBytes;     // stage ring (+ resident weights)
+  static constexpr int kTotal = 1024 /*align slack*/ + kRing + kTableBytes + kBarBytes + kScaleBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
 };
 
-template <int BLOCK_N, int BLOCK_K>
+// RESB: convs whose whole weight tensor fits in kResidentBBytes (one output-channel tile) load B ONCE per CTA
+// and the stage ring carries only A — the mainloop is bound by the TMA box-row rate, and B is a third (N=64)
+// to a half (N=128) of the rows of a K block.
+template <int BLOCK_N, int BLOCK_K, bool RESB = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
-  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  using S = ConvSmem<BLOCK_N, BLOCK_K, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  KBlock* tbl = reinterpret_cast<KBlock*>(smem + S::kStages * S::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + S::kTableBytes);
+  uint8_t* b_res = smem + S::kStages * S::kStageBytes;                 // RESB only
+  KBlock* tbl = reinterpret_cast<KBlock*>(smem + S::kRing);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kRing + S::kTableBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + S::kStages;         // [kStages]
   uint64_t* tmem_full = bars + 2 * S::kStages;     // [2]
   uint64_t* tmem_empty = bars + 2 * S::kStages + 2;  // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 4);
-  float* s_scale = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kTableBytes + S::kBarBytes);
+  uint64_t* bres_bar = bars + 2 * S::kStages + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 5);
+  float* s_scale = reinterpret_cast<float*>(smem + S::kRing + S::kTableBytes + S::kBarBytes);
   float* s_bias = s_scale + 512;
 
   const int warp = threadIdx.x >> 5;
@@ -243,6 +252,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 256);
     }
+    ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&bmap);
     ptx::prefetch_tmap(&amaps.m[0]);
@@ -261,6 +271,10 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (RESB && blockIdx.x < total_tiles) {
+        ptx::mbar_expect_tx(bres_bar, (uint32_t)num_kb * S::kBBytesRaw);
+        for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(b_res + kb * S::kBBytes, &bmap, bres_bar, kb * BLOCK_K, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int r = tile;
         const int ct = r % p.tiles_co; r /= p.tiles_co;
@@ -272,7 +286,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
         const KBlock* kb_tbl = tbl + par * num_kb;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 1);
-          ptx::mbar_expect_tx(&full[stage], S::kABytes + S::kBBytesRaw);
+          ptx::mbar_expect_tx(&full[stage], RESB ? S::kABytes : S::kABytes + S::kBBytesRaw);
           const KBlock e = kb_tbl[kb];
           uint8_t* sA = stage_base + stage * S::kStageBytes;
           uint8_t* sB = sA + S::kABytes;
@@ -285,7 +299,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             default: break;
           }
           ptx::tma_load_4d(sA, am, &full[stage], e.c0, b0 + e.db, a0 + e.da, n0);
-          ptx::tma_load_2d(sB, &bmap, &full[stage], kb * BLOCK_K, co0);
+          if (!RESB) ptx::tma_load_2d(sB, &bmap, &full[stage], kb * BLOCK_K, co0);
           if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -298,6 +312,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (RESB && blockIdx.x < total_tiles) ptx::mbar_wait(bres_bar, 0, p.error_flag, 5);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 2);
         ptx::tc_fence_after();
@@ -306,7 +321,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
           ptx::mbar_wait(&full[stage], phase, p.error_flag, 3);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * S::kStageBytes);
-          const uint32_t b_addr = a_addr + S::kABytes;
+          const uint32_t b_addr = RESB ? ptx::smem_u32(b_res + kb * S::kBBytes) : a_addr + S::kABytes;
           const uint64_t adesc = make_kmajor_desc<BLOCK_K>(a_addr);
           const uint64_t bdesc = make_kmajor_desc<BLOCK_K>(b_addr);
 #pragma unroll
@@ -523,6 +538,7 @@ class ConvOp {
   std::unique_ptr<RowConvOp> row_;
   std::unique_ptr<RowStemOp> stem_;
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
+  bool resb_ = false;         // weights resident in smem (see conv_igemm_kernel RESB)
   double flops_ = 0;
 };
 

@@ -495,9 +495,9 @@ static void check_device_flag(wsi_ctx* c, cudaStream_t s) {
 static int64_t auto_batch(const wsi_ctx* c, int ph, int pw, int64_t T) {
   int64_t b = c->batch_tiles;
   if (b <= 0) {
-    // ~8 Mpx of tile area per batch: enough output tiles to fill 148 SMs in the deepest layers while
-    // the working set of the high-resolution layers stays near the 126 MB L2
-    b = std::max<int64_t>(1, (8LL << 20) / ((int64_t)ph * pw));
+    // ~16 Mpx of tile area per batch (64 tiles of 512^2): the deepest layers need >= 2 full waves of
+    // output tiles on 148 SMs (measured: 16 -> 204, 32 -> 228, 64 -> 239, 96 -> 232 slide-Mpx/s)
+    b = std::max<int64_t>(1, (16LL << 20) / ((int64_t)ph * pw));
     b = std::min<int64_t>(b, 1024);
   }
   return std::max<int64_t>(1, std::min<int64_t>(b, T));
