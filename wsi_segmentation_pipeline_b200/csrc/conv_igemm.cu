@@ -97,11 +97,12 @@ bool ConvOp::routes_to_rowtile(const std::vector<ConvInputPart>& parts, const Co
 
 void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
                    const float* scale, const float* bias, const void* residual, void* out,
-                   const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms, int out_layout) {
+                   const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms, int out_layout,
+                   int res_layout) {
   WSI_REQUIRE(!parts.empty() && parts.size() <= 2, WSI_ERR_INVALID, "conv: 1 or 2 input parts");
   if (routes_to_rowtile(parts, spec, residual)) {
     row_.reset(new RowConvOp());
-    row_->build(parts, spec, w_oihw, scale, bias, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
+    row_->build(parts, spec, w_oihw, scale, bias, residual, res_layout, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
     flops_ = row_->flops();
     block_n_ = spec.cout;
     block_k_ = 16;
@@ -110,7 +111,8 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   }
   row_.reset();
   stem_.reset();
-  WSI_REQUIRE(out_layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: only the row-tile kernel writes planar outputs");
+  WSI_REQUIRE(out_layout == LAYOUT_NHWC && (residual == nullptr || res_layout == LAYOUT_NHWC), WSI_ERR_UNSUPPORTED,
+              "conv: only the row-tile kernel reads/writes planar tensors");
   for (auto& q : parts) WSI_REQUIRE(q.t.layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC operands");
   bool any_up = false;
   for (auto& q : parts) any_up |= q.up2;

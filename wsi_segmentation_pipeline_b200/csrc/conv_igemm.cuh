@@ -513,7 +513,7 @@ class ConvOp {
   void build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
              const float* scale, const float* bias, const void* residual, void* out,
              const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms,
-             int out_layout = LAYOUT_NHWC);
+             int out_layout = LAYOUT_NHWC, int res_layout = LAYOUT_NHWC);
   bool is_rowtile() const { return (bool)row_; }
   // would build() route this conv to the row-tile kernel?  (lets the caller chain planar layouts)
   static bool routes_to_rowtile(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual);

@@ -206,17 +206,20 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
       }
     }
   } else {
-    // ================================ epilogue (4 warps) ================================
-    // folded-BN constants and the fused 1x1 head live in registers for the life of the CTA
-    // two groups of 4 warps alternate tiles (group e drains accumulator stages e, e+2), so the epilogue of
-    // tile t overlaps the epilogue of tile t+1 as well as the MMAs of t+2..
+    // ================================ epilogue (2 x 4 warps) ============================
+    // Two groups of 4 warps alternate tiles (group e drains accumulator stages e, e+2, ..).  Columns are
+    // drained 16 at a time: sum of the two partial accumulators (G == 1), folded BN, residual, ReLU, store.
+    // Folded-BN constants and the fused 1x1 head live in registers (BN <= 32) or smem (BN == 64).
     const uint32_t tmem_base = *tmem_holder;
     const int q = warp & 3;
     const int egrp = (warp - kRowProducerWarps - kRowMmaWarps) >> 2;
     const int row = q * 32 + lane;
-    float r_scale[BN], r_bias[BN];
+    constexpr int RB = (BN <= 32) ? BN : 1;
+    float r_scale[RB], r_bias[RB];
+    if (BN <= 32) {
 #pragma unroll
-    for (int j = 0; j < BN; ++j) { r_scale[j] = s_scale[j]; r_bias[j] = s_bias[j]; }
+      for (int j = 0; j < RB; ++j) { r_scale[j] = s_scale[j]; r_bias[j] = s_bias[j]; }
+    }
     float r_hw[HEAD ? 64 : 1], r_hb[HEAD ? 4 : 1];
     if (HEAD) {
 #pragma unroll
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
     }
     const float lo = p.relu ? 0.f : -INFINITY;
     const bool planar_out = (p.out_layout == LAYOUT_PLANAR);
+    const bool planar_res = (p.res_layout == LAYOUT_PLANAR);
     const size_t chunk_step = (size_t)p.od.Wrow * 16;
     int acc = egrp;
     uint32_t acc_phase = 0;
@@ -233,6 +237,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
     tc.init(t_begin + egrp, p.tiles_x, p.OH);
     for (int tile = t_begin + egrp; tile < t_end; tile += kRowEpiGroups, tc.advance(kRowEpiGroups, p.tiles_x, p.OH)) {
       const size_t rowpix = ((size_t)tc.n * p.OH + tc.y) * p.OW;
+      const size_t prow = p.od.row_off(tc.n, tc.y, 0, 0);
       ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 14);
       ptx::tc_fence_after();
 #pragma unroll
@@ -241,55 +246,73 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_rowtile_kernel(const __gr
         const bool valid = x < p.OW;
         const size_t pix = rowpix + x;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * G + g) * NA * BN);
-        uint32_t v[NA * BN];
+        // byte offsets of this pixel's first 8-channel chunk and the step to the next chunk
+        const size_t o_off = planar_out ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
+        const size_t o_step = planar_out ? chunk_step : 16;
+        const size_t r_off = planar_res ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
+        const size_t r_step = planar_res ? chunk_step : 16;
+        float4 hacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < NA * BN; c += 16) ptx::tmem_ld16(t_row + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
-        ptx::tmem_ld_wait();
-        float yv[BN];
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[NA * 16];
+          ptx::tmem_ld16(t_row + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          if (NA == 2) ptx::tmem_ld16(t_row + (uint32_t)(BN + c), *reinterpret_cast<uint32_t(*)[16]>(&v[NA == 2 ? 16 : 0]));
+          uint4 rv[2];
+          const bool has_res = (p.res != nullptr) && valid;
+          if (has_res) {
+            rv[0] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)(c / 8) * r_step));
+            rv[1] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)(c / 8 + 1) * r_step));
+          }
+          ptx::tmem_ld_wait();
+          float yv[16];
 #pragma unroll
-        for (int j = 0; j < BN; ++j) {
-          const float a = (NA == 2) ? (__uint_as_float(v[j]) + __uint_as_float(v[BN + j])) : __uint_as_float(v[j]);
-          yv[j] = fmaxf(fmaf(a, r_scale[j], r_bias[j]), lo);
-        }
-        if (HEAD) {
-          float4 o;
-          float* op = reinterpret_cast<float*>(&o);
+          for (int j = 0; j < 16; ++j) {
+            const float a = (NA == 2) ? (__uint_as_float(v[j]) + __uint_as_float(v[(NA == 2 ? 16 : 0) + j])) : __uint_as_float(v[j]);
+            const float sc = (BN <= 32) ? r_scale[(BN <= 32) ? c + j : 0] : s_scale[c + j];
+            const float bi = (BN <= 32) ? r_bias[(BN <= 32) ? c + j : 0] : s_bias[c + j];
+            yv[j] = fmaf(a, sc, bi);
+          }
+          if (has_res) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // two independent chains per logit (ILP), summed in a fixed order
-            float s0 = 0.f, s1 = 0.f;
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t w[4] = {rv[k].x, rv[k].y, rv[k].z, rv[k].w};
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              s0 = fmaf(yv[j], r_hw[HEAD ? k * 16 + j : 0], s0);
-              s1 = fmaf(yv[j + 1], r_hw[HEAD ? k * 16 + j + 1 : 0], s1);
+              for (int t = 0; t < 4; ++t) {
+                yv[8 * k + 2 * t + 0] += __uint_as_float(w[t] << 16);
+                yv[8 * k + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+              }
             }
-            op[k] = (s0 + s1) + r_hb[HEAD ? k : 0];
           }
-          if (valid) reinterpret_cast<float4*>(p.head_out)[pix] = o;
-        }
-        if (valid && p.out != nullptr) {
-          uint4 w4[BN / 8];
 #pragma unroll
-          for (int j = 0; j < BN / 8; ++j) {
-            uint32_t w[4];
+          for (int j = 0; j < 16; ++j) yv[j] = fmaxf(yv[j], lo);
+          if (HEAD) {
+            float* hp = reinterpret_cast<float*>(&hacc);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(yv[8 * j + 2 * t], yv[8 * j + 2 * t + 1]);
-              w[t] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int k = 0; k < 4; ++k) {
+              // two independent chains per logit (ILP), summed in a fixed order
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                s0 = fmaf(yv[j], r_hw[HEAD ? k * 16 + j : 0], s0);
+                s1 = fmaf(yv[j + 1], r_hw[HEAD ? k * 16 + j + 1 : 0], s1);
+              }
+              hp[k] = (s0 + s1) + r_hb[HEAD ? k : 0];
             }
-            w4[j] = make_uint4(w[0], w[1], w[2], w[3]);
           }
-          if (planar_out) {
-            // chunk rows are contiguous along x: consecutive lanes write consecutive 16-byte entries
-            uint8_t* o = p.out + p.od.row_off(tc.n, tc.y, 0, 0) + (size_t)(x + kRowPad) * 16;
+          if (valid && p.out != nullptr) {
 #pragma unroll
-            for (int j = 0; j < BN / 8; ++j) *reinterpret_cast<uint4*>(o + j * chunk_step) = w4[j];
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(p.out + pix * (size_t)(BN * 2));
+            for (int k = 0; k < 2; ++k) {
+              uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < BN / 8; ++j) o[j] = w4[j];
+              for (int t = 0; t < 4; ++t) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(yv[8 * k + 2 * t], yv[8 * k + 2 * t + 1]);
+                w[t] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(p.out + o_off + (size_t)(c / 8 + k) * o_step) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
           }
         }
+        if (HEAD && valid) reinterpret_cast<float4*>(p.head_out)[pix] = hacc;
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
@@ -532,9 +555,10 @@ void RowStemOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
 // one thread = 8 channels of one output pixel; all nine taps are in range thanks to the zero border
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_planar_kernel(const uint8_t* __restrict__ x, int n, int h, int w, int kcs,
-                                                              bf16* __restrict__ y) {
+                                                              uint8_t* __restrict__ y, int y_layout) {
   const PlanarDims d = PlanarDims::make(h, w, kcs * 8, LAYOUT_PLANAR_PARITY);
   const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+  const PlanarDims od = PlanarDims::make(oh, ow, kcs * 8, LAYOUT_PLANAR);
   const int64_t total = (int64_t)n * oh * ow * kcs;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // ox fastest: consecutive lanes read consecutive 16-byte entries of the same planar runs
@@ -572,15 +596,17 @@ __global__ void __launch_bounds__(256) maxpool_planar_kernel(const uint8_t* __re
       __nv_bfloat162 h2 = __floats2bfloat162_rn(m[2 * t], m[2 * t + 1]);
       o[t] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    *reinterpret_cast<uint4*>(y + (((int64_t)b * oh + oy) * ow + ox) * (kcs * 8) + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    const size_t off = (y_layout == LAYOUT_PLANAR) ? od.row_off(b, oy, g, 0) + (size_t)(ox + kRowPad) * 16
+                                                   : ((((size_t)b * oh + oy) * ow + ox) * kcs + g) * 16;
+    *reinterpret_cast<uint4*>(y + off) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
-void launch_maxpool_planar(const void* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc) {
+void launch_maxpool_planar(const void* x, int n, int h, int w, int c, void* y, int y_layout, cudaStream_t s, LaunchCounter* lc) {
   const int64_t total = (int64_t)n * ((h - 1) / 2 + 1) * ((w - 1) / 2 + 1) * (c / 8);
   if (total <= 0) return;
   const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
-  maxpool_planar_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(x), n, h, w, c / 8, y);
+  maxpool_planar_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(x), n, h, w, c / 8, static_cast<uint8_t*>(y), y_layout);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
@@ -620,8 +646,10 @@ void launch_relayout_planar(const void* src_nhwc, void* dst, int N, int H, int W
 // host side
 // ---------------------------------------------------------------------------------------------
 bool RowConvOp::eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual) {
-  if (spec.ksize != 3 || spec.stride != 1 || spec.pad != 1 || residual != nullptr) return false;
-  if (spec.cout != 16 && spec.cout != 32) return false;
+  if (spec.ksize != 3 || spec.stride != 1 || spec.pad != 1) return false;
+  if (spec.cout != 16 && spec.cout != 32 && spec.cout != 64) return false;
+  if (spec.cout == 64 && parts[0].up2) return false;            // TMEM: 4 stages x 2 accumulators x 64 columns = 512
+  (void)residual;
   if (spec.head && spec.cout != 16) return false;
   if (parts.empty() || parts.size() > 2) return false;
   int slabs = 0;
@@ -638,9 +666,10 @@ bool RowConvOp::eligible(const std::vector<ConvInputPart>& parts, const ConvSpec
 }
 
 void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw, const float* scale,
-                      const float* bias, void* out, int out_layout, const float* head_w, const float* head_b, float* head_out,
-                      int* error_flag, int num_sms) {
-  WSI_REQUIRE(eligible(parts, spec, nullptr), WSI_ERR_UNSUPPORTED, "conv is not eligible for the row-tile kernel");
+                      const float* bias, const void* residual, int res_layout, void* out, int out_layout, const float* head_w,
+                      const float* head_b, float* head_out, int* error_flag, int num_sms) {
+  WSI_REQUIRE(eligible(parts, spec, residual), WSI_ERR_UNSUPPORTED, "conv is not eligible for the row-tile kernel");
+  WSI_REQUIRE(res_layout == LAYOUT_NHWC || res_layout == LAYOUT_PLANAR, WSI_ERR_INVALID, "row conv: bad residual layout");
   RowParams& p = p_;
   p = RowParams{};
   relayouts_.clear();
@@ -684,6 +713,8 @@ void RowConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& s
   p.relu = spec.relu ? 1 : 0;
   p.out = static_cast<uint8_t*>(out);
   p.out_layout = out_layout;
+  p.res = static_cast<const uint8_t*>(residual);
+  p.res_layout = res_layout;
   WSI_REQUIRE(out_layout == LAYOUT_NHWC || out_layout == LAYOUT_PLANAR, WSI_ERR_INVALID, "row conv: bad output layout");
   p.od = PlanarDims::make(OH, OW, BN, LAYOUT_PLANAR);
   p.error_flag = error_flag;
@@ -795,9 +826,11 @@ void RowConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (p_.Cout == 16) {
     if (p_.up2) { if (head) launch_row<16, true, 2>(p_, grid_, smem_, stream); else launch_row<16, false, 2>(p_, grid_, smem_, stream); }
     else        { if (head) launch_row<16, true, 1>(p_, grid_, smem_, stream); else launch_row<16, false, 1>(p_, grid_, smem_, stream); }
-  } else {
+  } else if (p_.Cout == 32) {
     if (p_.up2) launch_row<32, false, 2>(p_, grid_, smem_, stream);
     else        launch_row<32, false, 1>(p_, grid_, smem_, stream);
+  } else {
+    launch_row<64, false, 1>(p_, grid_, smem_, stream);
   }
   if (lc) lc->n++;
 }

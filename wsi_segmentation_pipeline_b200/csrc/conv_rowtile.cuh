@@ -1,7 +1,8 @@
 // conv_rowtile.cuh — 3x3/s1 convolution for the high-resolution, small-channel layers (sm_100a).
 //
-// The decoder's last levels (smp Unet: 128->32->32 @ H/2, 32->16->16 @ H) have
-// 16..64 channels per operand and 16/32 output channels.  Per-tap TMA boxes move one 32..128-byte
+// The decoder's last levels (smp Unet: 128->32->32 @ H/2, 32->16->16 @ H) and the
+// 64->64 BasicBlocks of layer1 / decoder level 3 (resnets_shift.py:49-65) have 16..64 channels per operand
+// and 16/32/64 output channels.  Per-tap TMA boxes move one 32..128-byte
 // row per pixel per tap (9x re-reads, bound by the TMA box-row rate: measured ~4 cycles/row), and
 // 16-byte cp.async producers starve for memory-level parallelism (measured 2 TB/s).  Instead:
 //
@@ -81,6 +82,8 @@ struct RowParams {
   int relu;
   uint8_t* out;                  // bf16 output, or nullptr
   int out_layout;                // LAYOUT_NHWC or LAYOUT_PLANAR
+  const uint8_t* res;            // bf16 residual [N,OH,OW,BN] added before the ReLU, or nullptr
+  int res_layout;                // LAYOUT_NHWC or LAYOUT_PLANAR (same geometry as a planar output)
   PlanarDims od;                 // geometry of a planar output
   const float* head_w;           // [4][16] or nullptr
   const float* head_b;
@@ -94,8 +97,8 @@ class RowConvOp {
   static bool eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual);
   // parts / out may be NHWC (converted by an internal relayout launch; output written NHWC) or planar.
   void build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw, const float* scale,
-             const float* bias, void* out, int out_layout, const float* head_w, const float* head_b, float* head_out,
-             int* error_flag, int num_sms);
+             const float* bias, const void* residual, int res_layout, void* out, int out_layout, const float* head_w,
+             const float* head_b, float* head_out, int* error_flag, int num_sms);
   void launch(cudaStream_t stream, LaunchCounter* lc) const;
   double flops() const { return flops_; }
   int block_n() const { return p_.Cout; }
@@ -150,8 +153,9 @@ class RowStemOp {
 };
 
 // 3x3/s2/p1 max pool reading the stem's parity-planar output (values are post-ReLU >= 0, so the layout's
-// zero border is equivalent to the reference's -inf padding), writing NHWC
-void launch_maxpool_planar(const void* x_parity_planar, int n, int h, int w, int c, bf16* y_nhwc, cudaStream_t s, LaunchCounter* lc);
+// zero border is equivalent to the reference's -inf padding), writing NHWC or the planar layout
+void launch_maxpool_planar(const void* x_parity_planar, int n, int h, int w, int c, void* y, int y_layout, cudaStream_t s,
+                           LaunchCounter* lc);
 
 // NHWC bf16 -> padded planar (interior only; the zero border is written once at allocation)
 void launch_relayout_planar(const void* src_nhwc, void* dst, int N, int H, int W, int C, int layout, cudaStream_t s,

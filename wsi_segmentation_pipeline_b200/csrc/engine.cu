@@ -248,14 +248,23 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
     trace = getenv("WSI_CONV_TRACE") != nullptr;
   }
   // ---- maxpool 3x3/s2/p1 (:199) ----
-  Act* p0 = new_act(cap, (x0->H - 1) / 2 + 1, (x0->W - 1) / 2 + 1, 64);
+  // layer1's four 64->64 convs run on the row-tile kernel: the pooled tensor, the block-internal tensors and
+  // the first block's output stay in the planar layout (also as residuals); layer1's output goes back to NHWC
+  // for the TMA kernel (layer2, decoder level-3 skip)
+  bool l1_row = false;
+  {
+    ConvSpec sp; sp.ksize = 3; sp.stride = 1; sp.pad = 1; sp.cout = 64; sp.relu = true;
+    const ConvInputPart probe{TensorView{nullptr, cap, (x0->H - 1) / 2 + 1, (x0->W - 1) / 2 + 1, 64, LAYOUT_NHWC}, false};
+    l1_row = (x0_layout == LAYOUT_PLANAR_PARITY) && ConvOp::routes_to_rowtile({probe}, sp, nullptr);
+  }
+  Act* p0 = new_act(cap, (x0->H - 1) / 2 + 1, (x0->W - 1) / 2 + 1, 64, l1_row ? LAYOUT_PLANAR : LAYOUT_NHWC);
   steps.push_back(Step{1, ST_MAXPOOL, nullptr, x0, p0});
 
   auto add_conv = [&](const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w, const Folded* f,
                       const Act* res, Act* out, const float* hw = nullptr, const float* hb = nullptr, float* hout = nullptr) {
     ConvOp* op = new_op();
     op->build(parts, spec, w, f ? f->scale.data() : nullptr, f ? f->bias.data() : nullptr, res ? res->buf.p : nullptr,
-              out ? out->buf.p : nullptr, hw, hb, hout, ef, sms, out ? out->layout : LAYOUT_NHWC);
+              out ? out->buf.p : nullptr, hw, hb, hout, ef, sms, out ? out->layout : LAYOUT_NHWC, res ? res->layout : LAYOUT_NHWC);
     steps.push_back(Step{0, ST_CONV, op, nullptr, out});
     conv_flops += op->flops();
     char d[160];
@@ -278,7 +287,8 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
       const std::string q = tp + "layer" + std::to_string(li) + "." + std::to_string(b);
       const int bc_in = (b == 0) ? cin : cout;
       const int OH = (cur->H + 2 - 3) / stride + 1, OW = (cur->W + 2 - 3) / stride + 1;
-      Act* t = new_act(cap, OH, OW, cout);
+      const bool planar_block = l1_row && li == 1;
+      Act* t = new_act(cap, OH, OW, cout, planar_block ? LAYOUT_PLANAR : LAYOUT_NHWC);
       {
         const HostTensor& w = conv_weight(c, q + ".conv1.weight", cout, bc_in, 3);
         const Folded f = fold_bn(c, q + ".bn1", cout);
@@ -296,7 +306,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
       } else {
         WSI_REQUIRE(stride == 1 && bc_in == cout, WSI_ERR_NOMODEL, "block %s needs a downsample projection", q.c_str());
       }
-      Act* out = new_act(cap, OH, OW, cout);
+      Act* out = new_act(cap, OH, OW, cout, (planar_block && b == 0) ? LAYOUT_PLANAR : LAYOUT_NHWC);
       {
         const HostTensor& w = conv_weight(c, q + ".conv2.weight", cout, cout, 3);
         const Folded f = fold_bn(c, q + ".bn2", cout);
@@ -461,7 +471,7 @@ void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
         ++conv_idx;
       } else if (st.kind == 1) {
         if (st.in->layout == LAYOUT_PLANAR_PARITY)
-          launch_maxpool_planar(st.in->buf.p, st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
+          launch_maxpool_planar(st.in->buf.p, st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.p, st.out->layout, s, &c->lc);
         else
           launch_maxpool(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
       } else {
