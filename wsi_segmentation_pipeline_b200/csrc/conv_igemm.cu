@@ -171,53 +171,73 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   for (int i = 0; i < kMaxAMaps; ++i)  // unused slots alias map 0 so every descriptor is valid
     if (i >= (any_up ? (parts.size() == 2 ? 5 : 1) : (spec.stride == 1 ? (int)parts.size() : 4))) amaps_.m[i] = amaps_.m[0];
 
-  // K-block table (per parity) and packed weights (parity independent)
+  // K-block table and packed weights.  Plain / strided convs: one table, one weight matrix.  x2-upsample
+  // convs: per parity class, the upsampled operand contributes its 4 collapsed positions (weights = fp32 sum
+  // of the taps that read that half-resolution pixel), the skip operand its 9 taps; weights are packed per parity.
   const int taps = k * k;
-  int kb_per_tap = 0;
-  for (auto& q : parts) kb_per_tap += q.t.C / bk;
-  const int num_kb = taps * kb_per_tap;
+  int kb_per_par = 0;
+  for (auto& q : parts) kb_per_par += (q.t.C / bk) * ((any_up && q.up2) ? 4 : taps);
+  const int num_kb = kb_per_par;
   WSI_REQUIRE(num_kb <= 128, WSI_ERR_UNSUPPORTED, "conv: %d K blocks > 128", num_kb);
   const int K = num_kb * bk;
-  std::vector<uint16_t> wp((size_t)spec.cout * K);
+  const int wsets = any_up ? 4 : 1;
+  std::vector<uint16_t> wp((size_t)spec.cout * K * wsets);
+  const size_t Ktot = (size_t)K * wsets;          // row length of the packed [Cout][wsets*K] matrix
+  auto w_at = [&](int co, int ci, int r, int s) { return w_oihw[(((size_t)co * cin + ci) * k + r) * k + s]; };
   for (int par = 0; par < num_parity; ++par) {
     const int py = par >> 1, px = par & 1;
-    for (int r = 0; r < k; ++r)
-      for (int s = 0; s < k; ++s) {
-        int part_off = 0;
-        for (size_t pi = 0; pi < parts.size(); ++pi) {
-          const auto& q = parts[pi];
+    int kbi = 0;
+    int part_off = 0;
+    for (size_t pi = 0; pi < parts.size(); ++pi) {
+      const auto& q = parts[pi];
+      if (any_up && q.up2) {
+        for (int pos = 0; pos < 4; ++pos)
           for (int c0 = 0; c0 < q.t.C; c0 += bk) {
             KBlock e{};
-            e.c0 = c0;
-            if (any_up) {
-              const int ty = py + r - 1, tx = px + s - 1;
-              if (q.up2) {
-                e.map = 0; e.da = (int8_t)floor_div2(ty); e.db = (int8_t)floor_div2(tx);
-              } else {
+            e.c0 = c0; e.map = 0;
+            e.da = (int8_t)(floor_div2(py - 1) + (pos >> 1));
+            e.db = (int8_t)(floor_div2(px - 1) + (pos & 1));
+            for (int co = 0; co < spec.cout; ++co)
+              for (int j = 0; j < bk; ++j) {
+                float v = 0.f;
+                for (int r = 0; r < 3; ++r)
+                  for (int s2 = 0; s2 < 3; ++s2) {
+                    const int dy = floor_div2(py + r - 1) - floor_div2(py - 1), dx = floor_div2(px + s2 - 1) - floor_div2(px - 1);
+                    if (dy * 2 + dx == pos) v += w_at(co, part_off + c0 + j, r, s2);
+                  }
+                wp[(size_t)co * Ktot + (size_t)par * K + (size_t)kbi * bk + j] = f32_to_bf16_bits(v);
+              }
+            table.push_back(e);
+            ++kbi;
+          }
+      } else {
+        for (int r = 0; r < k; ++r)
+          for (int s2 = 0; s2 < k; ++s2)
+            for (int c0 = 0; c0 < q.t.C; c0 += bk) {
+              KBlock e{};
+              e.c0 = c0;
+              if (any_up) {
+                const int ty = py + r - 1, tx = px + s2 - 1;
                 const int hp = ty & 1, wpp = tx & 1;
                 e.map = (int8_t)(1 + hp * 2 + wpp); e.da = (int8_t)((ty - hp) / 2); e.db = (int8_t)((tx - wpp) / 2);
+              } else if (spec.stride == 1) {
+                e.map = (int8_t)pi; e.da = (int8_t)(r - spec.pad); e.db = (int8_t)(s2 - spec.pad);
+              } else {
+                const int ty = r - spec.pad, tx = s2 - spec.pad;
+                const int hp = ty & 1, wpp = tx & 1;
+                e.map = (int8_t)(hp * 2 + wpp); e.da = (int8_t)((ty - hp) / 2); e.db = (int8_t)((tx - wpp) / 2);
               }
-            } else if (spec.stride == 1) {
-              e.map = (int8_t)pi; e.da = (int8_t)(r - spec.pad); e.db = (int8_t)(s - spec.pad);
-            } else {
-              const int ty = r - spec.pad, tx = s - spec.pad;
-              const int hp = ty & 1, wpp = tx & 1;
-              e.map = (int8_t)(hp * 2 + wpp); e.da = (int8_t)((ty - hp) / 2); e.db = (int8_t)((tx - wpp) / 2);
-            }
-            if (par == 0) {
-              const int kb = (int)table.size();
               for (int co = 0; co < spec.cout; ++co)
-                for (int j = 0; j < bk; ++j) {
-                  const float v = w_oihw[(((size_t)co * cin + part_off + c0 + j) * k + r) * k + s];
-                  wp[(size_t)co * K + (size_t)kb * bk + j] = f32_to_bf16_bits(v);
-                }
+                for (int j = 0; j < bk; ++j)
+                  wp[(size_t)co * Ktot + (size_t)par * K + (size_t)kbi * bk + j] = f32_to_bf16_bits(w_at(co, part_off + c0 + j, r, s2));
+              table.push_back(e);
+              ++kbi;
             }
-            table.push_back(e);
-          }
-          part_off += q.t.C;
-        }
       }
+      part_off += q.t.C;
+    }
   }
+  p.b_parity_stride = any_up ? K : 0;
   p.num_kb = num_kb;
   flops_ = 2.0 * N * OH * OW * (double)spec.cout * cin * taps;
 
@@ -228,7 +248,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
     p.head_w = headw_.as<float>(); p.head_b = headb_.as<float>(); p.head_out = head_out;
     flops_ += 2.0 * N * OH * OW * 16 * 4;
   }
-  finish(table, num_parity, wp, K, scale, bias, num_sms);
+  finish(table, num_parity, wp, K * wsets, scale, bias, num_sms);
 }
 
 bool ConvOp::stem_routes_to_rowtile() { return getenv("WSI_NO_ROWTILE") == nullptr; }
@@ -302,7 +322,7 @@ void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std:
   {
     const int bbytes = (block_n_ * block_k_ * 2 + 1023) / 1024 * 1024;
     resb_ = (p.tiles_co == 1) && (block_k_ == 64) && (block_n_ == 64 || block_n_ == 128) &&
-            ((long long)p.num_kb * bbytes <= kResidentBBytes) && getenv("WSI_NO_RESB") == nullptr;
+            ((long long)p.num_kb * bbytes <= kResidentBBytes) && p.b_parity_stride == 0 && getenv("WSI_NO_RESB") == nullptr;
   }
   CUDA_CHECK(cudaStreamSynchronize(0));   // uploads above used the default stream
 }

@@ -15,7 +15,9 @@
 // * the decoder's nearest x2 upsample + channel concat is folded into the operand addressing:
 //   output pixels are processed per parity class (oh%2, ow%2), for which every tap of the
 //   upsampled operand is a plain box of the half-resolution tensor, and the skip operand is a
-//   parity view.  No upsampled or concatenated tensor ever exists in HBM.
+//   parity view.  No upsampled or concatenated tensor ever exists in HBM.  Within a parity class
+//   the 9 taps of the upsampled operand read only 2 x 2 distinct half-resolution pixels, so their
+//   weights are summed (fp32, per parity) on the host: 4 K blocks per channel chunk instead of 9.
 // * the stem reads the gather kernel's zero-padded 4-channel tiles through an overlapping-window
 //   map (dim1 stride 16 B): one K block = one filter row = 8 px x 4 ch = 32 elements.
 // * B (weights) is pre-packed [Cout][K] bf16, K ordered exactly as the K-block table.
@@ -61,6 +63,7 @@ struct ConvParams {
   const float* head_b;        // [4]
   float* head_out;            // [N, OH, OW, 4] fp32
   const KBlock* kblocks;      // [num_parity][num_kb]
+  int b_parity_stride;        // K offset (elements) between the packed weights of consecutive parity classes (0: shared)
   int* error_flag;            // set to 1 by a timed-out barrier wait
 };
 
@@ -299,7 +302,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             default: break;
           }
           ptx::tma_load_4d(sA, am, &full[stage], e.c0, b0 + e.db, a0 + e.da, n0);
-          if (!RESB) ptx::tma_load_2d(sB, &bmap, &full[stage], kb * BLOCK_K, co0);
+          if (!RESB) ptx::tma_load_2d(sB, &bmap, &full[stage], par * p.b_parity_stride + kb * BLOCK_K, co0);
           if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
         }
       }
