@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <mutex>
 
+#include "conv_rowstream.cuh"
 #include "conv_rowtile.cuh"
 
 namespace wsi {
@@ -100,6 +101,17 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
                    const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms, int out_layout,
                    int res_layout) {
   WSI_REQUIRE(!parts.empty() && parts.size() <= 2, WSI_ERR_INVALID, "conv: 1 or 2 input parts");
+  stream_.reset();
+  if (routes_to_rowtile(parts, spec, residual) && RowStreamOp::eligible(parts, spec) && getenv("WSI_NO_ROWSTREAM") == nullptr) {
+    stream_.reset(new RowStreamOp());
+    stream_->build(parts[0], spec, w_oihw, scale, bias, residual, res_layout, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
+    flops_ = stream_->flops();
+    block_n_ = spec.cout;
+    block_k_ = 16;
+    row_.reset();
+    stem_.reset();
+    return;
+  }
   if (routes_to_rowtile(parts, spec, residual)) {
     row_.reset(new RowConvOp());
     row_->build(parts, spec, w_oihw, scale, bias, residual, res_layout, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
@@ -257,6 +269,7 @@ void ConvOp::build_stem(const void* padded_tiles, int n, int ph, int pw, const f
                         const float* bias, void* out, int* error_flag, int num_sms, int out_layout) {
   WSI_REQUIRE(ph % 2 == 0 && pw % 2 == 0, WSI_ERR_UNSUPPORTED, "stem: tile size must be even");
   row_.reset();
+  stream_.reset();
   if (stem_routes_to_rowtile()) {
     stem_.reset(new RowStemOp());
     stem_->build(padded_tiles, n, ph, pw, w_oihw, scale, bias, out, out_layout, error_flag, num_sms);
@@ -341,6 +354,7 @@ static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams
 }
 
 void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
+  if (stream_) { stream_->launch(stream, lc); return; }
   if (row_) { row_->launch(stream, lc); return; }
   if (stem_) { stem_->launch(stream, lc); return; }
   if (resb_) {

@@ -500,6 +500,7 @@ struct ConvSpec {
 
 class RowConvOp;   // conv_rowtile.cuh: halo-resident kernel for the small-channel 3x3 layers
 class RowStemOp;   // conv_rowtile.cuh: the stem in the same style
+class RowStreamOp; // conv_rowstream.cuh: row-streaming kernel for plain 3x3 convs on <= 64 channels
 
 // A fully prepared conv launch: tensor maps, K-block table, packed weights, epilogue params.
 // build() routes small-channel 3x3/s1 convs to the row-tile kernel (conv_rowtile.cuh) and
@@ -540,6 +541,7 @@ class ConvOp {
   DevBuf w_, scale_, bias_, tbl_, headw_, headb_;
   std::unique_ptr<RowConvOp> row_;
   std::unique_ptr<RowStemOp> stem_;
+  std::unique_ptr<RowStreamOp> stream_;
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
   bool resb_ = false;         // weights resident in smem (see conv_igemm_kernel RESB)
   double flops_ = 0;

@@ -1,0 +1,436 @@
+// conv_rowstream.cu — see conv_rowstream.cuh.
+#include "conv_rowstream.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace wsi {
+
+namespace sptx {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace sptx
+
+__device__ __forceinline__ uint64_t stream_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// instruction descriptor: D fp32, A/B bf16 K-major, M = 128, N given at run time
+__device__ __forceinline__ uint32_t stream_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+struct UnitCoord {   // unit u -> (image n, column block xb, row segment seg); consecutive units walk down a strip
+  int n, xb, seg;
+  __device__ __forceinline__ void init(int u, int segs, int tiles_x) {
+    seg = u % segs;
+    const int t = u / segs;
+    xb = t % tiles_x;
+    n = t / tiles_x;
+  }
+  __device__ __forceinline__ void next(int segs, int tiles_x) {
+    if (++seg == segs) {
+      seg = 0;
+      if (++xb == tiles_x) { xb = 0; ++n; }
+    }
+  }
+};
+
+template <int BN, bool HEAD>
+__global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const __grid_constant__ StreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int RS = kStreamRing;
+  const int w_bytes = p.nslabs * 3 * 2 * 3 * BN * 16;
+  uint8_t* s_w = smem;
+  float* s_scale = reinterpret_cast<float*>(smem + w_bytes);
+  float* s_bias = s_scale + BN;
+  float* s_hw = s_bias + BN;
+  float* s_hb = s_hw + 64;
+  uint8_t* s_stage = smem + ((w_bytes + (2 * BN + 68) * 4 + 127) & ~127);
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + (size_t)S * (p.nslabs * kStreamStageBytes));
+  uint64_t* full = bars;                 // producer -> MMA: input row landed
+  uint64_t* empty = bars + S;            // MMA -> producer AND epilogue: all MMAs of this input row retired
+  uint64_t* slot_free = bars + 2 * S;    // epilogue -> MMA: accumulator slot drained
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S + RS);
+  const int stage_bytes = p.nslabs * kStreamStageBytes;
+  constexpr uint32_t kTmemCols = RS * BN;
+  static_assert(kTmemCols >= 32 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    for (int i = threadIdx.x; i < w_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) { s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i]; }
+    if (HEAD)
+      for (int i = threadIdx.x; i < 68; i += blockDim.x) s_hw[i] = (i < 64) ? p.head_w[i] : p.head_b[i - 64];
+    uint4* st = reinterpret_cast<uint4*>(s_stage);
+    for (int i = threadIdx.x; i < S * stage_bytes / 16; i += blockDim.x) st[i] = make_uint4(0, 0, 0, 0);
+    sptx::fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < RS; ++i) ptx::mbar_init(&slot_free[i], 128);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_holder, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  const int u_begin = (int)((long long)p.total_units * blockIdx.x / gridDim.x);
+  const int u_end = (int)((long long)p.total_units * (blockIdx.x + 1) / gridDim.x);
+  const int L = p.seg_rows;
+
+  if (warp == 0) {
+    // ================================ producer ==========================================
+    // one pipeline stage = one input row, all slabs: lane l copies chunk run l (2 runs per 16-channel slab)
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t stage0 = ptx::smem_u32(s_stage);
+    const size_t run_step = (size_t)p.d.Wrow * 16;
+    const int nruns = 2 * p.nslabs;
+    UnitCoord uc;
+    uc.init(u_begin, p.segs, p.tiles_x);
+    for (int u = u_begin; u < u_end; ++u, uc.next(p.segs, p.tiles_x)) {
+      const int y0 = uc.seg * L;
+      const int Lu = min(L, p.OH - y0);
+      const int b0 = uc.xb * 128;
+      const uint32_t bytes = (uint32_t)min(kRowHaloCols, p.d.Wrow - b0) * 16u;
+      const uint8_t* rowp = p.in + p.d.row_off(uc.n, y0 - 1, 0, 0) + (size_t)b0 * 16 + (size_t)(lane < nruns ? lane : 0) * run_step;
+      const size_t row_step = (size_t)p.d.KC * run_step;
+      for (int t = 0; t < Lu + 2; ++t) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 31);
+        if (lane == 0) ptx::mbar_expect_tx(&full[stage], (uint32_t)nruns * bytes);
+        __syncwarp();
+        if (lane < nruns) sptx::bulk_g2s(stage0 + (uint32_t)(stage * stage_bytes + lane * kRowRunBytes), rowp + (size_t)t * row_step, bytes, &full[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ========================================
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_holder);
+    if (ptx::elect_one()) {
+      const uint64_t a_desc0 = stream_nosw_desc(ptx::smem_u32(s_stage), kRowRunBytes, 128);
+      const uint64_t b_desc0 = stream_nosw_desc(ptx::smem_u32(s_w), 3 * BN * 16, 128);
+      const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
+      constexpr uint32_t kSlabUnits = kStreamStageBytes >> 4;      // A: next 16-channel slab of the row
+      constexpr uint32_t kWSlab = 3 * 2 * 3 * BN, kWShift = 2 * 3 * BN;   // B: next slab / next horizontal shift (16-byte units)
+      const uint32_t id1 = stream_idesc(BN), id2 = stream_idesc(2 * BN), id3 = stream_idesc(3 * BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int job0 = 0;                                    // output-row jobs issued by this CTA before the current unit
+      // blocks [a, b] of the stacked weights (block 2-r <-> vertical tap r) into the slots of rows i = t-2+a .. t-2+b
+      auto issue = [&](uint64_t a_desc, uint64_t b_desc, int jrow_a, int a, int b, uint32_t accumulate) {
+        int cnt = b - a + 1;
+        int slot = jrow_a % RS;
+        int blk = a;
+        while (cnt > 0) {
+          const int n_here = min(cnt, RS - slot);      // split where the ring wraps
+          ptx::umma_bf16(tmem_base + (uint32_t)(slot * BN), a_desc, b_desc + (uint64_t)(blk * BN), stream_idesc(n_here * BN), accumulate);
+          cnt -= n_here;
+          blk += n_here;
+          slot = 0;
+        }
+      };
+      for (int u = u_begin; u < u_end; ++u) {
+        const int seg = u % p.segs;
+        const int y0 = seg * L;
+        const int Lu = min(L, p.OH - y0);
+        for (int t = 0; t < Lu + 2; ++t) {
+          const bool opens = (t <= Lu - 1);            // output row i = t gets its first contribution from this input row
+          if (opens) {
+            const int j = job0 + t;
+            ptx::mbar_wait(&slot_free[j % RS], (uint32_t)(((j / RS) & 1) ^ 1), p.error_flag, 32);
+          }
+          const uint64_t a_row = a_desc0 + (uint64_t)((uint32_t)stage * stage_units) + (uint64_t)(kRowPad - 1);
+          ptx::mbar_wait(&full[stage], phase, p.error_flag, 33);
+          ptx::tc_fence_after();
+          const int slot_lo = (job0 + t - 2 + RS) % RS;
+          if (t >= 2 && opens && slot_lo <= RS - 3) {
+            // fast path (interior row, the three target slots are contiguous): 3 MMAs of N = 3*BN per slab,
+            // except that the very first one is split so that the newly opened row is overwritten
+            const uint32_t d_lo = tmem_base + (uint32_t)(slot_lo * BN);
+            ptx::umma_bf16(d_lo + 2 * BN, a_row, b_desc0 + (uint64_t)(2 * BN), id1, 0u);
+            ptx::umma_bf16(d_lo, a_row, b_desc0, id2, 1u);
+            ptx::umma_bf16(d_lo, a_row + 1, b_desc0 + (uint64_t)kWShift, id3, 1u);
+            ptx::umma_bf16(d_lo, a_row + 2, b_desc0 + (uint64_t)(2 * kWShift), id3, 1u);
+#pragma unroll 1
+            for (int sl = 1; sl < p.nslabs; ++sl) {
+              const uint64_t a_sl = a_row + (uint64_t)(sl * kSlabUnits), b_sl = b_desc0 + (uint64_t)(sl * kWSlab);
+              ptx::umma_bf16(d_lo, a_sl, b_sl, id3, 1u);
+              ptx::umma_bf16(d_lo, a_sl + 1, b_sl + (uint64_t)kWShift, id3, 1u);
+              ptx::umma_bf16(d_lo, a_sl + 2, b_sl + (uint64_t)(2 * kWShift), id3, 1u);
+            }
+          } else {
+            const int i_lo = max(0, t - 2), i_hi = min(Lu - 1, t);
+            const int blk_lo = 2 - t + i_lo, blk_hi = 2 - t + i_hi;
+            for (int sl = 0; sl < p.nslabs; ++sl) {
+              for (int sft = 0; sft < 3; ++sft) {
+                const uint64_t a_desc = a_row + (uint64_t)(sl * kSlabUnits + sft);
+                const uint64_t b_desc = b_desc0 + (uint64_t)(sl * kWSlab + sft * kWShift);
+                if (sl == 0 && sft == 0 && opens) {
+                  issue(a_desc, b_desc, job0 + t, 2, 2, 0u);                                    // overwrite the new row
+                  if (blk_lo <= 1) issue(a_desc, b_desc, job0 + t - 2 + blk_lo, blk_lo, 1, 1u);
+                } else {
+                  issue(a_desc, b_desc, job0 + t - 2 + blk_lo, blk_lo, blk_hi, 1u);
+                }
+              }
+            }
+          }
+          // ONE commit per input row: it frees the stage for the producer and tells the epilogue that output
+          // row i = t-2 is complete (a tcgen05.commit drains the tensor pipe — ~600 cycles measured — so the
+          // number of commits, not of MMAs, bounded the previous schedules)
+          ptx::umma_commit(&empty[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        job0 += Lu;
+      }
+    }
+  } else {
+    // ================================ epilogue (2 x 4 warps) ============================
+    const uint32_t tmem_base = *tmem_holder;
+    const int q = warp & 3;
+    const int egrp = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    constexpr int RB = (BN <= 32) ? BN : 1;
+    float r_scale[RB], r_bias[RB];
+    if (BN <= 32) {
+#pragma unroll
+      for (int j = 0; j < RB; ++j) { r_scale[j] = s_scale[j]; r_bias[j] = s_bias[j]; }
+    }
+    float r_hw[HEAD ? 64 : 1], r_hb[HEAD ? 4 : 1];
+    if (HEAD) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) r_hw[HEAD ? j : 0] = s_hw[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r_hb[HEAD ? j : 0] = s_hb[j];
+    }
+    const float lo = p.relu ? 0.f : -INFINITY;
+    const bool planar_out = (p.out_layout == LAYOUT_PLANAR);
+    const bool planar_res = (p.res_layout == LAYOUT_PLANAR);
+    const size_t chunk_step = (size_t)p.od.Wrow * 16;
+    int job = 0;
+    int g0 = 0;                     // input rows consumed by this CTA before the current unit (stage counter)
+    UnitCoord uc;
+    uc.init(u_begin, p.segs, p.tiles_x);
+    for (int u = u_begin; u < u_end; ++u, uc.next(p.segs, p.tiles_x)) {
+      const int y0 = uc.seg * L;
+      const int Lu = min(L, p.OH - y0);
+      const int x = uc.xb * 128 + row;
+      const bool valid = x < p.OW;
+      for (int i = 0; i < Lu; ++i, ++job) {
+        if ((job & 1) != egrp) continue;
+        const int y = y0 + i;
+        const int slot = job % RS;
+        const size_t pix = ((size_t)uc.n * p.OH + y) * p.OW + x;
+        const size_t prow = p.od.row_off(uc.n, y, 0, 0);
+        // output row i is complete when the MMAs of input row t = i+2 have retired: that is the commit on that
+        // row's stage barrier (the ring cannot lap: the MMA warp needs this slot back before it gets S rows ahead)
+        const int g = g0 + i + 2;
+        ptx::mbar_wait(&empty[g % S], (uint32_t)((g / S) & 1), p.error_flag, 34);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
+        const size_t o_off = planar_out ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
+        const size_t o_step = planar_out ? chunk_step : 16;
+        const size_t r_off = planar_res ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
+        const size_t r_step = planar_res ? chunk_step : 16;
+        const bool has_res = (p.res != nullptr) && valid;
+        float4 hacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld16(t_row + (uint32_t)c, v);
+          uint4 rv[2];
+          if (has_res) {
+            rv[0] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)(c / 8) * r_step));
+            rv[1] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)(c / 8 + 1) * r_step));
+          }
+          ptx::tmem_ld_wait();
+          float yv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float sc = (BN <= 32) ? r_scale[(BN <= 32) ? c + j : 0] : s_scale[c + j];
+            const float bi = (BN <= 32) ? r_bias[(BN <= 32) ? c + j : 0] : s_bias[c + j];
+            yv[j] = fmaf(__uint_as_float(v[j]), sc, bi);
+          }
+          if (has_res) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t w[4] = {rv[k].x, rv[k].y, rv[k].z, rv[k].w};
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                yv[8 * k + 2 * tt + 0] += __uint_as_float(w[tt] << 16);
+                yv[8 * k + 2 * tt + 1] += __uint_as_float(w[tt] & 0xffff0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) yv[j] = fmaxf(yv[j], lo);
+          if (HEAD) {
+            float* hp = reinterpret_cast<float*>(&hacc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float s0 = 0.f, s1 = 0.f;      // two independent chains per logit, summed in a fixed order
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                s0 = fmaf(yv[j], r_hw[HEAD ? k * 16 + j : 0], s0);
+                s1 = fmaf(yv[j + 1], r_hw[HEAD ? k * 16 + j + 1 : 0], s1);
+              }
+              hp[k] = (s0 + s1) + r_hb[HEAD ? k : 0];
+            }
+          }
+          if (valid && p.out != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              uint32_t w[4];
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(yv[8 * k + 2 * tt], yv[8 * k + 2 * tt + 1]);
+                w[tt] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(p.out + o_off + (size_t)(c / 8 + k) * o_step) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+        if (HEAD && valid) reinterpret_cast<float4*>(p.head_out)[pix] = hacc;
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&slot_free[slot]);
+      }
+      g0 += Lu + 2;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(*tmem_holder, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+bool RowStreamOp::eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec) {
+  if (spec.ksize != 3 || spec.stride != 1 || spec.pad != 1) return false;
+  if (spec.cout != 16 && spec.cout != 32 && spec.cout != 64) return false;
+  if (spec.head && spec.cout != 16) return false;
+  if (parts.size() != 1 || parts[0].up2) return false;
+  const int C = parts[0].t.C;
+  return C % 16 == 0 && C > 0 && C <= 64;
+}
+
+void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const float* w_oihw, const float* scale, const float* bias,
+                        const void* residual, int res_layout, void* out, int out_layout, const float* head_w, const float* head_b,
+                        float* head_out, int* error_flag, int num_sms) {
+  StreamParams& p = p_;
+  p = StreamParams{};
+  const TensorView& t = part.t;
+  const int N = t.N, OH = t.H, OW = t.W, C = t.C, BN = spec.cout;
+  p.d = PlanarDims::make(t.H, t.W, C, LAYOUT_PLANAR);
+  relayout_ = false;
+  if (t.layout == LAYOUT_NHWC) {
+    stage_in_.alloc(p.d.bytes(N));
+    CUDA_CHECK(cudaMemset(stage_in_.p, 0, stage_in_.bytes));
+    relayout_ = true;
+    relayout_src_ = t.ptr;
+    p.in = stage_in_.as<uint8_t>();
+  } else {
+    WSI_REQUIRE(t.layout == LAYOUT_PLANAR, WSI_ERR_INVALID, "row-stream conv: operand layout %d", t.layout);
+    p.in = static_cast<const uint8_t*>(t.ptr);
+  }
+  WSI_REQUIRE(out_layout == LAYOUT_NHWC || out_layout == LAYOUT_PLANAR, WSI_ERR_INVALID, "row-stream conv: bad output layout");
+  WSI_REQUIRE(res_layout == LAYOUT_NHWC || res_layout == LAYOUT_PLANAR, WSI_ERR_INVALID, "row-stream conv: bad residual layout");
+  p.nslabs = C / 16;
+  p.N = N; p.OH = OH; p.OW = OW; p.Cout = BN;
+  p.tiles_x = (int)ceil_div(OW, 128);
+  // row segments: long enough that the 2 extra halo rows are cheap, short enough for >= ~4 units per SM
+  const long long strips = (long long)N * p.tiles_x;
+  int L = OH;
+  while (L > 16 && strips * ceil_div(OH, L) < 4LL * num_sms) L = (L + 1) / 2;
+  p.seg_rows = L;
+  p.segs = (int)ceil_div(OH, L);
+  const long long total = strips * p.segs;
+  WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "row-stream conv: too many units");
+  p.total_units = (int)total;
+  p.relu = spec.relu ? 1 : 0;
+  p.out = static_cast<uint8_t*>(out);
+  p.out_layout = out_layout;
+  p.od = PlanarDims::make(OH, OW, BN, LAYOUT_PLANAR);
+  p.res = static_cast<const uint8_t*>(residual);
+  p.res_layout = res_layout;
+  p.error_flag = error_flag;
+  // stacked weights: [slab][s][2 chunks][3*BN][8], N order = vertical tap r = 2 | 1 | 0
+  std::vector<uint16_t> wp((size_t)p.nslabs * 3 * 2 * 3 * BN * 8);
+  for (int sl = 0; sl < p.nslabs; ++sl)
+    for (int s = 0; s < 3; ++s)
+      for (int ch = 0; ch < 2; ++ch)
+        for (int blk = 0; blk < 3; ++blk)
+          for (int n = 0; n < BN; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int r = 2 - blk, ci = sl * 16 + ch * 8 + e;
+              const float v = w_oihw[(((size_t)n * C + ci) * 3 + r) * 3 + s];
+              wp[(((((size_t)sl * 3 + s) * 2 + ch) * 3 + blk) * BN + n) * 8 + e] = f32_to_bf16_bits(v);
+            }
+  upload(w_, wp);
+  std::vector<float> sc(BN, 1.f), bi(BN, 0.f);
+  if (scale) sc.assign(scale, scale + BN);
+  if (bias) bi.assign(bias, bias + BN);
+  upload(scale_, sc);
+  upload(bias_, bi);
+  p.w = w_.as<bf16>(); p.scale = scale_.as<float>(); p.bias = bias_.as<float>();
+  flops_ = 2.0 * N * OH * OW * (double)BN * C * 9;
+  if (spec.head) {
+    WSI_REQUIRE(head_w && head_b && head_out, WSI_ERR_INVALID, "fused head needs weights and an output");
+    std::vector<float> hw(head_w, head_w + 64), hb(head_b, head_b + 4);
+    upload(headw_, hw);
+    upload(headb_, hb);
+    p.head_w = headw_.as<float>(); p.head_b = headb_.as<float>(); p.head_out = head_out;
+    flops_ += 2.0 * N * OH * OW * 16 * 4;
+  }
+  const int w_bytes = p.nslabs * 3 * 2 * 3 * BN * 16;
+  const int fixed = 128 + ((w_bytes + (2 * BN + 68) * 4 + 127) & ~127) + 1024;
+  const int stage_bytes = p.nslabs * kStreamStageBytes;
+  p.stages = std::min(24, (226 * 1024 - fixed) / stage_bytes);
+  WSI_REQUIRE(p.stages + 2 >= kStreamRing, WSI_ERR_UNSUPPORTED, "row-stream conv: not enough shared memory");   // see the epilogue wait
+  smem_ = fixed + p.stages * stage_bytes;
+  grid_ = (int)std::min<long long>(total, num_sms);
+  CUDA_CHECK(cudaStreamSynchronize(0));
+}
+
+template <int BN, bool HEAD>
+static void launch_stream(const StreamParams& p, int grid, int smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(conv_rowstream_kernel<BN, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    configured = true;
+  }
+  conv_rowstream_kernel<BN, HEAD><<<grid, kStreamThreads, smem, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void RowStreamOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
+  if (relayout_) launch_relayout_planar(relayout_src_, stage_in_.p, p_.N, p_.OH, p_.OW, p_.nslabs * 16, LAYOUT_PLANAR, stream, lc);
+  const bool head = p_.head_out != nullptr;
+  if (p_.Cout == 16) { if (head) launch_stream<16, true>(p_, grid_, smem_, stream); else launch_stream<16, false>(p_, grid_, smem_, stream); }
+  else if (p_.Cout == 32) launch_stream<32, false>(p_, grid_, smem_, stream);
+  else launch_stream<64, false>(p_, grid_, smem_, stream);
+  if (lc) lc->n++;
+}
+
+}  // namespace wsi
