@@ -241,25 +241,26 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
         const size_t prow = p.od.row_off(uc.n, y, 0, 0);
         // output row i is complete when the MMAs of input row t = i+2 have retired: that is the commit on that
         // row's stage barrier (the ring cannot lap: the MMA warp needs this slot back before it gets S rows ahead)
-        const int g = g0 + i + 2;
-        ptx::mbar_wait(&empty[g % S], (uint32_t)((g / S) & 1), p.error_flag, 34);
-        ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
         const size_t o_off = planar_out ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
         const size_t o_step = planar_out ? chunk_step : 16;
         const size_t r_off = planar_res ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
         const size_t r_step = planar_res ? chunk_step : 16;
         const bool has_res = (p.res != nullptr) && valid;
+        // the whole residual row of this pixel is requested before waiting for the accumulator
+        uint4 rall[BN / 8];
+        if (has_res) {
+#pragma unroll
+          for (int k = 0; k < BN / 8; ++k) rall[k] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)k * r_step));
+        }
+        const int g = g0 + i + 2;
+        ptx::mbar_wait(&empty[g % S], (uint32_t)((g / S) & 1), p.error_flag, 34);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
         float4 hacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < BN; c += 16) {
           uint32_t v[16];
           ptx::tmem_ld16(t_row + (uint32_t)c, v);
-          uint4 rv[2];
-          if (has_res) {
-            rv[0] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)(c / 8) * r_step));
-            rv[1] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)(c / 8 + 1) * r_step));
-          }
           ptx::tmem_ld_wait();
           float yv[16];
 #pragma unroll
@@ -271,7 +272,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           if (has_res) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              const uint32_t w[4] = {rv[k].x, rv[k].y, rv[k].z, rv[k].w};
+              const uint4 rv = rall[c / 8 + k];
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int tt = 0; tt < 4; ++tt) {
                 yv[8 * k + 2 * tt + 0] += __uint_as_float(w[tt] << 16);
