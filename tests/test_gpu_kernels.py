@@ -112,7 +112,9 @@ CONV_CASES = [
     (2, 20, 28, 64, 64, 3, 1, 1, False, False),      # extents that are not powers of two
     (1, 64, 64, 64, 64, 3, 1, 1, True, True),        # many M tiles per CTA (persistent loop, 2 TMEM buffers)
     (2, 2, 2, 512, 512, 3, 1, 1, False, True),       # 2x2 feature map (64 px tiles at /32)
-    # row-tile kernel (cout 16/32, <=64 channels per operand): halo-resident taps, cp.async producers
+    (20, 48, 48, 64, 256, 3, 1, 1, True, True),      # BLOCK_N 256 (enough M tiles for every SM), residual
+    (6, 64, 64, 256, 512, 3, 1, 1, False, True),     # BLOCK_N 256, two N tiles, K = 2304
+    # row-tile / row-stream kernels (cout 16/32/64, <=64 channels per operand): halo-resident taps, cp.async producers
     (2, 40, 300, 32, 32, 3, 1, 1, False, True),      # 3 x-tiles per row, ragged last tile
     (1, 24, 136, 16, 16, 3, 1, 1, False, False),     # 1 slab, no relu
     (3, 8, 8, 64, 32, 3, 1, 1, False, True),         # 4 slabs, rows shorter than the tile

@@ -141,8 +141,15 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   for (auto& q : parts) while (q.t.C % bk) bk /= 2;
   const int OH = (Hin + 2 * spec.pad - k) / spec.stride + 1, OW = (Win + 2 * spec.pad - k) / spec.stride + 1;
   WSI_REQUIRE(spec.cout % 16 == 0 && spec.cout <= 512, WSI_ERR_UNSUPPORTED, "conv: cout (%d) must be a multiple of 16, at most 512", spec.cout);
+  // Output-channel tile.  The MMA rate is bound by the shared-memory operand fetch (~50 B/clk measured), so a
+  // 128x256 tile (12 KB of operands per 128 math cycles) beats 128x128 (8 KB per 64) whenever Cout allows it
+  // and there are still enough tiles for every SM.
   int bn_out = 128;
   while (spec.cout % bn_out) bn_out /= 2;
+  if (spec.cout % 256 == 0 && bk == 64 && getenv("WSI_NO_BN256") == nullptr) {
+    const long long m_tiles = ceil_div((long long)N * OH * OW, kBlockM);
+    if (m_tiles * (spec.cout / 256) >= 2LL * num_sms) bn_out = 256;
+  }
   block_n_ = bn_out;
   block_k_ = bk;
 
@@ -365,7 +372,7 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   }
 #define WSI_CASE(BN, BK) \
   if (block_n_ == BN && block_k_ == BK) { launch_inst<BN, BK>(amaps_, bmap_, p_, grid_, stream); if (lc) lc->n++; return; }
-  WSI_CASE(128, 64) WSI_CASE(64, 64) WSI_CASE(32, 64) WSI_CASE(16, 64)
+  WSI_CASE(256, 64) WSI_CASE(128, 64) WSI_CASE(64, 64) WSI_CASE(32, 64) WSI_CASE(16, 64)
   WSI_CASE(128, 32) WSI_CASE(64, 32) WSI_CASE(32, 32) WSI_CASE(16, 32)
   WSI_CASE(128, 16) WSI_CASE(64, 16) WSI_CASE(32, 16) WSI_CASE(16, 16)
 #undef WSI_CASE

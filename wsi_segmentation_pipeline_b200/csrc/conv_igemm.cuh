@@ -206,14 +206,14 @@ struct ConvSmem {
   static constexpr int kBBytes = (kBBytesRaw + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = RESB ? kABytes : kABytes + kBBytes;
   static constexpr int kResBytes = RESB ? kResidentBBytes : 0;
-  static constexpr int kStagesWanted = ((RESB ? 112 : 160) * 1024) / kStageBytes;
+  static constexpr int kStagesWanted = ((RESB ? 112 : (BLOCK_N > 128 ? 200 : 160)) * 1024) / kStageBytes;
   static constexpr int kStages = kStagesWanted > 8 ? 8 : (kStagesWanted < 2 ? 2 : kStagesWanted);
   static constexpr int kTableBytes = 4 * 128 * (int)sizeof(KBlock);   // up to 4 parities x 128 K blocks
   static constexpr int kBarBytes = 256;
   static constexpr int kScaleBytes = 2 * 512 * (int)sizeof(float);    // folded-BN scale + bias of up to 512 channels
   static constexpr int kRing = kStages * kStageBytes + kResBytes;     // stage ring (+ resident weights)
   static constexpr int kTotal = 1024 /*align slack*/ + kRing + kTableBytes + kBarBytes + kScaleBytes;
-  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);     // two accumulators (512 columns at BLOCK_N = 256)
 };
 
 // RESB: convs whose whole weight tensor fits in kResidentBBytes (one output-channel tile) load B ONCE per CTA
