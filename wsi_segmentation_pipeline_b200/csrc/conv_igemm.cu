@@ -147,8 +147,11 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   int bn_out = 128;
   while (spec.cout % bn_out) bn_out /= 2;
   if (spec.cout % 256 == 0 && bk == 64 && getenv("WSI_NO_BN256") == nullptr) {
+    // a 128x256 tile does twice the math of a 128x128 one in ~1.6x the time (operand bytes 48 KB vs 32 KB per
+    // K block); take it unless wave quantisation over the SMs eats that
     const long long m_tiles = ceil_div((long long)N * OH * OW, kBlockM);
-    if (m_tiles * (spec.cout / 256) >= 2LL * num_sms) bn_out = 256;
+    const long long w128 = ceil_div(m_tiles * (spec.cout / 128), num_sms), w256 = ceil_div(m_tiles * (spec.cout / 256), num_sms);
+    if (w256 * 16 <= w128 * 10) bn_out = 256;
   }
   block_n_ = bn_out;
   block_k_ = bk;
@@ -160,6 +163,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   p.res = static_cast<const bf16*>(residual);
   p.out = static_cast<bf16*>(out);
   p.error_flag = error_flag;
+  if (const char* e = getenv("WSI_IGEMM_DBG")) p.dbg = atoi(e);
 
   std::vector<KBlock> table;
   int num_parity = 1;

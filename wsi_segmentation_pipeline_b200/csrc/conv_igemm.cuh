@@ -65,6 +65,8 @@ struct ConvParams {
   const KBlock* kblocks;      // [num_parity][num_kb]
   int b_parity_stride;        // K offset (elements) between the packed weights of consecutive parity classes (0: shared)
   int* error_flag;            // set to 1 by a timed-out barrier wait
+  int dbg;                    // timing experiments only (WSI_IGEMM_DBG; results are garbage): 1 no MMAs, 2 no TMA loads,
+                              // 3 A loads only, 4 B loads only
 };
 
 struct AMaps {
@@ -289,6 +291,15 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
         const KBlock* kb_tbl = tbl + par * num_kb;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 1);
+          if (p.dbg >= 2) {
+            const bool la = (p.dbg == 3), lb = (p.dbg == 4) && !RESB;
+            ptx::mbar_expect_tx(&full[stage], (la ? S::kABytes : 0) + (lb ? S::kBBytesRaw : 0));
+            uint8_t* sA = stage_base + stage * S::kStageBytes;
+            if (la) ptx::tma_load_4d(sA, &amaps.m[0], &full[stage], 0, b0, a0, n0);
+            if (lb) ptx::tma_load_2d(sA + S::kABytes, &bmap, &full[stage], par * p.b_parity_stride + kb * BLOCK_K, co0);
+            if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           ptx::mbar_expect_tx(&full[stage], RESB ? S::kABytes : S::kABytes + S::kBBytesRaw);
           const KBlock e = kb_tbl[kb];
           uint8_t* sA = stage_base + stage * S::kStageBytes;
@@ -327,6 +338,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
           const uint32_t b_addr = RESB ? ptx::smem_u32(b_res + kb * S::kBBytes) : a_addr + S::kABytes;
           const uint64_t adesc = make_kmajor_desc<BLOCK_K>(a_addr);
           const uint64_t bdesc = make_kmajor_desc<BLOCK_K>(b_addr);
+          if (p.dbg != 1)
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advancing 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field

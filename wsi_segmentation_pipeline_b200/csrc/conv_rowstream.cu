@@ -29,27 +29,34 @@ __device__ __forceinline__ uint32_t stream_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
-struct UnitCoord {   // unit u -> (image n, column block xb, row segment seg); consecutive units walk down a strip
-  int n, xb, seg;
-  __device__ __forceinline__ void init(int u, int segs, int tiles_x) {
-    seg = u % segs;
-    const int t = u / segs;
-    xb = t % tiles_x;
-    n = t / tiles_x;
+// Work split: the (strip, output row) space — strips of 128 output columns, strip-major — is cut into gridDim.x
+// equal contiguous ranges, so every CTA streams the same number of rows (+ 2 halo rows per strip it touches).
+// A unit is the part of one strip inside the CTA's range.
+struct UnitIter {
+  int g, g_end, OH, tiles_x;
+  int n, xb, y0, Lu;
+  __device__ __forceinline__ void init(const StreamParams& p) {
+    g = (int)((long long)p.total_rows * blockIdx.x / gridDim.x);
+    g_end = (int)((long long)p.total_rows * (blockIdx.x + 1) / gridDim.x);
+    OH = p.OH;
+    tiles_x = p.tiles_x;
   }
-  __device__ __forceinline__ void next(int segs, int tiles_x) {
-    if (++seg == segs) {
-      seg = 0;
-      if (++xb == tiles_x) { xb = 0; ++n; }
-    }
+  __device__ __forceinline__ bool next() {
+    if (g >= g_end) return false;
+    const int strip = g / OH;
+    y0 = g - strip * OH;
+    Lu = min(OH - y0, g_end - g);
+    n = strip / tiles_x;
+    xb = strip - n * tiles_x;
+    g += Lu;
+    return true;
   }
 };
 
-template <int BN, bool HEAD>
+template <int BN, bool HEAD, int RS>
 __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const __grid_constant__ StreamParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  constexpr int RS = kStreamRing;
   const int w_bytes = p.nslabs * 3 * 2 * 3 * BN * 16;
   uint8_t* s_w = smem;
   float* s_scale = reinterpret_cast<float*>(smem + w_bytes);
@@ -92,9 +99,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
   __syncthreads();
   ptx::tc_fence_after();
 
-  const int u_begin = (int)((long long)p.total_units * blockIdx.x / gridDim.x);
-  const int u_end = (int)((long long)p.total_units * (blockIdx.x + 1) / gridDim.x);
-  const int L = p.seg_rows;
 
   if (warp == 0) {
     // ================================ producer ==========================================
@@ -104,20 +108,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
     const uint32_t stage0 = ptx::smem_u32(s_stage);
     const size_t run_step = (size_t)p.d.Wrow * 16;
     const int nruns = 2 * p.nslabs;
-    UnitCoord uc;
-    uc.init(u_begin, p.segs, p.tiles_x);
-    for (int u = u_begin; u < u_end; ++u, uc.next(p.segs, p.tiles_x)) {
-      const int y0 = uc.seg * L;
-      const int Lu = min(L, p.OH - y0);
+    UnitIter uc;
+    uc.init(p);
+    while (uc.next()) {
+      const int y0 = uc.y0, Lu = uc.Lu;
       const int b0 = uc.xb * 128;
       const uint32_t bytes = (uint32_t)min(kRowHaloCols, p.d.Wrow - b0) * 16u;
       const uint8_t* rowp = p.in + p.d.row_off(uc.n, y0 - 1, 0, 0) + (size_t)b0 * 16 + (size_t)(lane < nruns ? lane : 0) * run_step;
       const size_t row_step = (size_t)p.d.KC * run_step;
       for (int t = 0; t < Lu + 2; ++t) {
         ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 31);
-        if (lane == 0) ptx::mbar_expect_tx(&full[stage], (uint32_t)nruns * bytes);
+        if (lane == 0) ptx::mbar_expect_tx(&full[stage], p.dbg == 2 ? 0u : (uint32_t)nruns * bytes);
         __syncwarp();
-        if (lane < nruns) sptx::bulk_g2s(stage0 + (uint32_t)(stage * stage_bytes + lane * kRowRunBytes), rowp + (size_t)t * row_step, bytes, &full[stage]);
+        if (lane < nruns && p.dbg != 2) sptx::bulk_g2s(stage0 + (uint32_t)(stage * stage_bytes + lane * kRowRunBytes), rowp + (size_t)t * row_step, bytes, &full[stage]);
         if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
@@ -147,10 +150,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           slot = 0;
         }
       };
-      for (int u = u_begin; u < u_end; ++u) {
-        const int seg = u % p.segs;
-        const int y0 = seg * L;
-        const int Lu = min(L, p.OH - y0);
+      UnitIter uc;
+      uc.init(p);
+      while (uc.next()) {
+        const int Lu = uc.Lu;
         for (int t = 0; t < Lu + 2; ++t) {
           const bool opens = (t <= Lu - 1);            // output row i = t gets its first contribution from this input row
           if (opens) {
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           ptx::mbar_wait(&full[stage], phase, p.error_flag, 33);
           ptx::tc_fence_after();
           const int slot_lo = (job0 + t - 2 + RS) % RS;
-          if (t >= 2 && opens && slot_lo <= RS - 3) {
+          if (p.dbg == 1) {
+          } else if (t >= 2 && opens && slot_lo <= RS - 3) {
             // fast path (interior row, the three target slots are contiguous): 3 MMAs of N = 3*BN per slab,
             // except that the very first one is split so that the newly opened row is overwritten
             const uint32_t d_lo = tmem_base + (uint32_t)(slot_lo * BN);
@@ -226,11 +230,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
     const size_t chunk_step = (size_t)p.od.Wrow * 16;
     int job = 0;
     int g0 = 0;                     // input rows consumed by this CTA before the current unit (stage counter)
-    UnitCoord uc;
-    uc.init(u_begin, p.segs, p.tiles_x);
-    for (int u = u_begin; u < u_end; ++u, uc.next(p.segs, p.tiles_x)) {
-      const int y0 = uc.seg * L;
-      const int Lu = min(L, p.OH - y0);
+    UnitIter uc;
+    uc.init(p);
+    while (uc.next()) {
+      const int y0 = uc.y0, Lu = uc.Lu;
       const int x = uc.xb * 128 + row;
       const bool valid = x < p.OW;
       for (int i = 0; i < Lu; ++i, ++job) {
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
         float4 hacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dbg != 3)
 #pragma unroll
         for (int c = 0; c < BN; c += 16) {
           uint32_t v[16];
@@ -361,15 +365,9 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   p.nslabs = C / 16;
   p.N = N; p.OH = OH; p.OW = OW; p.Cout = BN;
   p.tiles_x = (int)ceil_div(OW, 128);
-  // row segments: long enough that the 2 extra halo rows are cheap, short enough for >= ~4 units per SM
-  const long long strips = (long long)N * p.tiles_x;
-  int L = OH;
-  while (L > 16 && strips * ceil_div(OH, L) < 4LL * num_sms) L = (L + 1) / 2;
-  p.seg_rows = L;
-  p.segs = (int)ceil_div(OH, L);
-  const long long total = strips * p.segs;
-  WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "row-stream conv: too many units");
-  p.total_units = (int)total;
+  const long long total = (long long)N * p.tiles_x * OH;      // (strip, output row) pairs, split evenly over the CTAs
+  WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "row-stream conv: too many rows");
+  p.total_rows = (int)total;
   p.relu = spec.relu ? 1 : 0;
   p.out = static_cast<uint8_t*>(out);
   p.out_layout = out_layout;
@@ -377,6 +375,7 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   p.res = static_cast<const uint8_t*>(residual);
   p.res_layout = res_layout;
   p.error_flag = error_flag;
+  if (const char* e = getenv("WSI_STREAM_DBG")) p.dbg = atoi(e);
   // stacked weights: [slab][s][2 chunks][3*BN][8], N order = vertical tap r = 2 | 1 | 0
   std::vector<uint16_t> wp((size_t)p.nslabs * 3 * 2 * 3 * BN * 8);
   for (int sl = 0; sl < p.nslabs; ++sl)
@@ -409,21 +408,33 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   const int fixed = 128 + ((w_bytes + (2 * BN + 68) * 4 + 127) & ~127) + 1024;
   const int stage_bytes = p.nslabs * kStreamStageBytes;
   p.stages = std::min(24, (226 * 1024 - fixed) / stage_bytes);
-  WSI_REQUIRE(p.stages + 2 >= kStreamRing, WSI_ERR_UNSUPPORTED, "row-stream conv: not enough shared memory");   // see the epilogue wait
+  // accumulator ring: 16 output rows in flight when TMEM (512 columns) and the stage ring allow it — the chain
+  // commit -> epilogue drain -> slot_free -> MMA of a later row has more slack to hide in
+  p.ring = (BN <= 32 && p.stages >= 18) ? 16 : 8;
+  if (const char* e = getenv("WSI_STREAM_RING")) { const int r = atoi(e); if ((r == 8 || r == 16) && r * BN <= 512) p.ring = r; }
+  WSI_REQUIRE(p.stages + 2 >= p.ring, WSI_ERR_UNSUPPORTED, "row-stream conv: not enough shared memory");   // see the epilogue wait
   smem_ = fixed + p.stages * stage_bytes;
   grid_ = (int)std::min<long long>(total, num_sms);
   CUDA_CHECK(cudaStreamSynchronize(0));
 }
 
-template <int BN, bool HEAD>
-static void launch_stream(const StreamParams& p, int grid, int smem, cudaStream_t s) {
+template <int BN, bool HEAD, int RS>
+static void launch_stream_rs(const StreamParams& p, int grid, int smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_rowstream_kernel<BN, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_rowstream_kernel<BN, HEAD, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
-  conv_rowstream_kernel<BN, HEAD><<<grid, kStreamThreads, smem, s>>>(p);
+  conv_rowstream_kernel<BN, HEAD, RS><<<grid, kStreamThreads, smem, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
+}
+
+template <int BN, bool HEAD>
+static void launch_stream(const StreamParams& p, int grid, int smem, cudaStream_t s) {
+  if constexpr (BN <= 32) {
+    if (p.ring == 16) { launch_stream_rs<BN, HEAD, 16>(p, grid, smem, s); return; }
+  }
+  launch_stream_rs<BN, HEAD, 8>(p, grid, smem, s);
 }
 
 void RowStreamOp::launch(cudaStream_t stream, LaunchCounter* lc) const {

@@ -25,7 +25,6 @@
 namespace wsi {
 
 constexpr int kRowRunBytes = kRowHaloCols * 16;               // 2304: one halo row of one 8-channel chunk
-constexpr int kStreamRing = 8;                             // TMEM accumulator slots (output rows in flight)
 constexpr int kStreamStageBytes = 2 * kRowRunBytes;        // one input row of one 16-channel slab: 2 chunk runs
 constexpr int kStreamThreads = (1 + 1 + 8) * 32;           // producer, MMA issuer, 2 x 4 epilogue warps
 
@@ -34,8 +33,9 @@ struct StreamParams {
   PlanarDims d;
   int nslabs;                    // C / 16
   int N, OH, OW, Cout;
-  int tiles_x, seg_rows, segs, total_units;
+  int tiles_x, total_rows;        // strips of 128 output columns per image; N * tiles_x * OH
   int stages;                    // pipeline stages, one input row (all slabs) each
+  int ring;                      // TMEM accumulator slots (output rows in flight): 8 or 16
   const bf16* w;                 // [slab][s][2 chunks][3*BN][8] bf16, N order r = 2 | 1 | 0
   const float* scale;
   const float* bias;
@@ -49,6 +49,8 @@ struct StreamParams {
   const float* head_b;
   float* head_out;
   int* error_flag;
+  int dbg;                       // timing experiments only (WSI_STREAM_DBG; results are garbage): 1 no MMAs, 2 no loads,
+                                 // 3 epilogue drains nothing
 };
 
 class RowStreamOp {
