@@ -112,6 +112,8 @@ CONV_CASES = [
     (2, 20, 28, 64, 64, 3, 1, 1, False, False),      # extents that are not powers of two
     (1, 64, 64, 64, 64, 3, 1, 1, True, True),        # many M tiles per CTA (persistent loop, 2 TMEM buffers)
     (2, 2, 2, 512, 512, 3, 1, 1, False, True),       # 2x2 feature map (64 px tiles at /32)
+    (5, 8, 8, 256, 128, 3, 1, 1, True, True),        # CTA-pair kernel, odd M-tile count (out-of-range tail tile)
+    (9, 16, 16, 128, 128, 3, 1, 1, True, True),      # CTA-pair kernel, BLOCK_N 128
     (20, 48, 48, 64, 256, 3, 1, 1, True, True),      # BLOCK_N 256 (enough M tiles for every SM), residual
     (6, 64, 64, 256, 512, 3, 1, 1, False, True),     # BLOCK_N 256, two N tiles, K = 2304
     # row-tile / row-stream kernels (cout 16/32/64, <=64 channels per operand): halo-resident taps, cp.async producers

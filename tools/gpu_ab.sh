@@ -1,9 +1,11 @@
 #!/bin/bash
-# scratch A/B
+# scratch A/B: pair kernel timing experiments (WSI_IGEMM_DBG; results are garbage for dbg != 0), auto batch 74
 mkdir -p gpurun_out
-echo "=== kernels"; timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_kernels.log 2>&1; echo "exit $?"; tail -n 5 gpurun_out/pytest_kernels.log
-for r in 8 16; do
-  echo "=== WSI_STREAM_RING=$r"
-  WSI_STREAM_RING=$r WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/conv_trace_ring$r.log 2>&1; echo "exit $?"
-  grep -E "iter 2|BK16" gpurun_out/conv_trace_ring$r.log | cut -c1-110
+for d in 0 1 2 3 4; do
+  echo "=== WSI_IGEMM_DBG=$d"
+  WSI_IGEMM_DBG=$d WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/conv_trace_pdbg$d.log 2>&1; echo "exit $?"
+  grep -E "iter 2|cap=|BK64" gpurun_out/conv_trace_pdbg$d.log | cut -c1-112
 done
+echo "=== batch 64"
+WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet 64 > gpurun_out/conv_trace_b64.log 2>&1; echo "exit $?"
+grep -E "iter 2|cap=" gpurun_out/conv_trace_b64.log | cut -c1-112

@@ -1,5 +1,6 @@
 // conv_igemm.cu — host side of the tcgen05 implicit-GEMM convolution (see conv_igemm.cuh).
 #include "conv_igemm.cuh"
+#include "conv_pair.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -335,12 +336,12 @@ void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std:
   upload(scale_, sc); upload(bias_, bi);
   upload(tbl_, table);
   p.scale = scale_.as<float>(); p.bias = bias_.as<float>(); p.kblocks = tbl_.as<KBlock>();
-  encode2(&bmap_, w_.p, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, (uint32_t)block_k_, (uint32_t)block_n_, block_k_);
   p.tiles_w = (int)ceil_div(p.A_w, p.bw);
   p.tiles_h = (int)ceil_div(p.A_h, p.bh);
   p.tiles_n = (int)ceil_div(p.N, p.bn);
   p.tiles_co = p.Cout / block_n_;
-  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co * num_parity;
+  const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  long long total = tiles_m * p.tiles_co * num_parity;
   WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "conv: too many tiles");
   grid_ = (int)std::min<long long>(total, num_sms);
   {
@@ -348,6 +349,24 @@ void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std:
     resb_ = (p.tiles_co == 1) && (block_k_ == 64) && (block_n_ == 64 || block_n_ == 128) &&
             ((long long)p.num_kb * bbytes <= kResidentBBytes) && p.b_parity_stride == 0 && getenv("WSI_NO_RESB") == nullptr;
   }
+  // CTA pairs (conv_pair.cuh): a 128 x N x 16 MMA costs ~64 + N/2 cycles on one CTA and ~64 + N/4 per CTA of a pair
+  // (operand-fetch bound, measured); take the pair kernel when that beats the single-CTA schedule after wave
+  // quantisation (pairs run on num_sms / 2 SM pairs)
+  pair_ = false;
+  if (block_k_ == 64 && p.Cout % 128 == 0 && !resb_ && p.head_out == nullptr && num_sms >= 2 && getenv("WSI_NO_PAIR") == nullptr) {
+    const int bnp = (p.Cout % 256 == 0) ? 256 : 128;
+    const long long pair_tiles = (tiles_m + 1) / 2 * (p.Cout / bnp) * num_parity;
+    const long long cost_single = ceil_div(total, num_sms) * (64 + block_n_ / 2);
+    const long long cost_pair = ceil_div(pair_tiles, num_sms / 2) * (64 + bnp / 4);
+    if (cost_pair < cost_single) {
+      pair_ = true;
+      block_n_ = bnp;
+      p.tiles_co = p.Cout / bnp;
+      grid_ = 2 * (int)std::min<long long>(pair_tiles, num_sms / 2);
+    }
+  }
+  // B tile of one CTA: block_n_ weight rows, or half of them in the pair kernel
+  encode2(&bmap_, w_.p, (uint64_t)K, (uint64_t)p.Cout, (uint64_t)K * 2, (uint32_t)block_k_, (uint32_t)(pair_ ? block_n_ / 2 : block_n_), block_k_);
   CUDA_CHECK(cudaStreamSynchronize(0));   // uploads above used the default stream
 }
 
@@ -364,10 +383,29 @@ static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams
   CUDA_CHECK(cudaGetLastError());
 }
 
+template <int BN>
+static void launch_pair(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
+  using S = PairSmem<BN>;
+  static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  conv_igemm_pair_kernel<BN><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);   // __cluster_dims__(2, 1, 1)
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (stream_) { stream_->launch(stream, lc); return; }
   if (row_) { row_->launch(stream, lc); return; }
   if (stem_) { stem_->launch(stream, lc); return; }
+  if (pair_) {
+    if (block_n_ == 256) launch_pair<256>(amaps_, bmap_, p_, grid_, stream);
+    else launch_pair<128>(amaps_, bmap_, p_, grid_, stream);
+    if (lc) lc->n++;
+    return;
+  }
   if (resb_) {
     if (block_n_ == 64) launch_inst<64, 64, true>(amaps_, bmap_, p_, grid_, stream);
     else launch_inst<128, 64, true>(amaps_, bmap_, p_, grid_, stream);

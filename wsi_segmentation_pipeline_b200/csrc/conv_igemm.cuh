@@ -543,6 +543,7 @@ class ConvOp {
   double flops() const { return flops_; }
   int block_n() const { return block_n_; }
   int block_k() const { return block_k_; }
+  bool is_pair() const { return pair_; }
 
  private:
   void finish(const std::vector<KBlock>& table, int num_parity, const std::vector<uint16_t>& wpacked, int K,
@@ -556,6 +557,7 @@ class ConvOp {
   std::unique_ptr<RowStreamOp> stream_;
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
   bool resb_ = false;         // weights resident in smem (see conv_igemm_kernel RESB)
+  bool pair_ = false;         // CTA-pair kernel (conv_pair.cuh)
   double flops_ = 0;
 };
 

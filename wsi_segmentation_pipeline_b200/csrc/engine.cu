@@ -270,9 +270,9 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
     char d[160];
     int cin_t = 0;
     for (auto& q : parts) cin_t += q.t.C;
-    snprintf(d, sizeof(d), "conv%dx%d/s%d %4d->%-4d @%dx%d%s%s BN%d BK%d", spec.ksize, spec.ksize, spec.stride, cin_t, spec.cout,
+    snprintf(d, sizeof(d), "conv%dx%d/s%d %4d->%-4d @%dx%d%s%s BN%d BK%d%s", spec.ksize, spec.ksize, spec.stride, cin_t, spec.cout,
              parts[0].up2 ? 2 * parts[0].t.H : parts[0].t.H, parts[0].up2 ? 2 * parts[0].t.W : parts[0].t.W, parts[0].up2 ? " up2" : "",
-             res ? " +res" : "", op->block_n(), op->block_k());
+             res ? " +res" : "", op->block_n(), op->block_k(), op->is_pair() ? " x2" : "");
     op_stats.push_back(OpStat{d, 0, op->flops(), 0});
   };
 
@@ -508,7 +508,12 @@ static int64_t auto_batch(const wsi_ctx* c, int ph, int pw, int64_t T) {
     // ~16 Mpx of tile area per batch (64 tiles of 512^2): the deepest layers need >= 2 full waves of
     // output tiles on 148 SMs (measured: 16 -> 204, 32 -> 228, 64 -> 239, 96 -> 232 slide-Mpx/s)
     b = std::max<int64_t>(1, (16LL << 20) / ((int64_t)ph * pw));
-    b = std::min<int64_t>(b, 1024);
+    // ... rounded to a multiple of num_sms / 4: every layer's output-tile count is batch x (H x W / 128) x N tiles
+    // with power-of-two factors, so this makes all of them whole waves over the SMs / SM pairs (74 tiles of 512^2
+    // on 148 SMs: 4.0 waves at 32x32x256 instead of 3.46)
+    const int64_t q = std::max(1, c->num_sms / 4);
+    if (2 * b >= q) b = std::max<int64_t>(1, (b + q / 2) / q) * q;
+    b = std::min<int64_t>(b, 1036);
   }
   return std::max<int64_t>(1, std::min<int64_t>(b, T));
 }
