@@ -102,45 +102,64 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
 
   if (warp == 0) {
     // ================================ producer ==========================================
-    // one pipeline stage = one input row, all slabs: lane l copies chunk run l (2 runs per 16-channel slab)
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t stage0 = ptx::smem_u32(s_stage);
-    const size_t run_step = (size_t)p.d.Wrow * 16;
-    const int nruns = 2 * p.nslabs;
-    UnitIter uc;
-    uc.init(p);
-    while (uc.next()) {
-      const int y0 = uc.y0, Lu = uc.Lu;
-      const int b0 = uc.xb * 128;
-      const uint32_t bytes = (uint32_t)min(kRowHaloCols, p.d.Wrow - b0) * 16u;
-      const uint8_t* rowp = p.in + p.d.row_off(uc.n, y0 - 1, 0, 0) + (size_t)b0 * 16 + (size_t)(lane < nruns ? lane : 0) * run_step;
+    // one pipeline stage = one input row, all slabs (2 chunk runs per 16-channel slab).  One elected lane issues
+    // everything: its operands stay on the uniform datapath and the per-row instruction stream is short — the
+    // three roles are each a single dependent instruction chain, which is what bounds the small-channel layers.
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage0 = ptx::smem_u32(s_stage);
+      uint32_t dst = stage0;
+      const size_t run_step = (size_t)p.d.Wrow * 16;
       const size_t row_step = (size_t)p.d.KC * run_step;
-      for (int t = 0; t < Lu + 2; ++t) {
-        ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 31);
-        if (lane == 0) ptx::mbar_expect_tx(&full[stage], p.dbg == 2 ? 0u : (uint32_t)nruns * bytes);
-        __syncwarp();
-        if (lane < nruns && p.dbg != 2) sptx::bulk_g2s(stage0 + (uint32_t)(stage * stage_bytes + lane * kRowRunBytes), rowp + (size_t)t * row_step, bytes, &full[stage]);
-        if (++stage == S) { stage = 0; phase ^= 1u; }
+      const int nruns = 2 * p.nslabs;
+      UnitIter uc;
+      uc.init(p);
+      while (uc.next()) {
+        const int b0 = uc.xb * 128;
+        const uint32_t bytes = (uint32_t)min(kRowHaloCols, p.d.Wrow - b0) * 16u;
+        const uint32_t row_tx = (p.dbg == 2) ? 0u : (uint32_t)nruns * bytes;
+        const uint8_t* rowp = p.in + p.d.row_off(uc.n, uc.y0 - 1, 0, 0) + (size_t)b0 * 16;
+        const int rows = uc.Lu + 2;
+        for (int t = 0; t < rows; ++t) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 31);
+          ptx::mbar_expect_tx(&full[stage], row_tx);
+          if (p.dbg != 2) {
+            const uint8_t* src = rowp;
+            uint32_t d = dst;
+#pragma unroll 2
+            for (int r = 0; r < nruns; ++r) {
+              sptx::bulk_g2s(d, src, bytes, &full[stage]);
+              d += kRowRunBytes;
+              src += run_step;
+            }
+          }
+          rowp += row_step;
+          dst += (uint32_t)stage_bytes;
+          if (++stage == S) { stage = 0; phase ^= 1u; dst = stage0; }
+        }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ========================================
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_holder);
     if (ptx::elect_one()) {
-      const uint64_t a_desc0 = stream_nosw_desc(ptx::smem_u32(s_stage), kRowRunBytes, 128);
+      constexpr uint32_t RM = RS - 1;                              // RS is a power of two
+      const uint64_t a_desc0 = stream_nosw_desc(ptx::smem_u32(s_stage), kRowRunBytes, 128) + (uint64_t)(kRowPad - 1);
       const uint64_t b_desc0 = stream_nosw_desc(ptx::smem_u32(s_w), 3 * BN * 16, 128);
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       constexpr uint32_t kSlabUnits = kStreamStageBytes >> 4;      // A: next 16-channel slab of the row
       constexpr uint32_t kWSlab = 3 * 2 * 3 * BN, kWShift = 2 * 3 * BN;   // B: next slab / next horizontal shift (16-byte units)
       const uint32_t id1 = stream_idesc(BN), id2 = stream_idesc(2 * BN), id3 = stream_idesc(3 * BN);
+      const int nslabs = p.nslabs;
+      const bool no_mma = (p.dbg == 1);
       int stage = 0;
-      uint32_t phase = 0;
-      int job0 = 0;                                    // output-row jobs issued by this CTA before the current unit
-      // blocks [a, b] of the stacked weights (block 2-r <-> vertical tap r) into the slots of rows i = t-2+a .. t-2+b
-      auto issue = [&](uint64_t a_desc, uint64_t b_desc, int jrow_a, int a, int b, uint32_t accumulate) {
+      uint32_t phase = 0, a_off = 0;                   // a_off: stage * stage_units
+      uint32_t jb = 0;                                 // output-row jobs issued by this CTA before the current unit
+      // blocks [a, b] of the stacked weights (block 2-r <-> vertical tap r) into the slots of jobs jrow_a ...
+      auto issue = [&](uint64_t a_desc, uint64_t b_desc, uint32_t jrow_a, int a, int b, uint32_t accumulate) {
         int cnt = b - a + 1;
-        int slot = jrow_a % RS;
+        int slot = (int)(jrow_a & RM);
         int blk = a;
         while (cnt > 0) {
           const int n_here = min(cnt, RS - slot);      // split where the ring wraps
@@ -155,27 +174,27 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
       while (uc.next()) {
         const int Lu = uc.Lu;
         for (int t = 0; t < Lu + 2; ++t) {
-          const bool opens = (t <= Lu - 1);            // output row i = t gets its first contribution from this input row
-          if (opens) {
-            const int j = job0 + t;
-            ptx::mbar_wait(&slot_free[j % RS], (uint32_t)(((j / RS) & 1) ^ 1), p.error_flag, 32);
-          }
-          const uint64_t a_row = a_desc0 + (uint64_t)((uint32_t)stage * stage_units) + (uint64_t)(kRowPad - 1);
+          const bool opens = (t < Lu);                 // output row i = t gets its first contribution from this input row
+          const uint32_t j = jb + (uint32_t)t;
+          if (opens) ptx::mbar_wait(&slot_free[j & RM], ((j / RS) & 1u) ^ 1u, p.error_flag, 32);
+          const uint64_t a_row = a_desc0 + (uint64_t)a_off;
           ptx::mbar_wait(&full[stage], phase, p.error_flag, 33);
           ptx::tc_fence_after();
-          const int slot_lo = (job0 + t - 2 + RS) % RS;
-          if (p.dbg == 1) {
+          const uint32_t slot_lo = (j - 2u) & RM;
+          if (no_mma) {
           } else if (t >= 2 && opens && slot_lo <= RS - 3) {
             // fast path (interior row, the three target slots are contiguous): 3 MMAs of N = 3*BN per slab,
             // except that the very first one is split so that the newly opened row is overwritten
-            const uint32_t d_lo = tmem_base + (uint32_t)(slot_lo * BN);
+            const uint32_t d_lo = tmem_base + slot_lo * BN;
             ptx::umma_bf16(d_lo + 2 * BN, a_row, b_desc0 + (uint64_t)(2 * BN), id1, 0u);
             ptx::umma_bf16(d_lo, a_row, b_desc0, id2, 1u);
             ptx::umma_bf16(d_lo, a_row + 1, b_desc0 + (uint64_t)kWShift, id3, 1u);
             ptx::umma_bf16(d_lo, a_row + 2, b_desc0 + (uint64_t)(2 * kWShift), id3, 1u);
+            uint64_t a_sl = a_row, b_sl = b_desc0;
 #pragma unroll 1
-            for (int sl = 1; sl < p.nslabs; ++sl) {
-              const uint64_t a_sl = a_row + (uint64_t)(sl * kSlabUnits), b_sl = b_desc0 + (uint64_t)(sl * kWSlab);
+            for (int sl = 1; sl < nslabs; ++sl) {
+              a_sl += kSlabUnits;
+              b_sl += kWSlab;
               ptx::umma_bf16(d_lo, a_sl, b_sl, id3, 1u);
               ptx::umma_bf16(d_lo, a_sl + 1, b_sl + (uint64_t)kWShift, id3, 1u);
               ptx::umma_bf16(d_lo, a_sl + 2, b_sl + (uint64_t)(2 * kWShift), id3, 1u);
@@ -183,15 +202,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           } else {
             const int i_lo = max(0, t - 2), i_hi = min(Lu - 1, t);
             const int blk_lo = 2 - t + i_lo, blk_hi = 2 - t + i_hi;
-            for (int sl = 0; sl < p.nslabs; ++sl) {
+            for (int sl = 0; sl < nslabs; ++sl) {
               for (int sft = 0; sft < 3; ++sft) {
                 const uint64_t a_desc = a_row + (uint64_t)(sl * kSlabUnits + sft);
                 const uint64_t b_desc = b_desc0 + (uint64_t)(sl * kWSlab + sft * kWShift);
                 if (sl == 0 && sft == 0 && opens) {
-                  issue(a_desc, b_desc, job0 + t, 2, 2, 0u);                                    // overwrite the new row
-                  if (blk_lo <= 1) issue(a_desc, b_desc, job0 + t - 2 + blk_lo, blk_lo, 1, 1u);
+                  issue(a_desc, b_desc, j, 2, 2, 0u);                                    // overwrite the new row
+                  if (blk_lo <= 1) issue(a_desc, b_desc, jb + (uint32_t)i_lo, blk_lo, 1, 1u);
                 } else {
-                  issue(a_desc, b_desc, job0 + t - 2 + blk_lo, blk_lo, blk_hi, 1u);
+                  issue(a_desc, b_desc, jb + (uint32_t)i_lo, blk_lo, blk_hi, 1u);
                 }
               }
             }
@@ -200,9 +219,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           // row i = t-2 is complete (a tcgen05.commit drains the tensor pipe — ~600 cycles measured — so the
           // number of commits, not of MMAs, bounded the previous schedules)
           ptx::umma_commit(&empty[stage]);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          a_off += stage_units;
+          if (++stage == S) { stage = 0; phase ^= 1u; a_off = 0; }
         }
-        job0 += Lu;
+        jb += (uint32_t)Lu;
       }
     }
   } else {
@@ -228,35 +248,40 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
     const bool planar_out = (p.out_layout == LAYOUT_PLANAR);
     const bool planar_res = (p.res_layout == LAYOUT_PLANAR);
     const size_t chunk_step = (size_t)p.od.Wrow * 16;
-    int job = 0;
-    int g0 = 0;                     // input rows consumed by this CTA before the current unit (stage counter)
+    const size_t plane_row_step = (size_t)p.od.KC * p.od.P * chunk_step;      // next image row of a planar tensor
+    const size_t o_step = planar_out ? chunk_step : 16, o_inc = planar_out ? plane_row_step : (size_t)p.OW * (BN * 2);
+    const size_t r_step = planar_res ? chunk_step : 16, r_inc = planar_res ? plane_row_step : (size_t)p.OW * (BN * 2);
+    uint32_t job = 0;
+    // stage / phase of the input row whose commit completes the next output row (input row i+2 for output row i);
+    // everything per row is incremental — this loop is one dependent instruction chain per warp
+    int gs = 2;
+    uint32_t gph = 0;
     UnitIter uc;
     uc.init(p);
     while (uc.next()) {
-      const int y0 = uc.y0, Lu = uc.Lu;
+      const int Lu = uc.Lu;
       const int x = uc.xb * 128 + row;
       const bool valid = x < p.OW;
-      for (int i = 0; i < Lu; ++i, ++job) {
-        if ((job & 1) != egrp) continue;
-        const int y = y0 + i;
-        const int slot = job % RS;
-        const size_t pix = ((size_t)uc.n * p.OH + y) * p.OW + x;
-        const size_t prow = p.od.row_off(uc.n, y, 0, 0);
-        // output row i is complete when the MMAs of input row t = i+2 have retired: that is the commit on that
-        // row's stage barrier (the ring cannot lap: the MMA warp needs this slot back before it gets S rows ahead)
-        const size_t o_off = planar_out ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
-        const size_t o_step = planar_out ? chunk_step : 16;
-        const size_t r_off = planar_res ? prow + (size_t)(x + kRowPad) * 16 : pix * (size_t)(BN * 2);
-        const size_t r_step = planar_res ? chunk_step : 16;
-        const bool has_res = (p.res != nullptr) && valid;
+      size_t pix = ((size_t)uc.n * p.OH + uc.y0) * p.OW + x;
+      const size_t prow = p.od.row_off(uc.n, uc.y0, 0, 0) + (size_t)(x + kRowPad) * 16;
+      size_t o_off = planar_out ? prow : pix * (size_t)(BN * 2);
+      size_t r_off = planar_res ? prow : pix * (size_t)(BN * 2);
+      const bool has_res = (p.res != nullptr) && valid;
+      for (int i = 0; i < Lu; ++i, ++job, pix += (size_t)p.OW, o_off += o_inc, r_off += r_inc) {
+        const int gs_row = gs;
+        const uint32_t gph_row = gph;
+        if (++gs == S) { gs = 0; gph ^= 1u; }
+        if ((job & 1u) != (uint32_t)egrp) continue;
+        const uint32_t slot = job & (uint32_t)(RS - 1);
         // the whole residual row of this pixel is requested before waiting for the accumulator
         uint4 rall[BN / 8];
         if (has_res) {
 #pragma unroll
           for (int k = 0; k < BN / 8; ++k) rall[k] = __ldg(reinterpret_cast<const uint4*>(p.res + r_off + (size_t)k * r_step));
         }
-        const int g = g0 + i + 2;
-        ptx::mbar_wait(&empty[g % S], (uint32_t)((g / S) & 1), p.error_flag, 34);
+        // output row i is complete when the MMAs of input row t = i+2 have retired: that is the commit on that
+        // row's stage barrier (the ring cannot lap: the MMA warp needs this slot back before it gets S rows ahead)
+        ptx::mbar_wait(&empty[gs_row], gph_row, p.error_flag, 34);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
         float4 hacc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -317,7 +342,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
         ptx::tc_fence_before();
         ptx::mbar_arrive(&slot_free[slot]);
       }
-      g0 += Lu + 2;
+      for (int k = 0; k < 2; ++k)      // the two halo rows of the unit
+        if (++gs == S) { gs = 0; gph ^= 1u; }
     }
   }
 
