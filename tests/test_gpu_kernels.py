@@ -157,6 +157,13 @@ UP_CASES = [
     (2, 12, 70, 64, 64, 32),      # decoder level 4 shape: x2(64) + skip(64) -> 32, 8 slabs
     (1, 6, 6, 16, 16, 16),        # tiny
     (1, 33, 129, 32, 32, 32),     # odd low-res extents
+    # x2 row-stream kernel: long strips (TMEM ring wraps, units cut inside strips), several strips and images
+    (1, 3000, 24, 16, 16, 16),    # ~20 source rows per CTA, 16-slot ring
+    (1, 1500, 24, 32, 32, 32),    # ~10 source rows per CTA, 8-slot ring
+    (4, 70, 130, 64, 64, 32),     # 2 strips per image (second 2 columns wide), units span strips and images
+    (3, 40, 200, 32, 0, 16),      # no skip, ragged second strip
+    (12, 16, 16, 64, 64, 32),     # many 1-2 row units per CTA: an epilogue group's first job comes several steps in
+    (12, 32, 32, 32, 0, 16),      #   (a per-step completion barrier deadlocked here; per-slot barriers do not)
 ]
 
 

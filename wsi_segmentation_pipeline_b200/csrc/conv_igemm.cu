@@ -1,6 +1,7 @@
 // conv_igemm.cu — host side of the tcgen05 implicit-GEMM convolution (see conv_igemm.cuh).
 #include "conv_igemm.cuh"
 #include "conv_pair.cuh"
+#include "conv_upstream.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -97,12 +98,28 @@ bool ConvOp::routes_to_rowtile(const std::vector<ConvInputPart>& parts, const Co
   return RowConvOp::eligible(parts, spec, residual) && getenv("WSI_NO_ROWTILE") == nullptr;
 }
 
+bool ConvOp::routes_to_upstream(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual, int out_layout) {
+  return routes_to_rowtile(parts, spec, residual) && UpStreamOp::eligible(parts, spec, residual, out_layout) &&
+         getenv("WSI_NO_UPSTREAM") == nullptr;
+}
+
 void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
                    const float* scale, const float* bias, const void* residual, void* out,
                    const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms, int out_layout,
                    int res_layout) {
   WSI_REQUIRE(!parts.empty() && parts.size() <= 2, WSI_ERR_INVALID, "conv: 1 or 2 input parts");
   stream_.reset();
+  upstream_.reset();
+  if (head_out == nullptr && routes_to_upstream(parts, spec, residual, out_layout)) {
+    upstream_.reset(new UpStreamOp());
+    upstream_->build(parts, spec, w_oihw, scale, bias, out, error_flag, num_sms);
+    flops_ = upstream_->flops();
+    block_n_ = spec.cout;
+    block_k_ = 16;
+    row_.reset();
+    stem_.reset();
+    return;
+  }
   if (routes_to_rowtile(parts, spec, residual) && RowStreamOp::eligible(parts, spec) && getenv("WSI_NO_ROWSTREAM") == nullptr) {
     stream_.reset(new RowStreamOp());
     stream_->build(parts[0], spec, w_oihw, scale, bias, residual, res_layout, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
@@ -398,6 +415,7 @@ static void launch_pair(const AMaps& am, const CUtensorMap& bm, const ConvParams
 
 void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (stream_) { stream_->launch(stream, lc); return; }
+  if (upstream_) { upstream_->launch(stream, lc); return; }
   if (row_) { row_->launch(stream, lc); return; }
   if (stem_) { stem_->launch(stream, lc); return; }
   if (pair_) {

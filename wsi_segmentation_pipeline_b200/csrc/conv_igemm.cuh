@@ -513,6 +513,7 @@ struct ConvSpec {
 class RowConvOp;   // conv_rowtile.cuh: halo-resident kernel for the small-channel 3x3 layers
 class RowStemOp;   // conv_rowtile.cuh: the stem in the same style
 class RowStreamOp; // conv_rowstream.cuh: row-streaming kernel for plain 3x3 convs on <= 64 channels
+class UpStreamOp;  // conv_upstream.cuh: row-streaming kernel for the x2-upsampling decoder convs (Cout 16 / 32)
 
 // A fully prepared conv launch: tensor maps, K-block table, packed weights, epilogue params.
 // build() routes small-channel 3x3/s1 convs to the row-tile kernel (conv_rowtile.cuh) and
@@ -533,6 +534,7 @@ class ConvOp {
   bool is_rowtile() const { return (bool)row_; }
   // would build() route this conv to the row-tile kernel?  (lets the caller chain planar layouts)
   static bool routes_to_rowtile(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual);
+  static bool routes_to_upstream(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual, int out_layout);
   // stem: x = gather output, zero-padded tiles [n][ph+6][pw+8][4] bf16; 7x7/s2/p3, cout 64.
   // out_layout: LAYOUT_NHWC or LAYOUT_PLANAR_PARITY (row-tile stem only; see stem_routes_to_rowtile)
   void build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw /*[64,3,7,7]*/,
@@ -555,6 +557,7 @@ class ConvOp {
   std::unique_ptr<RowConvOp> row_;
   std::unique_ptr<RowStemOp> stem_;
   std::unique_ptr<RowStreamOp> stream_;
+  std::unique_ptr<UpStreamOp> upstream_;
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
   bool resb_ = false;         // weights resident in smem (see conv_igemm_kernel RESB)
   bool pair_ = false;         // CTA-pair kernel (conv_pair.cuh)

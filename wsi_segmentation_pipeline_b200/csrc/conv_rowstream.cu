@@ -182,6 +182,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           ptx::tc_fence_after();
           const uint32_t slot_lo = (j - 2u) & RM;
           if (no_mma) {
+          } else if (p.dbg == 4 && BN == 16) {
+            // timing experiment: the same 4 MMAs, each into its own TMEM region -> no dependent chain inside a row
+            ptx::umma_bf16(tmem_base, a_row, b_desc0 + (uint64_t)(2 * BN), id1, 1u);
+            ptx::umma_bf16(tmem_base + 48, a_row, b_desc0, id2, 1u);
+            ptx::umma_bf16(tmem_base + 96, a_row + 1, b_desc0 + (uint64_t)kWShift, id3, 1u);
+            ptx::umma_bf16(tmem_base + 144, a_row + 2, b_desc0 + (uint64_t)(2 * kWShift), id3, 1u);
           } else if (t >= 2 && opens && slot_lo <= RS - 3) {
             // fast path (interior row, the three target slots are contiguous): 3 MMAs of N = 3*BN per slab,
             // except that the very first one is split so that the newly opened row is overwritten

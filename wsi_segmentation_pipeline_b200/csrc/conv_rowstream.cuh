@@ -49,7 +49,7 @@ struct StreamParams {
   const float* head_b;
   float* head_out;
   int* error_flag;
-  int dbg;                       // timing experiments only (WSI_STREAM_DBG; results are garbage): 1 no MMAs, 2 no loads,
+  int dbg;                       // timing experiments only (WSI_STREAM_DBG; results are garbage): 1 no MMAs, 2 no loads, 4 independent MMAs,
                                  // 3 epilogue drains nothing
 };
 

@@ -642,6 +642,30 @@ void launch_relayout_planar(const void* src_nhwc, void* dst, int N, int H, int W
   if (lc) lc->n++;
 }
 
+// inverse (plain planar -> NHWC): only used where a planar-only kernel must hand an NHWC tensor back (debug entry point)
+__global__ void __launch_bounds__(256) relayout_nhwc_kernel(const uint8_t* __restrict__ src, uint4* __restrict__ dst, int N, int H, int W,
+                                                             int KC) {
+  const PlanarDims d = PlanarDims::make(H, W, KC * 8, LAYOUT_PLANAR);
+  const int64_t total = (int64_t)N * H * KC * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kc = (int)(i % KC);
+    int64_t r = i / KC;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    dst[i] = *reinterpret_cast<const uint4*>(src + d.row_off(n, y, kc, 0) + (size_t)(x + kRowPad) * 16);
+  }
+}
+
+void launch_relayout_nhwc(const void* src_planar, void* dst_nhwc, int N, int H, int W, int C, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t total = (int64_t)N * H * (C / 8) * W;
+  if (total <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
+  relayout_nhwc_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(src_planar), static_cast<uint4*>(dst_nhwc), N, H, W, C / 8);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------

@@ -160,5 +160,6 @@ void launch_maxpool_planar(const void* x_parity_planar, int n, int h, int w, int
 // NHWC bf16 -> padded planar (interior only; the zero border is written once at allocation)
 void launch_relayout_planar(const void* src_nhwc, void* dst, int N, int H, int W, int C, int layout, cudaStream_t s,
                             LaunchCounter* lc);
+void launch_relayout_nhwc(const void* src_planar, void* dst_nhwc, int N, int H, int W, int C, cudaStream_t s, LaunchCounter* lc);
 
 }  // namespace wsi

@@ -956,9 +956,22 @@ int wsi_debug_conv(wsi_ctx* ctx, const void* x, int n, int h, int w, int cin, co
   ConvSpec sp;
   sp.ksize = ksize; sp.stride = stride; sp.pad = pad; sp.cout = cout; sp.relu = relu != 0;
   ConvOp op;
-  op.build(parts, sp, wt, scale, bias, res, y, nullptr, nullptr, nullptr, ctx->err_flag.as<int>(), ctx->num_sms);
-  op.launch(s, &ctx->lc);
-  check_device_flag(ctx, s);
+  if (ConvOp::routes_to_upstream(parts, sp, res, LAYOUT_PLANAR)) {
+    // the x2 row-stream kernel only writes the planar layout (what the engine chains): run it that way and hand NHWC back
+    const int OH = 2 * h, OW = 2 * w;
+    const PlanarDims od = PlanarDims::make(OH, OW, cout, LAYOUT_PLANAR);
+    DevBuf tmp;
+    tmp.alloc(od.bytes(n));
+    CUDA_CHECK(cudaMemsetAsync(tmp.p, 0, tmp.bytes, s));
+    op.build(parts, sp, wt, scale, bias, res, tmp.p, nullptr, nullptr, nullptr, ctx->err_flag.as<int>(), ctx->num_sms, LAYOUT_PLANAR);
+    op.launch(s, &ctx->lc);
+    launch_relayout_nhwc(tmp.p, y, n, OH, OW, cout, s, &ctx->lc);
+    check_device_flag(ctx, s);
+  } else {
+    op.build(parts, sp, wt, scale, bias, res, y, nullptr, nullptr, nullptr, ctx->err_flag.as<int>(), ctx->num_sms);
+    op.launch(s, &ctx->lc);
+    check_device_flag(ctx, s);
+  }
   WSI_API_END(ctx)
 }
 
