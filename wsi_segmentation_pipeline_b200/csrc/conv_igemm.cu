@@ -141,8 +141,10 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   }
   row_.reset();
   stem_.reset();
-  WSI_REQUIRE(out_layout == LAYOUT_NHWC && (residual == nullptr || res_layout == LAYOUT_NHWC), WSI_ERR_UNSUPPORTED,
-              "conv: only the row-tile kernel reads/writes planar tensors");
+  WSI_REQUIRE((out_layout == LAYOUT_NHWC || (out_layout == LAYOUT_PLANAR && head_out == nullptr)) &&
+                  (residual == nullptr || res_layout == LAYOUT_NHWC),
+              WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC tensors and writes NHWC or plain planar ones");
+  out_planar_ = (out_layout == LAYOUT_PLANAR);
   for (auto& q : parts) WSI_REQUIRE(q.t.layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC operands");
   bool any_up = false;
   for (auto& q : parts) any_up |= q.up2;
@@ -182,6 +184,14 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   p.out = static_cast<bf16*>(out);
   p.error_flag = error_flag;
   if (const char* e = getenv("WSI_IGEMM_DBG")) p.dbg = atoi(e);
+  if (out_planar_) {
+    WSI_REQUIRE(spec.cout % 8 == 0, WSI_ERR_UNSUPPORTED, "conv: planar output needs Cout %% 8 == 0");
+    const PlanarDims od = PlanarDims::make(OH, OW, spec.cout, LAYOUT_PLANAR);
+    p.out_planar = 1;
+    p.pl_chunk = (long long)od.Wrow * 16;
+    p.pl_row = (long long)od.KC * p.pl_chunk;
+    p.pl_img = (long long)(OH + 2) * p.pl_row;
+  }
 
   std::vector<KBlock> table;
   int num_parity = 1;
@@ -370,7 +380,7 @@ void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std:
   // (operand-fetch bound, measured); take the pair kernel when that beats the single-CTA schedule after wave
   // quantisation (pairs run on num_sms / 2 SM pairs)
   pair_ = false;
-  if (block_k_ == 64 && p.Cout % 128 == 0 && !resb_ && p.head_out == nullptr && num_sms >= 2 && getenv("WSI_NO_PAIR") == nullptr) {
+  if (block_k_ == 64 && p.Cout % 128 == 0 && !resb_ && p.head_out == nullptr && !p.out_planar && num_sms >= 2 && getenv("WSI_NO_PAIR") == nullptr) {
     const int bnp = (p.Cout % 256 == 0) ? 256 : 128;
     const long long pair_tiles = (tiles_m + 1) / 2 * (p.Cout / bnp) * num_parity;
     const long long cost_single = ceil_div(total, num_sms) * (64 + block_n_ / 2);

@@ -65,6 +65,8 @@ struct ConvParams {
   const KBlock* kblocks;      // [num_parity][num_kb]
   int b_parity_stride;        // K offset (elements) between the packed weights of consecutive parity classes (0: shared)
   int* error_flag;            // set to 1 by a timed-out barrier wait
+  int out_planar;             // 1: `out` is the zero-padded channel-chunk-planar layout of conv_rowtile.cuh (consumer = a row kernel)
+  long long pl_img, pl_row, pl_chunk;   // its byte strides: image, image row, 8-channel chunk row (entry = x + 8, 16 B each)
   int dbg;                    // timing experiments only (WSI_IGEMM_DBG; results are garbage): 1 no MMAs, 2 no TMA loads,
                               // 3 A loads only, 4 B loads only
 };
@@ -383,6 +385,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
       const int oh = p.sigma * a + (par >> 1), ow = p.sigma * b + (par & 1);
       const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
       const size_t off0 = pix * p.Cout + co0 + c_lo;
+      const size_t pl_off = (size_t)n * (size_t)p.pl_img + (size_t)(oh + 1) * (size_t)p.pl_row + (size_t)(ow + 8) * 16;
       const bool has_res = (p.res != nullptr) && valid;
 
       // residual of the first chunk: issued before waiting for the accumulator
@@ -447,7 +450,10 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             }
           }
           if (valid && p.out != nullptr) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c);
+            // NHWC: 2 * STEP contiguous bytes; planar: one 16-byte entry per 8-channel chunk row
+            uint8_t* ob = p.out_planar ? reinterpret_cast<uint8_t*>(p.out) + pl_off + (size_t)((co0 + c_lo + c) >> 3) * (size_t)p.pl_chunk
+                                       : reinterpret_cast<uint8_t*>(p.out + off0 + c);
+            const size_t ostep = p.out_planar ? (size_t)p.pl_chunk : 16;
 #pragma unroll
             for (int j = 0; j < STEP / 8; ++j) {
               uint32_t w[4];
@@ -456,7 +462,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
                 w[t] = *reinterpret_cast<uint32_t*>(&h2);
               }
-              op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(ob + (size_t)j * ostep) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
         }
@@ -561,6 +567,7 @@ class ConvOp {
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
   bool resb_ = false;         // weights resident in smem (see conv_igemm_kernel RESB)
   bool pair_ = false;         // CTA-pair kernel (conv_pair.cuh)
+  bool out_planar_ = false;   // TMA kernel writing the planar layout for a row-kernel consumer
   double flops_ = 0;
 };
 

@@ -357,7 +357,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
       const int ci = x->C + (skip ? skip->C : 0);
       const std::string q = "decoder.layer" + std::to_string(i) + ".block.";
       const size_t ia = 2 * (size_t)(i - 1), ib = ia + 1;
-      const bool a_planar = plan[ia].row && plan[ib].row;
+      const bool a_planar = plan[ib].row;      // consumer is a row kernel; every producer (row kernels, TMA kernel) can write planar
       const bool b_planar = (ib + 1 < plan.size()) && plan[ib].row && plan[ib + 1].row;
       Act* a = new_act(cap, 2 * x->H, 2 * x->W, co, a_planar ? LAYOUT_PLANAR : LAYOUT_NHWC);
       {
