@@ -36,6 +36,7 @@ struct StreamParams {
   int tiles_x, total_rows;        // strips of 128 output columns per image; N * tiles_x * OH
   int stages;                    // pipeline stages, one input row (all slabs) each
   int ring;                      // TMEM accumulator slots (output rows in flight): 8 or 16
+  int lanes;                     // 1: 128-column strips (conv_rowstream_kernel); 2: 256-column strips, two lanes (Cout <= 32)
   const bf16* w;                 // [slab][s][2 chunks][3*BN][8] bf16, N order r = 2 | 1 | 0
   const float* scale;
   const float* bias;
