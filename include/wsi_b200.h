@@ -123,6 +123,28 @@ WSI_API int wsi_band_tiles(const int32_t* xy, int64_t n, int32_t ph, double m, i
 WSI_API int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,
                   int head, const wsi_out_desc* out, void* stream);
 
+/* ---- foreground mask and masked tile plan on the GPU ------------------------------------
+ * wsi_find_nuclei: find_nuclei(wsi, mu_percent, mode='hsv', fill_mask=False) (utils/preprocessing.py:74-110):
+ * mask = u8 {0,1}, HSV saturation of the level-2 thumbnail > mu_percent, evaluated as skimage.color.rgb2hsv does
+ * (float64, S = (max-min)/max on u8/255, 0 where max == min) — bit-exact through a (max,min) table.
+ * rgb: u8 [H][row_stride] interleaved RGB in rgb_mem memory; mask: u8 [H][W] in mask_mem memory.                  */
+WSI_API int wsi_find_nuclei(wsi_ctx* ctx, const uint8_t* rgb, int64_t row_stride, int rgb_mem, int64_t H, int64_t W,
+                    double mu_percent, uint8_t* mask, int mask_mem, void* stream);
+/* wsi_plan_tiles_gpu: same result as wsi_plan_tiles (Dataset_wsi.__init__, utils/dataset.py:143-166) with the
+ * isforeground window counts (utils/preprocessing.py:60-71) evaluated on the device; `mask` (required) may be
+ * device-resident, e.g. the output of wsi_find_nuclei.  xy_out is malloc'd (wsi_free).                            */
+WSI_API int wsi_plan_tiles_gpu(wsi_ctx* ctx, int64_t ih, int64_t iw, int32_t ph, int32_t pw, int32_t sh, int32_t sw,
+                       const uint8_t* mask, int mask_mem, int64_t mh, int64_t mw, double m, int32_t** xy_out,
+                       int64_t* n_out, void* stream);
+
+/* ---- predict_wsis tail (utils/eval.py:66-71 cv2.resize per class to the level-2 size, :81 np.argmax) ----------
+ * canvas: f32 [4][H][W] summed logits at scan-level resolution (the `canvas` output of wsi_run_slide run with m = 1,
+ * H2 = ih, W2 = iw); classes: u8 [H2][W2]; pred_or_null: f32 [4][H2][W2] (the reference's resized `pred`).
+ * INTER_LINEAR exactly as OpenCV evaluates it (half-pixel centres, border clamp, float weights), fp32 accumulation.
+ * All three buffers in `mem` memory.                                                                              */
+WSI_API int wsi_resize_argmax(wsi_ctx* ctx, const float* canvas, int64_t H, int64_t W, int64_t H2, int64_t W2,
+                      uint8_t* classes, float* pred_or_null, int mem, void* stream);
+
 /* ---- one batch through the network (nn.Module shim forward; utils/eval.py:196-200) ----------- */
 /* x: f32 [n, 3, h, w] already normalised (standard_augmentor output); out: SEG f32 [n,C,h,w],
  * CLS [n,C], REG [n,1], FEATURES [n,512].  Both in `mem` memory.                                 */

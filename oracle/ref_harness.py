@@ -175,6 +175,10 @@ class UnetAdapter(nn.Module):
         self.regressor = R.Regressor(512, 1)
         self.regressor.load_state_dict({k[len("regressor."):]: v for k, v in sd.items() if k.startswith("regressor.")})
 
+    def forward(self, x):
+        """predict_wsis calls the model itself (utils/eval.py:51): smp.Unet.forward = decoder(encoder(x))."""
+        return self.decoder(self.encoder(x))
+
 
 # ------------------------------------------------------------------------------------------
 # run the reference loop on one synthetic slide
@@ -225,5 +229,59 @@ def run_reference_predict_tumorbed(model, levels: dict, mask: np.ndarray, workdi
         R.preprocessing.threshold_probs = orig
     heat = np.array(Image.open(os.path.join(a.val_save_pth, "0", f"{key}_{sw}_heatmap.png")))
     captured["heatmap"] = heat
+    captured["tiles"] = tiles
+    return captured
+
+
+class _StopAfterScores(Exception):
+    pass
+
+
+def run_reference_predict_wsis(model, levels: dict, mask: np.ndarray, workdir: str, *, ph, pw, sh, sw, scan_level=2,
+                               batch=16, shuffle_seed=0, key="slide0.svs"):
+    """Runs the reference's predict_wsis (utils/eval.py:22-60 loop, :66-71 cv2.resize to level 2) on one synthetic
+    slide and returns its tile list, the f64 scan-level canvas is not observable, so: `pred` = the RESIZED [C,H2,W2]
+    array handed to `preprocessing.pred_to_mask` (:139), where the run is stopped — pred_to_mask itself has the tuple
+    bug of SURVEY §8c and the rest of the function (scores, tumour-bed morphology, colour mask) is out of scope."""
+    from PIL import Image
+    R = ref_modules()
+    a = R.args
+    root = os.path.join(workdir, "wsi")
+    case = os.path.join(root, "Case_1")
+    os.makedirs(case, exist_ok=True)
+    maskdir = os.path.join(workdir, "masks")
+    os.makedirs(maskdir, exist_ok=True)
+    svs = os.path.join(case, key)
+    open(svs, "wb").close()
+    _SLIDES[os.path.abspath(svs)] = levels
+    Image.fromarray(mask.astype(np.uint8)).save(os.path.join(maskdir, key + ".png"))           # Dataset_wsi foreground mask
+    Image.fromarray(mask.astype(np.uint8)).save(svs + "_find_nuclei.png")                      # utils/eval.py:64
+
+    a.wsi_mask_pth = maskdir
+    a.val_save_pth = os.path.join(workdir, "out")
+    a.scan_level = scan_level
+    a.scan_resize = 1
+    a.workers = 0
+    a.num_classes = 4
+    a.tile_h, a.tile_w, a.tile_stride_h, a.tile_stride_w = ph, pw, sh, sw
+
+    ds = R.dataset.Dataset_wsis(root, {"ph": ph, "pw": pw, "sh": sh, "sw": sw}, bs=batch)
+    tiles = list(ds.wsis[key]["iterator"].dataset.datalist)
+    captured = {}
+    orig = R.preprocessing.pred_to_mask
+
+    def capture(pred, *k, **kw):
+        captured["pred"] = np.array(pred, copy=True)
+        raise _StopAfterScores()
+
+    R.preprocessing.pred_to_mask = capture
+    try:
+        torch.manual_seed(shuffle_seed)
+        try:
+            R.eval.predict_wsis(model, ds, 0)
+        except _StopAfterScores:
+            pass
+    finally:
+        R.preprocessing.pred_to_mask = orig
     captured["tiles"] = tiles
     return captured

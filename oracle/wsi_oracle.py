@@ -247,6 +247,46 @@ def coverage_counts(shape_hw, tiles, ph, pw, m=1.0) -> np.ndarray:
     return cnt
 
 
+def cv2_resize_linear(src: np.ndarray, W2: int, H2: int) -> np.ndarray:
+    """cv2.resize(src, (W2, H2)) with the default INTER_LINEAR for a CV_64F plane, restated from OpenCV's
+    resize.cpp as opencv-python 4.13 (the version in this image; the reference pins none) evaluates it — checked
+    against cv2 itself in tests/test_oracle_golden.py to a few ulp (OpenCV's build contracts a*b+c into FMAs):
+    source coordinate ``(d + 0.5) * scale - 0.5`` in double, floor + fraction, the horizontal border clamp resets
+    the fraction, weights (1 - f, f), horizontal pass then vertical pass, all in double.  An exact 2x2 decimation
+    is computed by OpenCV as INTER_AREA (the mean of the 2x2 block)."""
+    src = np.asarray(src, np.float64)
+    H, W = src.shape
+    if (H2, W2) == (H, W):
+        return src.copy()
+    if H == 2 * H2 and W == 2 * W2:
+        return (src[0::2, 0::2] + src[0::2, 1::2] + src[1::2, 0::2] + src[1::2, 1::2]) * 0.25
+    sx_scale, sy_scale = 1.0 / (W2 / W), 1.0 / (H2 / H)
+
+    def taps(n_dst, n_src, scale, clamp_resets):
+        f = (np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5
+        s = np.floor(f).astype(np.int64)
+        f = f - s
+        if clamp_resets:
+            lo, hi = s < 0, s >= n_src - 1
+            f[lo | hi] = 0
+            s[lo] = 0
+            s[hi] = n_src - 1
+        i0 = np.clip(s, 0, n_src - 1)
+        i1 = np.clip(s + 1, 0, n_src - 1)
+        return i0, i1, 1.0 - f, f
+
+    x0, x1, a0, a1 = taps(W2, W, sx_scale, True)
+    y0, y1, b0, b1 = taps(H2, H, sy_scale, False)
+    rows = src[:, x0] * a0[None, :] + src[:, x1] * a1[None, :]                # hresize
+    return rows[y0, :] * b0[:, None] + rows[y1, :] * b1[:, None]              # vresize
+
+
+def predict_wsis_scores(canvas: np.ndarray, W2: int, H2: int):
+    """utils/eval.py:66-71,81: per-class cv2.resize of the scan-level canvas to the level-2 size, then argmax."""
+    pred = np.stack([cv2_resize_linear(canvas[c], W2, H2) for c in range(canvas.shape[0])])
+    return np.argmax(pred, 0).astype(np.uint8), pred
+
+
 # --------------------------------------------------------------------------------------------
 # A10/A11: softmax over summed logits, floor, argmax, heatmap  (utils/preprocessing.py:156-172,
 #          utils/eval.py:217-228)
@@ -285,6 +325,23 @@ def predict_tumorbed(sd, arch, raster, mask, ph, pw, sh, sw, mode, batch=16, m=1
     return {"tiles": tiles, "canvas": canvas, "classes": classes, "probs": probs, "heatmap": heat,
             "counts": coverage_counts(mask.shape, tiles, ph, pw, m),
             "logits": np.concatenate(all_logits) if all_logits else np.zeros((0, C), np.float32)}
+
+
+def predict_wsis(sd, raster, mask, ph, pw, sh, sw, m=1.0, batch=16, tiles=None):
+    """utils/eval.py:22-81 for one slide, up to the argmax: the canvas lives at SCAN-LEVEL resolution (:44-47,
+    tiles land unscaled, :56-60), is resized per class to the level-2 size == mask.shape (:66-71), then argmax (:81).
+    ``m`` only enters the tile plan (foreground test of Dataset_wsi against the level-2 mask)."""
+    ih, iw = raster.shape[:2]
+    if tiles is None:
+        tiles = plan_tiles(ih, iw, ph, pw, sh, sw, mask, m)
+    canvas = np.zeros((4, ih, iw), np.float64)
+    for i in range(0, len(tiles), batch):
+        chunk = tiles[i:i + batch]
+        y = model_forward(sd, "unet_seg", gather_tiles(raster, chunk, ph, pw)).numpy()
+        stitch(canvas, chunk, y, ph, pw, 1.0)
+    H2, W2 = mask.shape
+    classes, pred = predict_wsis_scores(canvas, W2, H2)
+    return {"tiles": tiles, "canvas": canvas, "pred": pred, "classes": classes}
 
 
 # --------------------------------------------------------------------------------------------

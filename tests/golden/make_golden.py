@@ -8,6 +8,7 @@ Scenarios
   cls_small   predict_tumorbed(mode='cls'), reference resnets_shift.ResNet via the config-1 adapter
   cls_m4      same with scan_level=1 (m = 0.25: int(m*x) truncation, level-2 canvas)
   seg_small   predict_tumorbed(mode='seg'), reference ResNet encoder + restated smp decoder
+  wsis_l2/l1  predict_wsis up to the argmax (scan_level 2: resize is the identity; scan_level 1: cv2.resize 4x down)
   resnet_fwd  resnets_shift.ResNet.forward (multi-patch) on a [2,16,3,64,64] batch
   normalise   standard_augmentor(True) on a PIL tile
 """
@@ -104,6 +105,28 @@ def predict(name, arch, ih, iw, ph, pw, sh, sw, mode, scan_level=2, seed=0):
           "classes hist", np.bincount(r["classes"].ravel(), minlength=4))
 
 
+def predict_wsis(name, ih, iw, ph, pw, sh, sw, scan_level, seed):
+    """utils/eval.py:22-81 predict_wsis up to the argmax: canvas at scan-level resolution, cv2.resize to level 2."""
+    sd = O.random_state_dict("unet", seed)
+    model = H.UnetAdapter(sd)
+    raster = synth.synth_slide(ih, iw, 4321)
+    if scan_level == 2:
+        levels = {2: raster}
+        mask = small_mask(ih, iw, 78)
+    else:
+        levels = {scan_level: raster, 2: box_down(raster, 4)}
+        mask = small_mask(ih // 4, iw // 4, 78)
+    with tempfile.TemporaryDirectory() as td:
+        r = H.run_reference_predict_wsis(model, levels, mask, td, ph=ph, pw=pw, sh=sh, sw=sw, scan_level=scan_level, batch=5)
+    pred = r["pred"]
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        geom=np.array([ih, iw, ph, pw, sh, sw, scan_level], np.int32), seed=np.array(seed), mask=mask,
+        tiles=np.array(r["tiles"], np.int32).reshape(-1, 2), pred=pred.astype(np.float32),
+        classes=np.argmax(pred, 0).astype(np.uint8))
+    print(name, "tiles", len(r["tiles"]), "pred", pred.shape, "classes hist", np.bincount(np.argmax(pred, 0).ravel(), minlength=4))
+
+
 def resnet_fwd():
     sd = O.random_state_dict("resnet18", 3, with_fc=True)
     net = H.make_reference_resnet(sd)
@@ -133,3 +156,5 @@ if __name__ == "__main__":
     predict("cls_small", "resnet18_cls", 352, 416, 64, 64, 32, 32, "cls")
     predict("cls_m4", "resnet18_cls", 640, 768, 128, 128, 64, 64, "cls", scan_level=1, seed=1)
     predict("seg_small", "unet_seg", 160, 192, 64, 64, 32, 32, "seg", seed=2)
+    predict_wsis("wsis_l2", 160, 192, 64, 64, 32, 32, 2, 4)
+    predict_wsis("wsis_l1", 256, 320, 64, 64, 32, 32, 1, 5)

@@ -84,3 +84,34 @@ def test_predict_tumorbed_mirror(golden_dir, tmp_path, name, arch, mode):
     png = np.array(Image.open(tmp_path / "0" / f"slide0.svs_{sw}_heatmap.png"))
     np.testing.assert_array_equal(png, r["heatmap"])
     assert (tmp_path / "0" / f"slide0.svs_{sw}_overlay.png").exists()
+
+
+@pytest.mark.parametrize("name", ["wsis_l2", "wsis_l1"])
+def test_predict_wsis_mirror(golden_dir, name):
+    """A9: predict_wsis (utils/eval.py:22-81) up to the argmax — scan-level canvas, cv2.resize to level 2 — against the
+    reference's own output (golden) and the oracle in bf16 emulation."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g["geom"])
+    sd = O.random_state_dict("unet", int(g["seed"]))
+    net = models.unet_resnet18()
+    net.load_state_dict(sd, strict=False)
+    net = net.cuda()
+    raster = synth.synth_slide(ih, iw, 4321)
+    levels = {lvl: raster}
+    if lvl != 2:
+        levels[2] = np.zeros((ih // 4, iw // 4, 3), np.uint8)
+    data = ds.Dataset_wsis({"slide0.svs": ds.ArraySlide(levels)}, {"ph": ph, "pw": pw, "sh": sh, "sw": sw}, scan_level=lvl,
+                           masks={"slide0.svs": g["mask"]})
+    np.testing.assert_array_equal(data.wsis["slide0.svs"]["iterator"].tiles, g["tiles"])
+    r = ev.predict_wsis(net, data, 0)["slide0.svs"]
+    assert r["pred"].shape == g["pred"].shape and r["classes"].shape == g["classes"].shape and r["classes"].dtype == np.uint8
+    with O.bf16_emulation():
+        emu = O.predict_wsis(sd, raster, g["mask"], ph, pw, sh, sw, m=1.0 if lvl == 2 else 0.25, tiles=[tuple(t) for t in g["tiles"]])
+    scale = np.abs(g["pred"]).max()
+    noise = np.abs(emu["pred"] - g["pred"]).max()                 # what bf16 operands alone cost (no kernel involved)
+    err = np.abs(r["pred"] - g["pred"]).max()
+    agree = (r["classes"] == g["classes"]).mean()
+    print(f"{name}: summed logits max err {err:.3e} (bf16 emulation {noise:.3e}, scale {scale:.2f}), argmax agree {agree:.5f} "
+          f"(emulation {(emu['classes'] == g['classes']).mean():.5f})")
+    assert err <= 1.5 * noise + 5e-3 * scale
+    assert agree >= (emu["classes"] == g["classes"]).mean() - 5e-3

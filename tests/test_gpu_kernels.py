@@ -3,6 +3,8 @@
 Integer/byte work is compared bit-exactly with the oracle; the bf16 tensor-core convolutions are
 compared with a plain PyTorch fp32 reference of the same op evaluated on the same bf16-rounded
 operands (so the only differences are fp32 accumulation order and the final bf16 rounding)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -211,3 +213,62 @@ def test_stem(ctx, ph, pw, n):
     x = _bf16_round(O.gather_tiles(raster, [tuple(t) for t in tiles], ph, pw)).cuda()
     ref = F.relu(F.conv2d(x, _bf16_round(wt).cuda(), None, 2, 3) * scale.cuda().view(1, -1, 1, 1) + bias.cuda().view(1, -1, 1, 1))
     _assert_close_bf16(_nchw_f32(y), ref, f"stem {ph}x{pw}")
+
+
+@pytest.mark.parametrize("shape", [(256, 320, 64, 80), (100, 130, 33, 47), (64, 64, 32, 32), (40, 60, 80, 120), (97, 61, 13, 9), (37, 53, 37, 53)])
+def test_resize_argmax(ctx, shape):
+    """A9 tail (utils/eval.py:66-81): cv2.resize(INTER_LINEAR) per class + argmax, against the oracle's restatement of
+    OpenCV (pinned against cv2 in the CPU suite).  fp32 vs double blending: values to 1e-5, argmax except near-ties."""
+    H, W, H2, W2 = shape
+    g = torch.Generator().manual_seed(H * W2)
+    canvas = (torch.randn(4, H, W, generator=g) * 5).contiguous()
+    ref_cls, ref = O.predict_wsis_scores(canvas.double().numpy(), W2, H2)
+    for dev in ("cpu", "cuda"):
+        cls, pred = ctx.resize_argmax(canvas.to(dev), H2, W2)
+        cls, pred = cls.cpu().numpy(), pred.cpu().numpy()
+        np.testing.assert_allclose(pred, ref, rtol=1e-5, atol=2e-5)
+        top2 = np.sort(ref, axis=0)[-2:]
+        clear = (top2[1] - top2[0]) > 1e-4
+        assert (cls[clear] == ref_cls[clear]).all() and (cls == ref_cls).mean() > 0.999
+
+
+def test_find_nuclei_bit_exact(ctx):
+    """A12: find_nuclei(mode='hsv') — the device mask equals the float64 skimage formula (dataset.find_nuclei_hsv restates
+    it) on a synthetic H&E raster, on every (max, min) pair, and for other thresholds."""
+    from wsi_segmentation_pipeline_b200 import dataset as ds
+    raster = synth.synth_slide(300, 417, 11)
+    np.testing.assert_array_equal(ctx.find_nuclei(raster), ds.find_nuclei_hsv(raster))
+    dev = ctx.find_nuclei(torch.from_numpy(raster).cuda(), device_out=True)
+    np.testing.assert_array_equal(dev.cpu().numpy(), ds.find_nuclei_hsv(raster))
+    mx, mn = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    pairs = np.stack([mx, np.minimum(mx, mn), np.minimum(mx, mn)], -1)          # [256,256,3], max = R, min = G = B
+    for mu in (0.1, 0.05, 0.5):
+        np.testing.assert_array_equal(ctx.find_nuclei(pairs, mu), ds.find_nuclei_hsv(pairs, mu))
+    perm = np.ascontiguousarray(pairs[..., [2, 0, 1]])                            # max in another channel
+    np.testing.assert_array_equal(ctx.find_nuclei(perm), ds.find_nuclei_hsv(perm))
+
+
+def test_plan_tiles_gpu_matches_host_planner(ctx, golden_dir):
+    """A1/A12: wsi_plan_tiles_gpu == wsi_plan_tiles (itself pinned against the reference's enumeration) on the golden
+    geometries and on random masks / strides / scan levels, host and device-resident masks, non-{0,1} mask values."""
+    g = np.load(os.path.join(golden_dir, "plan.npz"))
+    for ci in range(int(g["n_cases"])):
+        ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g[f"case{ci}_geom"])
+        m = 1.0 if lvl == 2 else 0.25
+        got = ctx.plan_tiles(ih, iw, ph, pw, sh, sw, g[f"case{ci}_mask"], m)
+        np.testing.assert_array_equal(got, g[f"case{ci}_tiles"])
+    rng = np.random.default_rng(3)
+    for it in range(12):
+        ih, iw = int(rng.integers(200, 900)), int(rng.integers(200, 900))
+        ph, pw = int(rng.choice([32, 64, 100])), int(rng.choice([32, 64, 100]))
+        sh, sw = int(rng.integers(8, ph + 1)), int(rng.integers(8, pw + 1))
+        m = float(rng.choice([1.0, 0.25]))
+        mh, mw = int(ih * m), int(iw * m)
+        mask = (rng.random((mh, mw)) < rng.choice([0.02, 0.05, 0.08, 0.5])).astype(np.uint8) * int(rng.choice([1, 255, 7]))
+        want = capi.plan_tiles(ih, iw, ph, pw, sh, sw, mask, m)
+        np.testing.assert_array_equal(ctx.plan_tiles(ih, iw, ph, pw, sh, sw, mask, m), want)
+        np.testing.assert_array_equal(ctx.plan_tiles(ih, iw, ph, pw, sh, sw, torch.from_numpy(mask).cuda(), m), want)
+    # degenerate geometry: same status code as the host planner
+    with pytest.raises(capi.WsiError) as e:
+        ctx.plan_tiles(100, 700, 128, 64, 32, 32, np.ones((100, 700), np.uint8), 1.0)
+    assert e.value.status == -4          # WSI_ERR_DEGENERATE

@@ -70,6 +70,30 @@ def test_predict_tumorbed_matches_reference(golden_dir, name, arch, mode):
         assert (r["heatmap"][unc] == 127 * g["mask"][unc]).all()
 
 
+@pytest.mark.parametrize("shape", [(256, 320, 64, 80), (100, 130, 33, 47), (64, 64, 32, 32), (40, 60, 80, 120), (97, 61, 13, 9), (37, 53, 37, 53)])
+def test_cv2_resize_restatement(shape):
+    """A9: the oracle restates cv2.resize(INTER_LINEAR, CV_64F) — pinned against cv2 itself (same image on the GPU box)."""
+    cv2 = pytest.importorskip("cv2")
+    H, W, H2, W2 = shape
+    a = np.random.default_rng(H * W2).standard_normal((H, W)) * 5
+    np.testing.assert_allclose(O.cv2_resize_linear(a, W2, H2), cv2.resize(a, (W2, H2)), rtol=0, atol=2e-14)
+
+
+@pytest.mark.parametrize("name", ["wsis_l2", "wsis_l1"])
+def test_predict_wsis_matches_reference(golden_dir, name):
+    """A9: predict_wsis (utils/eval.py:22-81) run unmodified up to pred_to_mask by oracle/ref_harness.py."""
+    g = _load(golden_dir, name)
+    ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g["geom"])
+    m = 1.0 if lvl == 2 else 0.25
+    sd = O.random_state_dict("unet", int(g["seed"]))
+    raster = synth.synth_slide(ih, iw, 4321)
+    r = O.predict_wsis(sd, raster, g["mask"], ph, pw, sh, sw, m=m, batch=16)
+    np.testing.assert_array_equal(np.array(r["tiles"], np.int32).reshape(-1, 2), g["tiles"])
+    assert r["pred"].shape == g["pred"].shape == (4,) + g["mask"].shape
+    np.testing.assert_allclose(r["pred"], g["pred"], rtol=1e-4, atol=2e-4)
+    assert (r["classes"] == g["classes"]).mean() >= 0.999
+
+
 def test_synth_checksum_is_stable():
     s = synth.synth_slide(2048, 2048, 1234, y0=100, y1=164)
     assert s.shape == (64, 2048, 3)

@@ -28,7 +28,8 @@ SYMBOLS = (
     "wsi_set_class_probs", "wsi_kernel_launches", "wsi_model_load", "wsi_plan_tiles", "wsi_free",
     "wsi_band_partition", "wsi_band_tiles", "wsi_run_slide", "wsi_forward_batch", "wsi_forward_tiles",
     "wsi_synth_slide", "wsi_debug_conv", "wsi_debug_gather", "wsi_debug_stem", "wsi_debug_maxpool",
-    "wsi_stage_stats", "wsi_stage_reset",
+    "wsi_stage_stats", "wsi_stage_reset", "wsi_resize_argmax",
+    "wsi_find_nuclei", "wsi_plan_tiles_gpu",
 )
 
 
@@ -93,6 +94,10 @@ def lib() -> C.CDLL:
         "wsi_debug_maxpool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "wsi_stage_stats": (C.c_int, [vp, C.c_char_p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)]),
         "wsi_stage_reset": (C.c_int, [vp]),
+        "wsi_resize_argmax": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, vp, C.c_int, vp]),
+        "wsi_find_nuclei": (C.c_int, [vp, vp, i64, C.c_int, i64, i64, dbl, vp, C.c_int, vp]),
+        "wsi_plan_tiles_gpu": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, C.c_int, i64, i64, dbl, C.POINTER(C.POINTER(i32)),
+                                         C.POINTER(i64), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the library does not export it
@@ -314,6 +319,61 @@ class Context:
         _check(self._lib.wsi_forward_batch(self._h, C.c_void_p(x.data_ptr()), n, h, w, int(head), C.c_void_p(y.data_ptr()),
                                            mem, _stream_ptr(stream)), self._h)
         return y
+
+    def find_nuclei(self, rgb, mu_percent: float = 0.1, device_out: bool = False, stream=None):
+        """find_nuclei(mode='hsv') (utils/preprocessing.py:74-110) on the device.  rgb: u8 [H,W,3] numpy array or CUDA
+        tensor; returns the u8 {0,1} mask as a numpy array, or as a CUDA tensor when device_out."""
+        import torch
+        if isinstance(rgb, np.ndarray):
+            rgb = np.ascontiguousarray(rgb[..., :3], dtype=np.uint8)
+            H, W = rgb.shape[:2]
+            src, stride, mem = rgb.ctypes.data, 3 * W, MEM_HOST
+        else:
+            rgb = rgb.contiguous()
+            assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.shape[-1] == 3
+            H, W = int(rgb.shape[0]), int(rgb.shape[1])
+            src, stride, mem = rgb.data_ptr(), 3 * W, MEM_DEVICE
+        if device_out:
+            mask = torch.empty((H, W), dtype=torch.uint8, device=torch.device("cuda", self.device))
+            dst, dmem = mask.data_ptr(), MEM_DEVICE
+        else:
+            mask = np.empty((H, W), np.uint8)
+            dst, dmem = mask.ctypes.data, MEM_HOST
+        _check(self._lib.wsi_find_nuclei(self._h, C.c_void_p(src), stride, mem, H, W, float(mu_percent), C.c_void_p(dst), dmem,
+                                         _stream_ptr(stream)), self._h)
+        return mask
+
+    def plan_tiles(self, ih, iw, ph, pw, sh, sw, mask, m: float = 1.0, stream=None) -> np.ndarray:
+        """wsi_plan_tiles_gpu: the reference's tile list with the foreground test on the device.  mask: u8 [mh,mw] numpy
+        array or CUDA tensor (required; use capi.plan_tiles for the all-foreground case)."""
+        if isinstance(mask, np.ndarray):
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            ptr, mem = mask.ctypes.data, MEM_HOST
+        else:
+            mask = mask.contiguous()
+            ptr, mem = mask.data_ptr(), MEM_DEVICE
+        mh, mw = int(mask.shape[0]), int(mask.shape[1])
+        xy, n = C.POINTER(C.c_int32)(), C.c_int64()
+        _check(self._lib.wsi_plan_tiles_gpu(self._h, ih, iw, ph, pw, sh, sw, C.c_void_p(ptr), mem, mh, mw, float(m), C.byref(xy),
+                                            C.byref(n), _stream_ptr(stream)), self._h)
+        try:
+            return np.ctypeslib.as_array(xy, shape=(max(n.value, 1), 2))[:n.value].copy() if n.value else np.zeros((0, 2), np.int32)
+        finally:
+            self._lib.wsi_free(xy)
+
+    def resize_argmax(self, canvas, H2: int, W2: int, want_pred: bool = True, stream=None):
+        """predict_wsis tail (utils/eval.py:66-81): canvas f32 [4,H,W] (torch CPU or CUDA) -> classes u8 [H2,W2]
+        (argmax of the per-class cv2.resize) and, optionally, the resized pred f32 [4,H2,W2], on the same device."""
+        import torch
+        canvas = canvas.contiguous().float()
+        assert canvas.dim() == 3 and canvas.shape[0] == 4
+        H, W = int(canvas.shape[1]), int(canvas.shape[2])
+        classes = torch.empty((H2, W2), dtype=torch.uint8, device=canvas.device)
+        pred = torch.empty((4, H2, W2), dtype=torch.float32, device=canvas.device) if want_pred else None
+        mem = MEM_DEVICE if canvas.is_cuda else MEM_HOST
+        _check(self._lib.wsi_resize_argmax(self._h, C.c_void_p(canvas.data_ptr()), H, W, int(H2), int(W2), C.c_void_p(classes.data_ptr()),
+                                           C.c_void_p(pred.data_ptr()) if want_pred else None, mem, _stream_ptr(stream)), self._h)
+        return classes, pred
 
     def forward_tiles(self, slide: SlideDesc, tiles_xy: np.ndarray, head: int, device_out=False, stream=None):
         import torch

@@ -928,6 +928,124 @@ int wsi_forward_tiles(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* 
   WSI_API_END(ctx)
 }
 
+int wsi_resize_argmax(wsi_ctx* ctx, const float* canvas, int64_t H, int64_t W, int64_t H2, int64_t W2, uint8_t* classes,
+                      float* pred_or_null, int mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && canvas && classes && H > 0 && W > 0 && H2 > 0 && W2 > 0, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t in_bytes = (size_t)4 * H * W * sizeof(float), out_px = (size_t)H2 * W2;
+  if (mem == WSI_MEM_HOST) {
+    DevBuf in, cls, pr;
+    in.alloc(in_bytes);
+    cls.alloc(out_px);
+    if (pred_or_null) pr.alloc(out_px * 4 * sizeof(float));
+    CUDA_CHECK(cudaMemcpyAsync(in.p, canvas, in_bytes, cudaMemcpyHostToDevice, s));
+    launch_resize_argmax(in.as<float>(), H, W, H2, W2, cls.as<uint8_t>(), pred_or_null ? pr.as<float>() : nullptr, s, &ctx->lc);
+    CUDA_CHECK(cudaMemcpyAsync(classes, cls.p, out_px, cudaMemcpyDeviceToHost, s));
+    if (pred_or_null) CUDA_CHECK(cudaMemcpyAsync(pred_or_null, pr.p, out_px * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  } else {
+    launch_resize_argmax(canvas, H, W, H2, W2, classes, pred_or_null, s, &ctx->lc);
+  }
+  WSI_API_END(ctx)
+}
+
+int wsi_find_nuclei(wsi_ctx* ctx, const uint8_t* rgb, int64_t row_stride, int rgb_mem, int64_t H, int64_t W, double mu_percent,
+                    uint8_t* mask, int mask_mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && rgb && mask && H > 0 && W > 0 && row_stride >= 3 * W, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // skimage.color.rgb2hsv on the float64 image u8/255: S = (max - min) / max, 0 where max == min; S > mu_percent
+  std::vector<uint32_t> bits(2048, 0);
+  for (int mx = 0; mx < 256; ++mx)
+    for (int mn = 0; mn <= mx; ++mn) {
+      const double a = mx / 255.0, b = mn / 255.0, delta = a - b;
+      const double sat = (delta == 0.0) ? 0.0 : delta / a;
+      if (sat > mu_percent) bits[(mx * 256 + mn) >> 5] |= 1u << ((mx * 256 + mn) & 31);
+    }
+  DevBuf lut, in, out;
+  upload(lut, bits, s);
+  const uint8_t* rgb_d = rgb;
+  int64_t stride_d = row_stride;
+  if (rgb_mem == WSI_MEM_HOST) {
+    in.alloc((size_t)H * W * 3);
+    CUDA_CHECK(cudaMemcpy2DAsync(in.p, (size_t)W * 3, rgb, (size_t)row_stride, (size_t)W * 3, (size_t)H, cudaMemcpyHostToDevice, s));
+    rgb_d = in.as<uint8_t>();
+    stride_d = 3 * W;
+  }
+  uint8_t* mask_d = mask;
+  if (mask_mem == WSI_MEM_HOST) {
+    out.alloc((size_t)H * W);
+    mask_d = out.as<uint8_t>();
+  }
+  launch_find_nuclei(rgb_d, stride_d, H, W, lut.as<uint32_t>(), mask_d, s, &ctx->lc);
+  if (mask_mem == WSI_MEM_HOST) CUDA_CHECK(cudaMemcpyAsync(mask, mask_d, (size_t)H * W, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));      // lut / staging buffers die here
+  WSI_API_END(ctx)
+}
+
+int wsi_plan_tiles_gpu(wsi_ctx* ctx, int64_t ih, int64_t iw, int32_t ph, int32_t pw, int32_t sh, int32_t sw, const uint8_t* mask,
+                       int mask_mem, int64_t mh, int64_t mw, double m, int32_t** xy_out, int64_t* n_out, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && xy_out && n_out && mask && ih > 0 && iw > 0 && ph > 0 && pw > 0 && sh > 0 && sw > 0 && m > 0 && mh > 0 && mw > 0,
+              WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  *xy_out = nullptr;
+  *n_out = 0;
+  // candidates in the reference's order (utils/dataset.py:147-166): main grid, right column, bottom row, no corner
+  std::vector<int64_t> ys, xs;
+  for (int64_t y = 1; y < ih - 1 - ph; y += sh) ys.push_back(y);
+  for (int64_t x = 1; x < iw - 1 - pw; x += sw) xs.push_back(x);
+  const int64_t x_last = iw - 1 - pw, y_last = ih - 1 - ph;
+  std::vector<int32_t> cand;
+  cand.reserve((ys.size() * (xs.size() + 1) + xs.size()) * 2);
+  for (int64_t y : ys) for (int64_t x : xs) { cand.push_back((int32_t)x); cand.push_back((int32_t)y); }
+  for (int64_t y : ys) { cand.push_back((int32_t)x_last); cand.push_back((int32_t)y); }
+  for (int64_t x : xs) { cand.push_back((int32_t)x); cand.push_back((int32_t)y_last); }
+  const int64_t n = (int64_t)cand.size() / 2;
+  const int64_t dx = (int64_t)((double)pw * m), dy = (int64_t)((double)ph * m);
+  std::vector<int64_t> win((size_t)2 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    // the reference would index the mask with a negative origin
+    WSI_REQUIRE(cand[2 * i] >= 0 && cand[2 * i + 1] >= 0, WSI_ERR_DEGENERATE, "tile origin (%d,%d) is negative", cand[2 * i], cand[2 * i + 1]);
+    win[2 * i] = (int64_t)((double)cand[2 * i] * m);
+    win[2 * i + 1] = (int64_t)((double)cand[2 * i + 1] * m);
+  }
+  std::vector<int32_t> keep;
+  if (n > 0) {
+    DevBuf mask_buf, win_d, cnt_d, size_d;
+    const uint8_t* mask_d = mask;
+    if (mask_mem == WSI_MEM_HOST) {
+      mask_buf.alloc((size_t)mh * mw);
+      CUDA_CHECK(cudaMemcpyAsync(mask_buf.p, mask, (size_t)mh * mw, cudaMemcpyHostToDevice, s));
+      mask_d = mask_buf.as<uint8_t>();
+    }
+    upload(win_d, win, s);
+    cnt_d.alloc((size_t)n * sizeof(uint32_t));
+    size_d.alloc((size_t)n * sizeof(int64_t));
+    launch_window_count(mask_d, mh, mw, win_d.as<int64_t>(), n, dx, dy, cnt_d.as<uint32_t>(), size_d.as<int64_t>(), s, &ctx->lc);
+    std::vector<uint32_t> cnt((size_t)n);
+    std::vector<int64_t> size((size_t)n);
+    CUDA_CHECK(cudaMemcpyAsync(cnt.data(), cnt_d.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(size.data(), size_d.p, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n; ++i) {
+      // isforeground: python int / python int >= 0.05; an empty window raises ZeroDivisionError in the reference
+      WSI_REQUIRE(size[(size_t)i] > 0, WSI_ERR_DEGENERATE, "tile (%d,%d): empty mask window", cand[2 * i], cand[2 * i + 1]);
+      if ((double)cnt[(size_t)i] / (double)size[(size_t)i] >= 0.05) { keep.push_back(cand[2 * i]); keep.push_back(cand[2 * i + 1]); }
+    }
+  }
+  int32_t* buf = (int32_t*)malloc(std::max<size_t>(keep.size(), 2) * sizeof(int32_t));
+  WSI_REQUIRE(buf != nullptr, WSI_ERR_NOMEM, "out of host memory");
+  if (!keep.empty()) memcpy(buf, keep.data(), keep.size() * sizeof(int32_t));
+  *xy_out = buf;
+  *n_out = (int64_t)keep.size() / 2;
+  WSI_API_END(ctx)
+}
+
 int wsi_synth_slide(wsi_ctx* ctx, int64_t ih, int64_t iw, uint32_t seed, int64_t y0, int64_t y1, const uint8_t* lut, uint8_t* rgb_dev,
                     int64_t row_stride, uint8_t* mask_dev_or_null, void* stream) {
   WSI_API_BEGIN

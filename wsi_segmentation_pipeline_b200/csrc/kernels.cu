@@ -474,4 +474,134 @@ void launch_synth(int64_t ih, int64_t iw, uint32_t seed, int64_t y0, int64_t y1,
   if (lc) lc->n++;
 }
 
+// A9 (predict_wsis, utils/eval.py:66-81): per-class cv2.resize(pred[c], level-2 size) of the summed-logit canvas
+// — INTER_LINEAR as OpenCV computes it for CV_64F: source coordinate (d + 0.5) * scale - 0.5 in double, floor +
+// fraction, clamped to the border (fraction 0 there), weights 1 - f and f, horizontal pass then vertical pass —
+// followed by np.argmax over the classes (first maximum).  OpenCV blends in double, this kernel in fp32 (the
+// canvas is fp32): values agree to ~1e-6 relative, the argmax except at near-ties.  HBM-bound: 16 B read per
+// source pixel (each read once when downscaling), 17 B written per destination pixel.
+__global__ void __launch_bounds__(256) resize_argmax_kernel(const float* __restrict__ src, int64_t H, int64_t W, int64_t H2, int64_t W2,
+                                                             double scale_x, double scale_y, uint8_t* __restrict__ classes,
+                                                             float* __restrict__ pred) {
+  const int64_t plane_s = H * W, plane_d = H2 * W2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane_d; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t dy = idx / W2, dx = idx - dy * W2;
+    const double fxd = ((double)dx + 0.5) * scale_x - 0.5, fyd = ((double)dy + 0.5) * scale_y - 0.5;
+    int64_t sx = (int64_t)floor(fxd);
+    float fx = (float)(fxd - (double)sx);
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= W - 1) { sx = W - 1; fx = 0.f; }
+    const int64_t sy = (int64_t)floor(fyd);
+    const float fy = (float)(fyd - (double)sy);
+    const int64_t y0 = min(max(sy, (int64_t)0), H - 1), y1 = min(max(sy + 1, (int64_t)0), H - 1);
+    const int64_t x1 = min(sx + 1, W - 1);
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    float best = 0.f;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float* pl = src + (int64_t)c * plane_s;
+      const float h0 = __fadd_rn(__fmul_rn(__ldg(pl + y0 * W + sx), a0), __fmul_rn(__ldg(pl + y0 * W + x1), a1));
+      const float h1 = __fadd_rn(__fmul_rn(__ldg(pl + y1 * W + sx), a0), __fmul_rn(__ldg(pl + y1 * W + x1), a1));
+      const float v = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+      if (pred) pred[(int64_t)c * plane_d + idx] = v;
+      if (c == 0 || v > best) { best = v; arg = c; }
+    }
+    classes[idx] = (uint8_t)arg;
+  }
+}
+
+void launch_resize_argmax(const float* src, int64_t H, int64_t W, int64_t H2, int64_t W2, uint8_t* classes, float* pred, cudaStream_t s,
+                          LaunchCounter* lc) {
+  const int64_t plane = H2 * W2;
+  if (plane <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(plane, 256), 148 * 32);
+  // OpenCV: inv_scale = dsize / ssize (double), scale = 1 / inv_scale
+  const double scale_x = 1.0 / ((double)W2 / (double)W), scale_y = 1.0 / ((double)H2 / (double)H);
+  resize_argmax_kernel<<<grid, 256, 0, s>>>(src, H, W, H2, W2, scale_x, scale_y, classes, pred);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// A12 (find_nuclei mode='hsv', utils/preprocessing.py:74-110): mask = HSV saturation > mu_percent.  skimage's rgb2hsv
+// computes S = (max - min) / max on the float64 image u8/255 (0 where max == min); the comparison only depends on
+// (max, min), so the host evaluates exactly those float64 operations for all 256 x 256 pairs into a bit table and
+// the kernel is a max/min + lookup: bit-exact with the float64 formula by construction.  HBM-bound: 3 B read + 1 B
+// written per pixel.
+__global__ void __launch_bounds__(256) find_nuclei_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t H, int64_t W,
+                                                           const uint32_t* __restrict__ lut_bits, uint8_t* __restrict__ mask) {
+  __shared__ uint32_t s_lut[2048];      // 65536 bits: index mx * 256 + mn
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_lut[i] = lut_bits[i];
+  __syncthreads();
+  const int64_t total = H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t y = idx / W, x = idx - y * W;
+    const uint8_t* px = rgb + y * row_stride + 3 * x;
+    const int r = px[0], g = px[1], b = px[2];
+    const int mx = max(r, max(g, b)), mn = min(r, min(g, b));
+    const int bit = mx * 256 + mn;
+    mask[idx] = (uint8_t)((s_lut[bit >> 5] >> (bit & 31)) & 1u);
+  }
+}
+
+void launch_find_nuclei(const uint8_t* rgb, int64_t row_stride, int64_t H, int64_t W, const uint32_t* lut_bits, uint8_t* mask, cudaStream_t s,
+                        LaunchCounter* lc) {
+  const int64_t total = H * W;
+  if (total <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+  find_nuclei_kernel<<<grid, 256, 0, s>>>(rgb, row_stride, H, W, lut_bits, mask);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// A1/A12 (isforeground, utils/preprocessing.py:60-71, called per candidate tile from utils/dataset.py:147-166):
+// count_nonzero(mask[yp:yp+dy, xp:xp+dx]) with numpy's silent clipping at the mask edge; one CTA per candidate window,
+// 4-byte loads over the aligned body of each row.  counts[i] = nonzero pixels, sizes[i] = clipped window size.
+__global__ void __launch_bounds__(256) window_count_kernel(const uint8_t* __restrict__ mask, int64_t mh, int64_t mw,
+                                                            const int64_t* __restrict__ win /* [n][2] = (xp, yp) */, int64_t dx, int64_t dy,
+                                                            uint32_t* __restrict__ counts, int64_t* __restrict__ sizes) {
+  const int64_t i = blockIdx.x;
+  const int64_t xp = win[2 * i], yp = win[2 * i + 1];
+  const int64_t x0 = min(xp, mw), x1 = min(xp + dx, mw), y0 = min(yp, mh), y1 = min(yp + dy, mh);
+  const int64_t w = x1 - x0, h = y1 - y0;
+  uint32_t cnt = 0;
+  if (w > 0 && h > 0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int64_t y = y0 + warp; y < y1; y += nwarps) {
+      const uint8_t* row = mask + y * mw;
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(row + x0);
+      const int64_t head = min((int64_t)((4 - (int64_t)(a0 & 3)) & 3), w);
+      const int64_t body = (w - head) >> 2;
+      if (lane < head) cnt += row[x0 + lane] != 0;
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(row + x0 + head);
+      for (int64_t k = lane; k < body; k += 32) {
+        uint32_t t = __ldg(rw + k);
+        t |= t >> 4; t |= t >> 2; t |= t >> 1;      // bit 0 of every byte = OR of its 8 bits
+        cnt += __popc(t & 0x01010101u);
+      }
+      const int64_t tail0 = head + 4 * body;
+      if (lane < w - tail0) cnt += row[x0 + tail0 + lane] != 0;
+    }
+  }
+  __shared__ uint32_t s_cnt[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) c += s_cnt[k];
+    counts[i] = c;
+    sizes[i] = (w > 0 && h > 0) ? w * h : 0;
+  }
+}
+
+void launch_window_count(const uint8_t* mask, int64_t mh, int64_t mw, const int64_t* win, int64_t n, int64_t dx, int64_t dy, uint32_t* counts,
+                         int64_t* sizes, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return;
+  window_count_kernel<<<(unsigned)n, 256, 0, s>>>(mask, mh, mw, win, dx, dy, counts, sizes);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
 }  // namespace wsi

@@ -62,4 +62,15 @@ void launch_counts(const RectIndex& ri, int T, int64_t W2, int64_t own0, int64_t
 void launch_synth(int64_t ih, int64_t iw, uint32_t seed, int64_t y0, int64_t y1, const uint8_t* lut_dev,
                   uint8_t* rgb, int64_t row_stride, uint8_t* mask_or_null, cudaStream_t s, LaunchCounter* lc);
 
+// A9: cv2.resize(INTER_LINEAR) of the [4][H][W] summed-logit canvas to [H2][W2] + argmax (predict_wsis, utils/eval.py:66-81)
+void launch_resize_argmax(const float* src, int64_t H, int64_t W, int64_t H2, int64_t W2, uint8_t* classes, float* pred_or_null,
+                          cudaStream_t s, LaunchCounter* lc);
+
+// A12: find_nuclei(mode='hsv') — HSV saturation threshold through a (max, min) bit table built in float64 on the host
+void launch_find_nuclei(const uint8_t* rgb, int64_t row_stride, int64_t H, int64_t W, const uint32_t* lut_bits, uint8_t* mask, cudaStream_t s,
+                        LaunchCounter* lc);
+// A1/A12: isforeground window counts of the tile planner, one CTA per candidate window
+void launch_window_count(const uint8_t* mask, int64_t mh, int64_t mw, const int64_t* win, int64_t n, int64_t dx, int64_t dy, uint32_t* counts,
+                         int64_t* sizes, cudaStream_t s, LaunchCounter* lc);
+
 }  // namespace wsi

@@ -85,7 +85,9 @@ class Dataset_wsi:
     """One slide: the tile plan (``datalist``: list of (x, y) in scan-level pixels, reference
     order) and lazy access to the scan-level raster."""
 
-    def __init__(self, scan, params, mask: Optional[np.ndarray], scan_level: int = 2):
+    def __init__(self, scan, params, mask: Optional[np.ndarray], scan_level: int = 2, engine=None):
+        """engine: a capi.Context — the foreground mask (find_nuclei) and the foreground test of the tile plan then run
+        on the GPU (wsi_find_nuclei / wsi_plan_tiles_gpu, same results); None: host numpy / host C++ planner."""
         self.scan, self.params, self.scan_level = scan, params, scan_level
         self.datalist, self.tiles = [], np.zeros((0, 2), np.int32)
         self.mask = mask
@@ -93,10 +95,11 @@ class Dataset_wsi:
             return
         self.params.iw, self.params.ih = scan.level_dimensions[scan_level]
         if self.mask is None:                                # :131-134
-            self.mask = find_nuclei_hsv(_level_raster(scan, 2))
+            thumb = _level_raster(scan, 2)
+            self.mask = engine.find_nuclei(thumb) if engine is not None else find_nuclei_hsv(thumb)
         self.m = scan.level_downsamples[scan_level] / scan.level_downsamples[2]
-        self.tiles = capi.plan_tiles(self.params.ih, self.params.iw, self.params.ph, self.params.pw, self.params.sh, self.params.sw,
-                                     self.mask, self.m)
+        plan = engine.plan_tiles if engine is not None else capi.plan_tiles
+        self.tiles = plan(self.params.ih, self.params.iw, self.params.ph, self.params.pw, self.params.sh, self.params.sw, self.mask, self.m)
         self.datalist = [tuple(int(v) for v in t) for t in self.tiles]
         self._raster = None
 
@@ -116,7 +119,7 @@ class Dataset_wsis:
     (the reference caches these as PNGs under ``args.wsi_mask_pth``)."""
 
     def __init__(self, svs_pth, params, bs: int = 30, scan_level: int = 2, masks: Optional[Mapping] = None,
-                 wsi_mask_pth: Optional[str] = None):
+                 wsi_mask_pth: Optional[str] = None, engine=None):
         self.params = DotDict(params)
         self.wsis = {}
         self.scan_level = scan_level
@@ -132,7 +135,7 @@ class Dataset_wsis:
             if mask is None and msk_pth and os.path.exists(msk_pth):
                 from PIL import Image
                 mask = np.asarray(Image.open(msk_pth).convert("L"))
-            itr = Dataset_wsi(scan, DotDict(self.params), mask, scan_level)
+            itr = Dataset_wsi(scan, DotDict(self.params), mask, scan_level, engine=engine)
             if len(itr) > 0:                                  # GenerateIterator_wsi returns None for empty slides (:198-201)
                 self.params.iw, self.params.ih = itr.params.iw, itr.params.ih
                 self.wsis[key] = {"iterator": itr, "wsipath": path, "scan": scan, "maskpath": msk_pth, "mask": itr.mask}

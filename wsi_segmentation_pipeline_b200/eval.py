@@ -91,6 +91,39 @@ def predict_tumorbed(model, dataset, ep, mode: str = "seg", args=None, return_ou
     return outputs
 
 
+def predict_wsis(model, dataset, ep, args=None):
+    """utils/eval.py:22-81 up to the argmax: dense seg logits summed on a canvas at SCAN-LEVEL resolution
+    (``pred[:, y:y+ph, x:x+pw] += model(batch)``, :46-60), per-class ``cv2.resize`` to the level-2 size (:66-71) and
+    ``np.argmax`` (:81).  Returns {key: {'classes': u8 [H2,W2], 'pred': f32 [4,H2,W2]}}.
+
+    Not mirrored: the ground-truth scores, tumour-bed morphology and colour-mask PNG after the
+    argmax — ``pred_to_mask`` (utils/preprocessing.py:186-189) raises in the reference itself."""
+    a = _merge_args(args)
+    if a.scan_resize != 1:
+        raise NotImplementedError("scan_resize != 1 (utils/eval.py:52-55) is not on the CUDA path")
+    ctx = _engine_of(model)
+    ctx.set_class_probs([0.0, 0.0, 0.0, 0.0])
+    if hasattr(model, "eval"):
+        model.eval()
+    outputs = {}
+    for key in list(dataset.wsis):
+        entry = dataset.wsis[key]
+        if entry is None:
+            continue
+        it, scan = entry["iterator"], entry["scan"]
+        raster = it.raster()
+        ih, iw = raster.shape[:2]
+        W2, H2 = scan.level_dimensions[2]
+        # the canvas lives at scan-level resolution: tiles land at (x, y) unscaled, no foreground mask inside the loop
+        sl = ctx.slide_desc(raster, ih, iw, dataset.params.ph, dataset.params.pw, m=1.0, H2=ih, W2=iw, mask=None)
+        r = ctx.run_slide(sl, it.tiles, capi.HEAD_SEG, device_out=True, want_canvas=True)
+        classes, pred = ctx.resize_argmax(r["canvas"], H2, W2)
+        outputs[key] = {"classes": classes.cpu().numpy(), "pred": pred.cpu().numpy()}
+    if hasattr(model, "train"):
+        model.train()
+    return outputs
+
+
 def band_plan(ih: int, ph: int, sh: int, tiles: np.ndarray, m: float, world: int):
     """Per rank: (own0, own1, row0, row1, tile indices).  SURVEY 8e: boundaries on the tile grid;
     a rank evaluates every tile intersecting its band, so nothing is exchanged during compute."""
