@@ -372,6 +372,19 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
 // own TMEM region and its own two epilogue groups (4 x 4 epilogue warps in all), and a completed output row is
 // signalled per ring slot (row_done[slot]) so the stage ring and the accumulator ring are decoupled.
 // ---------------------------------------------------------------------------------------------
+// packed fp32 FMA (FFMA2): two independent IEEE fmas per instruction — halves the epilogue's FMA count without
+// changing any rounding
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ua, ub, uc, ud;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+  return d;
+}
+
 constexpr int kRun2Cols = 256 + 2 * kRowPad;              // 272 entries: x = b0-8 .. b0+263
 constexpr int kRun2Bytes = kRun2Cols * 16;                // 4352
 constexpr int kStream2Threads = (1 + 1 + 16) * 32;
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
     const int lane_sel = egrp >> 1;
     const uint32_t rowpar = (uint32_t)(egrp & 1);
     const int mrow = q * 32 + lane;
-    constexpr bool kRegSB = (BN == 16);                 // folded-BN constants in registers only where the budget allows
+    constexpr bool kRegSB = (BN == 16) && !HEAD;        // folded-BN constants in registers only where the budget allows
     float r_scale[kRegSB ? BN : 1], r_bias[kRegSB ? BN : 1];
     if (kRegSB) {
 #pragma unroll
@@ -607,13 +620,39 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
           ptx::tmem_ld16(t_row + (uint32_t)c, v);
           ptx::tmem_ld_wait();
           float yv[16];
+          if (HEAD) {
+            // d5b + final_conv: BN, ReLU and the 16 -> 4 head as packed FMAs; constants are broadcast smem reads.
+            // Lane .x of every pair carries the even channels, .y the odd ones: the same two summation chains per
+            // logit as the scalar formulation, so the result is bit-identical.
+            float2 y2[8];
+#pragma unroll
+            for (int jp = 0; jp < 8; ++jp) {
+              const float2 sc = reinterpret_cast<const float2*>(s_scale)[jp], bi = reinterpret_cast<const float2*>(s_bias)[jp];
+              y2[jp] = ffma2(make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])), sc, bi);
+              y2[jp].x = fmaxf(y2[jp].x, lo);
+              y2[jp].y = fmaxf(y2[jp].y, lo);
+            }
+            float* hp = reinterpret_cast<float*>(&hacc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int jp = 0; jp < 8; ++jp) acc = ffma2(y2[jp], reinterpret_cast<const float2*>(s_hw + k * 16)[jp], acc);
+              hp[k] = (acc.x + acc.y) + s_hb[k];
+            }
+            if (valid && p.out != nullptr) {
+#pragma unroll
+              for (int jp = 0; jp < 8; ++jp) { yv[2 * jp] = y2[jp].x; yv[2 * jp + 1] = y2[jp].y; }
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float sc = kRegSB ? r_scale[kRegSB ? c + j : 0] : s_scale[c + j];
             const float bi = kRegSB ? r_bias[kRegSB ? c + j : 0] : s_bias[c + j];
             yv[j] = fmaf(__uint_as_float(v[j]), sc, bi);
           }
-          if (has_res) {
+          }
+          if (!HEAD && has_res) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const uint4 rv = rall[c / 8 + k];
@@ -625,25 +664,9 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
               }
             }
           }
+          if (!HEAD) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) yv[j] = fmaxf(yv[j], lo);
-          if (HEAD) {
-            // fused 1x1 final conv: weights are broadcast reads from smem (the register budget of 576 threads has no
-            // room for them); two independent chains per logit, summed in a fixed order
-            float* hp = reinterpret_cast<float*>(&hacc);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-              for (int j4 = 0; j4 < 16; j4 += 4) {
-                const float4 hw = *reinterpret_cast<const float4*>(s_hw + k * 16 + j4);
-                s0 = fmaf(yv[j4 + 0], hw.x, s0);
-                s1 = fmaf(yv[j4 + 1], hw.y, s1);
-                s0 = fmaf(yv[j4 + 2], hw.z, s0);
-                s1 = fmaf(yv[j4 + 3], hw.w, s1);
-              }
-              hp[k] = (s0 + s1) + s_hb[k];
-            }
+            for (int j = 0; j < 16; ++j) yv[j] = fmaxf(yv[j], lo);
           }
           if (valid && p.out != nullptr) {
 #pragma unroll
