@@ -14,7 +14,7 @@ namespace wsi {
 //   Output is the stem's operand layout: [n][ph+6][pw+8][4] bf16, zero border (3 top/left), ch 3 = 0.
 // =============================================================================================
 __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t row0,
-                                                      const int32_t* __restrict__ tiles_xy, int ph, int pw,
+                                                      const int32_t* __restrict__ tiles_xy, int n_tiles, int ph, int pw,
                                                       const float* __restrict__ lut, bf16* __restrict__ padded,
                                                       float* __restrict__ norm_out) {
   // s_lut: the 3x256 possible outputs of Normalize(ToTensor(u8)) in fp32 (host-built, reference op order)
@@ -26,26 +26,29 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
     s_lut[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
   __syncthreads();
-  const int t = blockIdx.x / ph, r = blockIdx.x % ph;
-  const int x0 = tiles_xy[2 * t], y0 = tiles_xy[2 * t + 1];
-  const uint8_t* src = rgb + (int64_t)(y0 + r - row0) * row_stride + (int64_t)x0 * 3;
+  // persistent blocks over (tile, row) pairs: the table is built once per block, not once per 512 pixels
   const int64_t pitch = (int64_t)(pw + 8) * 4;
-  bf16* dst = padded + ((int64_t)t * (ph + 6) + (r + 3)) * pitch + 3 * 4;
-  for (int x = threadIdx.x; x < pw; x += blockDim.x) {
-    const uint8_t c0 = __ldg(src + 3 * x), c1 = __ldg(src + 3 * x + 1), c2 = __ldg(src + 3 * x + 2);
-    const uint16_t v0 = s_lut[c0], v1 = s_lut[256 + c1], v2 = s_lut[512 + c2];
-    if (padded) {
-      uint2 o;
-      o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
-      o.y = (uint32_t)v2;
-      *reinterpret_cast<uint2*>(dst + 4 * x) = o;
-    }
-    if (norm_out) {
-      const int64_t plane = (int64_t)ph * pw;
-      float* q = norm_out + (int64_t)t * 3 * plane + (int64_t)r * pw + x;
-      q[0] = s_f32[c0];
-      q[plane] = s_f32[256 + c1];
-      q[2 * plane] = s_f32[512 + c2];
+  for (int64_t job = blockIdx.x; job < (int64_t)n_tiles * ph; job += gridDim.x) {
+    const int t = (int)(job / ph), r = (int)(job - (int64_t)t * ph);
+    const int x0 = tiles_xy[2 * t], y0 = tiles_xy[2 * t + 1];
+    const uint8_t* src = rgb + (int64_t)(y0 + r - row0) * row_stride + (int64_t)x0 * 3;
+    bf16* dst = padded + ((int64_t)t * (ph + 6) + (r + 3)) * pitch + 3 * 4;
+    for (int x = threadIdx.x; x < pw; x += blockDim.x) {
+      const uint8_t c0 = __ldg(src + 3 * x), c1 = __ldg(src + 3 * x + 1), c2 = __ldg(src + 3 * x + 2);
+      const uint16_t v0 = s_lut[c0], v1 = s_lut[256 + c1], v2 = s_lut[512 + c2];
+      if (padded) {
+        uint2 o;
+        o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
+        o.y = (uint32_t)v2;
+        *reinterpret_cast<uint2*>(dst + 4 * x) = o;
+      }
+      if (norm_out) {
+        const int64_t plane = (int64_t)ph * pw;
+        float* q = norm_out + (int64_t)t * 3 * plane + (int64_t)r * pw + x;
+        q[0] = s_f32[c0];
+        q[plane] = s_f32[256 + c1];
+        q[2 * plane] = s_f32[512 + c2];
+      }
     }
   }
 }
@@ -53,7 +56,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
 void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n, int ph,
                    int pw, const float* lut_dev, bf16* padded, float* norm_out, cudaStream_t s, LaunchCounter* lc) {
   if (n <= 0) return;
-  gather_kernel<<<(unsigned)((int64_t)n * ph), 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, ph, pw, lut_dev, padded, norm_out);
+  const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n * ph, 148 * 8);
+  gather_kernel<<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
