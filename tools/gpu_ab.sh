@@ -1,11 +1,9 @@
 #!/bin/bash
-# scratch A/B: cost of tcgen05.commit in the two-lane row-stream kernel (WSI_STREAM_DBG=6 adds two per row; =1 no MMAs)
+# scratch A/B: do the high-resolution layers get faster when a batch's tensors fit in L2?  (per-layer ms / tiles)
 mkdir -p gpurun_out
-for d in 0 6 1; do
-  echo "=== WSI_STREAM_DBG=$d"
-  WSI_STREAM_DBG=$d WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/conv_trace_stdbg$d.log 2>&1; echo "exit $?"
-  grep -E "iter 2|16->16|32->32" gpurun_out/conv_trace_stdbg$d.log | cut -c1-110
+for b in 74 37 18 12 8; do
+  echo "=== batch $b"
+  WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet $b > gpurun_out/conv_trace_b$b.log 2>&1; echo "exit $?"
+  grep -E "iter 2|stem 7x7|BK16|192->64" gpurun_out/conv_trace_b$b.log | cut -c1-100
+  grep -E "iter 2" -A4 gpurun_out/conv_trace_b$b.log | grep -E "maxpool|gather" | tail -2
 done
-echo "=== single lane"
-WSI_STREAM_LANES1=1 WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/conv_trace_l1.log 2>&1; echo "exit $?"
-grep -E "iter 2|16->16|32->32" gpurun_out/conv_trace_l1.log | cut -c1-110
