@@ -202,3 +202,104 @@ def test_empty_tile_list_and_errors(ctx):
     with pytest.raises(capi.WsiError):      # no model loaded
         c2.run_slide(c2.slide_desc(raster, 128, 128, 64, 64), np.array([[1, 1]], np.int32), capi.HEAD_SEG)
     c2.close()
+
+
+def test_config1_resnet_cls_2048(ctx):
+    """BASELINE configs[0]: ResNet-18 4-class patch classifier on a synthetic 2048x2048 slide, 256x256 tiles stride 128
+    (T = 224), against the oracle in fp32 on the same slide, mask and weights: coordinates and counts bit-exact,
+    probabilities within the north-star bf16 tolerance."""
+    ih = iw = 2048
+    ph = pw = 256
+    sh = sw = 128
+    sd = _load_model(ctx, "resnet18_cls", 11)
+    raster = synth.synth_slide(ih, iw, 2024)
+    mask = np.ones((ih, iw), np.uint8)
+    tiles = capi.plan_tiles(ih, iw, ph, pw, sh, sw, mask, 1.0)
+    assert len(tiles) == 224                                            # SURVEY 8a: 14*14 + 14 + 14
+    ref = O.predict_tumorbed(sd, "resnet18_cls", raster, mask, ph, pw, sh, sw, "cls", batch=16)
+    np.testing.assert_array_equal(tiles, np.array(ref["tiles"], np.int32).reshape(-1, 2))
+    r = _run(ctx, raster, mask, tiles, ph, pw, 1.0, capi.HEAD_CLS)
+    np.testing.assert_array_equal(r["counts"].numpy(), ref["counts"])
+    with O.bf16_emulation():
+        emu = O.predict_tumorbed(sd, "resnet18_cls", raster, mask, ph, pw, sh, sw, "cls", batch=16)
+    probs, classes = r["probs"].numpy(), r["classes"].numpy()
+    e_err, e_agree = np.abs(probs - emu["probs"]).max(), (classes == emu["classes"]).mean()
+    f_err, f_agree = np.abs(probs - ref["probs"]).max(), (classes == ref["classes"]).mean()
+    noise, n_agree = np.abs(emu["probs"] - ref["probs"]).max(), (emu["classes"] == ref["classes"]).mean()
+    print(f"config 1: vs bf16-emulated oracle prob max {e_err:.2e} argmax agree {e_agree:.5f} | vs fp32 oracle {f_err:.2e} / {f_agree:.5f} "
+          f"| emulated-vs-fp32 {noise:.2e} / {n_agree:.5f}")
+    # random-init weights give near-uniform class probabilities (bf16 rounding alone flips 0.8 % of the argmax
+    # pixels against fp32), so the argmax gate is: identical wherever the margin exceeds twice the probability error
+    top2 = np.sort(emu["probs"], axis=0)[-2:]
+    clear = (top2[1] - top2[0]) > 2 * e_err
+    assert e_err <= PROB_TOL and (classes[clear] == emu["classes"][clear]).all() and clear.mean() > 0.9
+    assert f_err <= NOISE_FACTOR * noise + NOISE_SLACK and f_agree >= min(ARGMAX_AGREE, n_agree - 0.005)
+    assert np.abs(r["heatmap"].numpy().astype(int) - ref["heatmap"].astype(int)).max() <= int(255 * f_err * 2) + 2
+
+
+@pytest.mark.parametrize("stride", [64, 32, 16])
+def test_stride_sweep_counts_and_parity(ctx, stride):
+    """BASELINE configs[4] (tile-overlap sweep, here 64 px tiles at stride 64/32/16): overlap counts bit-exact for every
+    overlap factor, dense-seg probabilities no further from the fp32 oracle than bf16 operand rounding alone."""
+    ih, iw, p = 200, 264, 64
+    sd = _load_model(ctx, "unet_seg", 6)
+    raster = synth.synth_slide(ih, iw, 99)
+    mask = np.ones((ih, iw), np.uint8)
+    tiles = capi.plan_tiles(ih, iw, p, p, stride, stride, mask, 1.0)
+    r = _run(ctx, raster, mask, tiles, p, p, 1.0, capi.HEAD_SEG)
+    ref = O.predict_tumorbed(sd, "unet_seg", raster, mask, p, p, stride, stride, "seg", batch=32)
+    np.testing.assert_array_equal(tiles, np.array(ref["tiles"], np.int32).reshape(-1, 2))
+    np.testing.assert_array_equal(r["counts"].numpy(), ref["counts"])
+    assert r["counts"].max().item() >= (p // stride) ** 2 - 1 or stride == p
+    with O.bf16_emulation():
+        emu = O.predict_tumorbed(sd, "unet_seg", raster, mask, p, p, stride, stride, "seg", batch=32)
+    noise = np.abs(emu["probs"] - ref["probs"])
+    err = np.abs(r["probs"].numpy() - ref["probs"])
+    agree, n_agree = (r["classes"].numpy() == ref["classes"]).mean(), (emu["classes"] == ref["classes"]).mean()
+    print(f"stride {stride}: {len(tiles)} tiles, max count {r['counts'].max().item()}, prob err {err.max():.2e} (bf16 emulation {noise.max():.2e}), "
+          f"argmax agree {agree:.5f} ({n_agree:.5f})")
+    assert err.max() <= NOISE_FACTOR * noise.max() + NOISE_SLACK
+    assert agree >= n_agree - 0.01
+
+
+def test_full_size_slide_properties(ctx):
+    """BASELINE configs[1] at its full size (20k x 20k, 512 px tiles, stride 128, T = 23 715, U-Net dense seg), through
+    size-independent properties (the oracle cannot run this size): analytic overlap counts, uncovered-pixel outputs,
+    run-to-run determinism, tile-order invariance and row-band invariance — everything compared on the device."""
+    ih = iw = 20000
+    p, s = 512, 128
+    _load_model(ctx, "unet_seg", 3)
+    tiles = capi.plan_tiles(ih, iw, p, p, s, s, None, 1.0)
+    assert len(tiles) == 23715                                           # SURVEY 8a: 153^2 + 306
+    rgb = ctx.synth_slide(ih, iw, 1234)
+    sl = ctx.slide_desc(rgb, ih, iw, p, p)
+    base = ctx.run_slide(sl, tiles, capi.HEAD_SEG, device_out=True, want_counts=True)
+    cnt = base["counts"]
+    # overlap counts, bit-exact at full size: the plan is (grid rows x (grid + right columns)) + (bottom row x grid
+    # columns) — no corner tile — so the count map is a sum of two outer products of 1-D coverage profiles
+    def profile(starts, n):
+        c = np.zeros(n, np.int32)
+        for v in starts:
+            c[v:v + p] += 1
+        return torch.from_numpy(c).cuda()
+    gx, gy = list(range(1, iw - 1 - p, s)), list(range(1, ih - 1 - p, s))
+    Cg, Cr, Rg, Rb = profile(gx, iw), profile([iw - 1 - p], iw), profile(gy, ih), profile([ih - 1 - p], ih)
+    expect = Rg[:, None] * (Cg + Cr)[None, :] + Rb[:, None] * Cg[None, :]
+    assert torch.equal(cnt, expect)
+    assert int(cnt.sum(dtype=torch.int64).item()) == len(tiles) * p * p
+    del expect
+    unc = cnt == 0
+    assert int(unc.sum().item()) > 0                                       # row/column 0 and the unplanned corner stay uncovered
+    assert bool((base["classes"][unc] == 0).all()) and bool((base["heatmap"][unc] == 127).all())
+    again = ctx.run_slide(sl, tiles, capi.HEAD_SEG, device_out=True)
+    assert torch.equal(again["classes"], base["classes"]) and torch.equal(again["heatmap"], base["heatmap"])
+    perm = np.random.default_rng(0).permutation(len(tiles))
+    shuf = ctx.run_slide(sl, tiles[perm], capi.HEAD_SEG, device_out=True)
+    assert torch.equal(shuf["classes"], base["classes"]) and torch.equal(shuf["heatmap"], base["heatmap"])
+    del again, shuf
+    bands = capi.band_partition(ih, p, s, 4)
+    for own0, own1, row0, row1 in bands[[0, 2]]:                           # first and an interior band of a 4-GPU split
+        idx = capi.band_tiles(tiles, p, 1.0, own0, own1)
+        slb = ctx.slide_desc(rgb[row0:row1], ih, iw, p, p, row0=int(row0), rows=int(row1 - row0), own0=int(own0), own1=int(own1))
+        rb = ctx.run_slide(slb, tiles[idx], capi.HEAD_SEG, device_out=True)
+        assert torch.equal(rb["classes"], base["classes"][own0:own1]) and torch.equal(rb["heatmap"], base["heatmap"][own0:own1])
