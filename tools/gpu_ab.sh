@@ -1,9 +1,11 @@
 #!/bin/bash
-# scratch A/B: do the high-resolution layers get faster when a batch's tensors fit in L2?  (per-layer ms / tiles)
+# scratch A/B: TMA A-tile row cost, strided NHWC rows vs contiguous chunk-planar rows (WSI_IGEMM_ALT; garbage results)
 mkdir -p gpurun_out
-for b in 74 37 18 12 8; do
-  echo "=== batch $b"
-  WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet $b > gpurun_out/conv_trace_b$b.log 2>&1; echo "exit $?"
-  grep -E "iter 2|stem 7x7|BK16|192->64" gpurun_out/conv_trace_b$b.log | cut -c1-100
-  grep -E "iter 2" -A4 gpurun_out/conv_trace_b$b.log | grep -E "maxpool|gather" | tail -2
+for a in 0 1; do
+  for d in 0 1; do
+    echo "=== ALT=$a DBG=$d"
+    if [ $a == 1 ]; then export WSI_IGEMM_ALT=1; else unset WSI_IGEMM_ALT; fi
+    WSI_IGEMM_DBG=$d WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/conv_trace_alt$a$d.log 2>&1; echo "exit $?"
+    grep -E "iter 2|128->128  @64x64|256->256  @32x32 BN256|512->512  @16x16 BN256 BK64 x2   " gpurun_out/conv_trace_alt$a$d.log | cut -c1-100
+  done
 done
