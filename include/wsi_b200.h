@@ -123,6 +123,14 @@ WSI_API int wsi_band_tiles(const int32_t* xy, int64_t n, int32_t ph, double m, i
 WSI_API int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,
                   int head, const wsi_out_desc* out, void* stream);
 
+/* ---- resnets_shift.ResNet.forward (resnets_shift.py:189-217): multi-patch classifier with the ensemble head ---
+ * xs: f32 [P*B, 3, h, w] normalised patches, PATCH-MAJOR (xs.transpose(0, 1) of the reference's [B, P, 3, h, w]);
+ * y: f32 [P*B, 4] = cat(y_list, 0), the per-patch fc0 logits; ens: f32 [B, 4] = fc(cat(x_list, 1)), the ensemble head
+ * Linear(P*512, P*256) + ReLU + Linear(P*256, 4) on the pooled trunk features.  Needs WSI_ARCH_RESNET18 with
+ * fc.0.* / fc.2.* in the loaded state dict.  All buffers in `mem` memory.                                        */
+WSI_API int wsi_forward_patches(wsi_ctx* ctx, const float* xs, int64_t B, int32_t P, int32_t h, int32_t w, float* y,
+                        float* ens, int mem, void* stream);
+
 /* ---- foreground mask and masked tile plan on the GPU ------------------------------------
  * wsi_find_nuclei: find_nuclei(wsi, mu_percent, mode='hsv', fill_mask=False) (utils/preprocessing.py:74-110):
  * mask = u8 {0,1}, HSV saturation of the level-2 thumbnail > mu_percent, evaluated as skimage.color.rgb2hsv does

@@ -115,3 +115,25 @@ def test_predict_wsis_mirror(golden_dir, name):
           f"(emulation {(emu['classes'] == g['classes']).mean():.5f})")
     assert err <= 1.5 * noise + 5e-3 * scale
     assert agree >= (emu["classes"] == g["classes"]).mean() - 5e-3
+
+
+def test_ensemble_head_matches_torch_fp32():
+    """wsi_forward_patches: per-patch logits equal forward_batch(CLS), and the ensemble head equals torch's fp32
+    fc(cat(pooled features)) on the engine's own pooled features (B = 11: two batch groups in the fc1 kernel)."""
+    sd = O.random_state_dict("resnet18", 9, with_fc=True)
+    net = models.resnet18()
+    net.load_state_dict(sd, strict=False)
+    net = net.cuda().eval()
+    B, P = 11, 16
+    xs = torch.randn(B, P, 3, 32, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        y, out = net(xs)
+        flat = xs.transpose(0, 1).reshape(P * B, 3, 32, 32).contiguous()
+        ctx = net.ctx
+        y_ref = ctx.forward_batch(flat, capi.HEAD_CLS)
+        f = ctx.forward_batch(flat, capi.HEAD_FEATURES)
+        feats = f.view(P, B, 512).transpose(0, 1).reshape(B, P * 512)
+        out_ref = net.fc(feats)
+    assert y.shape == (P * B, 4) and out.shape == (B, 4)
+    assert torch.equal(y, y_ref)
+    assert (out - out_ref).abs().max().item() <= 1e-4 * max(out_ref.abs().max().item(), 1.0)

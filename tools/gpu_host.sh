@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "=== e2e (new)"; timeout 1200 python -m pytest tests/test_gpu_e2e.py -m gpu -q --no-header -p no:cacheprovider -s -k "config1 or stride_sweep or full_size" > gpurun_out/pytest_new.log 2>&1; echo "exit $?"; tail -n 25 gpurun_out/pytest_new.log | cut -c1-260
+echo "=== host"; timeout 900 python -m pytest tests/test_gpu_host.py -m gpu -q --no-header -p no:cacheprovider -s > gpurun_out/pytest_host.log 2>&1; echo "exit $?"; tail -n 15 gpurun_out/pytest_host.log | cut -c1-300

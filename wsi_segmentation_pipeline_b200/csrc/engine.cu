@@ -80,6 +80,9 @@ struct wsi_ctx {
   std::vector<cudaEvent_t> event_pool;
   // scratch reused across slides
   DevBuf raster, maskbuf, canvas, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, tile_logits, scratch_f32, counts;
+  // multi-patch ensemble head `fc` (uploaded on first use after a model load)
+  DevBuf ens_w1, ens_b1, ens_w2, ens_b2;
+  bool ens_ready = false;
 };
 
 namespace wsi {
@@ -185,6 +188,7 @@ struct NetPlan {
   DevBuf in_pad;                 // [cap][ph+6][pw+8][4] bf16, zero border
   DevBuf logits;                 // SEG: f32 [cap][ph][pw][4]; CLS/REG/FEATURES: f32 [cap][out_dim]
   DevBuf hw1, hb1, hw2, hb2;     // head weights
+  DevBuf pooled;                 // CLS head: the pooled 512-vectors next to the logits (multi-patch ensemble head reads them)
   int n1 = 0, n2 = 0, out_dim = 0;
   Act* x4 = nullptr;
   double conv_flops = 0, stem_flops = 0;   // per batch of `cap` tiles (algorithmic: 2*MAC, no padding)
@@ -410,6 +414,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
       out_dim = 512;
     }
     logits.alloc((size_t)cap * out_dim * sizeof(float));
+    if (head == WSI_HEAD_CLS) pooled.alloc((size_t)cap * 512 * sizeof(float));
     steps.push_back(Step{2, ST_HEAD, nullptr, x4, nullptr});
   }
   CUDA_CHECK(cudaDeviceSynchronize());
@@ -476,8 +481,9 @@ void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
           launch_maxpool(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
       } else {
         const bool feat = (head == WSI_HEAD_FEATURES);
+        float* feat_out = feat ? logits.as<float>() : (pooled.p ? pooled.as<float>() : nullptr);
         launch_pool_head(x4->buf.as<bf16>(), cap, x4->H * x4->W, x4->C, hw1.as<float>(), hb1.as<float>(), n1, hw2.as<float>(),
-                         hb2.as<float>(), n2, feat ? logits.as<float>() : nullptr, logits.as<float>(), s, &c->lc);
+                         hb2.as<float>(), n2, feat_out, logits.as<float>(), s, &c->lc);
       }
     }
   }
@@ -852,6 +858,7 @@ int wsi_model_load(wsi_ctx* ctx, int arch, const wsi_tensor_desc* tensors, int n
   WSI_REQUIRE(arch == WSI_ARCH_RESNET18 || arch == WSI_ARCH_UNET_R18, WSI_ERR_INVALID, "unknown arch %d", arch);
   CUDA_CHECK(cudaSetDevice(ctx->device));
   ctx->plan.reset();
+  ctx->ens_ready = false;
   ctx->sd.clear();
   ctx->arch = -1;
   for (int i = 0; i < n; ++i) {
@@ -899,6 +906,55 @@ int wsi_forward_batch(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_
     launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc);
   }
   forward_common(ctx, plan, (int)n, head, out, mem, s);
+  WSI_API_END(ctx)
+}
+
+int wsi_forward_patches(wsi_ctx* ctx, const float* xs, int64_t B, int32_t P, int32_t h, int32_t w, float* y, float* ens, int mem,
+                        void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && xs && y && ens && B > 0 && P > 0 && B * P < (1 << 20), WSI_ERR_INVALID, "bad argument");
+  WSI_REQUIRE(ctx->arch == WSI_ARCH_RESNET18, WSI_ERR_UNSUPPORTED, "the multi-patch forward is resnets_shift.ResNet's (WSI_ARCH_RESNET18)");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = B * P;
+  // ensemble head weights: fc = Linear(P*512, P*256) + ReLU + Linear(P*256, 4) (resnets_shift.py:133-139)
+  const HostTensor &w1 = weight(ctx, "fc.0.weight"), &b1 = weight(ctx, "fc.0.bias"), &w2 = weight(ctx, "fc.2.weight"), &b2 = weight(ctx, "fc.2.bias");
+  WSI_REQUIRE(w1.shape.size() == 2 && w1.shape[1] == (int64_t)P * 512 && b1.numel() == w1.shape[0] && w2.shape.size() == 2 &&
+                  w2.shape[1] == w1.shape[0] && b2.numel() == w2.shape[0],
+              WSI_ERR_NOMODEL, "fc.0 / fc.2 do not match %d patches x 512 features", P);
+  const int n_hid = (int)w1.shape[0], n_out = (int)w2.shape[0];
+  NetPlan* plan = get_plan(ctx, WSI_HEAD_CLS, (int)n, h, w);
+  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
+  DevBuf tmp, hid, ens_d;
+  const float* xd = xs;
+  const size_t in_bytes = (size_t)n * 3 * h * w * sizeof(float);
+  if (mem == WSI_MEM_HOST) {
+    tmp.alloc(in_bytes);
+    CUDA_CHECK(cudaMemcpyAsync(tmp.p, xs, in_bytes, cudaMemcpyHostToDevice, s));
+    xd = tmp.as<float>();
+  }
+  {
+    StageScope scope(ctx, s, ST_GATHER, (double)n * h * w * 18.0);
+    launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc);
+  }
+  forward_common(ctx, plan, (int)n, WSI_HEAD_CLS, y, mem, s);            // trunk + avgpool + fc0 for all P*B patches
+  if (!ctx->ens_ready) {
+    upload(ctx->ens_w1, w1.data, s); upload(ctx->ens_b1, b1.data, s); upload(ctx->ens_w2, w2.data, s); upload(ctx->ens_b2, b2.data, s);
+    ctx->ens_ready = true;
+  }
+  hid.alloc((size_t)B * n_hid * sizeof(float));
+  float* ens_dst = ens;
+  if (mem == WSI_MEM_HOST) {
+    ens_d.alloc((size_t)B * n_out * sizeof(float));
+    ens_dst = ens_d.as<float>();
+  }
+  {
+    StageScope scope(ctx, s, ST_HEAD, (double)n_hid * P * 512 * 4.0);
+    launch_ensemble_head(plan->pooled.as<float>(), (int)B, P, ctx->ens_w1.as<float>(), ctx->ens_b1.as<float>(), n_hid, ctx->ens_w2.as<float>(),
+                         ctx->ens_b2.as<float>(), n_out, hid.as<float>(), ens_dst, s, &ctx->lc);
+  }
+  if (mem == WSI_MEM_HOST) CUDA_CHECK(cudaMemcpyAsync(ens, ens_dst, (size_t)B * n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
   WSI_API_END(ctx)
 }
 

@@ -608,4 +608,65 @@ void launch_window_count(const uint8_t* mask, int64_t mh, int64_t mw, const int6
   if (lc) lc->n++;
 }
 
+// Ensemble head of the multi-patch ResNet (resnets_shift.py:133-139, :213-215): features = cat over the P patches
+// of the pooled 512-vectors -> Linear(P*512, P*256) + ReLU -> Linear(P*256, 4).  The engine holds the pooled features
+// patch-major (feats[(p*B + b)*512 + c]), the reference concatenates along dim 1 (k = p*512 + c).  fp32 weights and
+// accumulation (33.6 M parameters at P = 16: the kernel streams the weight matrix once per group of <= 8 batch
+// elements — weight-bandwidth bound, 134 MB).  One warp per output neuron, fixed lane-strided summation order.
+__global__ void __launch_bounds__(256) ensemble_fc1_kernel(const float* __restrict__ feats, int B, int P, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int n_out, float* __restrict__ hid) {
+  const int K = P * 512;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (j >= n_out) return;
+  const float4* wr = reinterpret_cast<const float4*>(w + (size_t)j * K);
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    const int nb = min(8, B - b0);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+      const float4 wv = __ldg(wr + k4);
+      const int k = 4 * k4, pch = k >> 9, c = k & 511;
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) {
+        if (bb < nb) {
+          const float4 fv = __ldg(reinterpret_cast<const float4*>(feats + ((size_t)pch * B + (b0 + bb)) * 512 + c));
+          acc[bb] = fmaf(fv.x, wv.x, acc[bb]);
+          acc[bb] = fmaf(fv.y, wv.y, acc[bb]);
+          acc[bb] = fmaf(fv.z, wv.z, acc[bb]);
+          acc[bb] = fmaf(fv.w, wv.w, acc[bb]);
+        }
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) {
+      float v = acc[bb];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && bb < nb) hid[(size_t)(b0 + bb) * n_out + j] = fmaxf(v + bias[j], 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) ensemble_fc2_kernel(const float* __restrict__ hid, int n_hid, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int n_out, float* __restrict__ out) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < n_out; j += (blockDim.x >> 5)) {
+    float v = 0.f;
+    for (int k = lane; k < n_hid; k += 32) v = fmaf(hid[(size_t)b * n_hid + k], __ldg(w + (size_t)j * n_hid + k), v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[(size_t)b * n_out + j] = v + bias[j];
+  }
+}
+
+void launch_ensemble_head(const float* feats, int B, int P, const float* w1, const float* b1, int n_hid, const float* w2, const float* b2,
+                          int n_out, float* hid, float* out, cudaStream_t s, LaunchCounter* lc) {
+  if (B <= 0) return;
+  ensemble_fc1_kernel<<<(unsigned)ceil_div(n_hid, 8), 256, 0, s>>>(feats, B, P, w1, b1, n_hid, hid);
+  CUDA_CHECK(cudaGetLastError());
+  ensemble_fc2_kernel<<<(unsigned)B, 128, 0, s>>>(hid, n_hid, w2, b2, n_out, out);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n += 2;
+}
+
 }  // namespace wsi

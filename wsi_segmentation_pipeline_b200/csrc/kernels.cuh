@@ -73,4 +73,8 @@ void launch_find_nuclei(const uint8_t* rgb, int64_t row_stride, int64_t H, int64
 void launch_window_count(const uint8_t* mask, int64_t mh, int64_t mw, const int64_t* win, int64_t n, int64_t dx, int64_t dy, uint32_t* counts,
                          int64_t* sizes, cudaStream_t s, LaunchCounter* lc);
 
+// multi-patch ResNet ensemble head `fc` (resnets_shift.py:133-139, :213-215) on patch-major pooled features
+void launch_ensemble_head(const float* feats, int B, int P, const float* w1, const float* b1, int n_hid, const float* w2, const float* b2,
+                          int n_out, float* hid, float* out, cudaStream_t s, LaunchCounter* lc);
+
 }  // namespace wsi

@@ -131,18 +131,14 @@ class ResNet(_EngineBound, _TrunkParams):
         self.fc2 = nn.Sequential(nn.Linear(16 * HR_NUM_SAMPLES, 4))                           # :147-150
 
     def forward(self, xs):
-        """resnets_shift.py:189-217.  The conv trunk + per-patch head fc0 run on the engine for all
-        P*B patches at once (patch-major order, as the reference concatenates); the ensemble head
-        ``fc`` (8192 -> 4096 -> 4, 33.6 M parameters, weight-bandwidth bound at small B) is applied to
-        the engine's pooled features."""
+        """resnets_shift.py:189-217, one call into the engine (wsi_forward_patches): the conv trunk, average pool and the
+        per-patch head fc0 for all P*B patches at once (patch-major order, as the reference concatenates), then the
+        ensemble head ``fc`` (8192 -> 4096 -> 4 at P = 16: 33.6 M fp32 parameters, weight-bandwidth bound) on the pooled
+        features.  Returns (cat(y_list, 0) [P*B, 4], fc(features) [B, 4])."""
         ctx = self._engine()
         B, P = xs.shape[:2]
         flat = xs.transpose(0, 1).reshape(P * B, *xs.shape[2:]).contiguous()
-        y = ctx.forward_batch(flat, capi.HEAD_CLS)                        # [P*B, 4]
-        f = ctx.forward_batch(flat, capi.HEAD_FEATURES)                   # [P*B, 512]
-        feats = f.view(P, B, 512).transpose(0, 1).reshape(B, P * 512)     # cat(x_list, 1)
-        out = self.fc(feats)
-        return y, out
+        return ctx.forward_patches(flat, B, P)
 
     # the predict_tumorbed protocol (SURVEY 8b config-1 adapter)
     @property
