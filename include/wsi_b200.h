@@ -123,6 +123,12 @@ WSI_API int wsi_band_tiles(const int32_t* xy, int64_t n, int32_t ph, double m, i
 WSI_API int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,
                   int head, const wsi_out_desc* out, void* stream);
 
+/* ---- 4-view test-time augmentation of predict_reg / predict_breastpathq (utils/eval.py:303-334, :384-405) ------
+ * x: f32 [n, 3, h, w] normalised square tiles; out: f32 [n, dim] = mean over the views {x, x.transpose(2,3), x.flip(2),
+ * x.transpose(2,3).flip(3)} of the REG (regressor, dim 1) or CLS head, accumulated in the reference's fp32 order.    */
+WSI_API int wsi_forward_batch_tta(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_t w, int head, float* out,
+                          int mem, void* stream);
+
 /* ---- resnets_shift.ResNet.forward (resnets_shift.py:189-217): multi-patch classifier with the ensemble head ---
  * xs: f32 [P*B, 3, h, w] normalised patches, PATCH-MAJOR (xs.transpose(0, 1) of the reference's [B, P, 3, h, w]);
  * y: f32 [P*B, 4] = cat(y_list, 0), the per-patch fc0 logits; ens: f32 [B, 4] = fc(cat(x_list, 1)), the ensemble head

@@ -285,3 +285,39 @@ def run_reference_predict_wsis(model, levels: dict, mask: np.ndarray, workdir: s
         R.preprocessing.pred_to_mask = orig
     captured["tiles"] = tiles
     return captured
+
+
+def run_reference_predict_reg(model, images: "torch.Tensor", workdir: str, batch=3):
+    """Runs the reference's predict_reg (utils/eval.py:288-352: 4-view TTA of the regressor) on normalised tiles
+    ``images`` f32 [n,3,h,h] and returns its local ``preds`` list — the function only prints l1/mse, so the value is
+    read from the frame at return time with sys.settrace (no reference code is edited).  It also writes overlay PNGs
+    under ./data/cell_seg, so it is run from ``workdir``."""
+    import sys
+    R = ref_modules()
+    n = images.shape[0]
+    data = []
+    for i in range(0, n, batch):
+        im = images[i:i + batch]
+        z = torch.zeros(im.shape[0])
+        data.append((im, z, z, z, z, torch.zeros(im.shape[0])))
+    captured = {}
+
+    def tracer(frame, event, arg):
+        if event == "call" and frame.f_code.co_name == "predict_reg":
+            def local(fr, ev, a):
+                if ev == "return":
+                    captured["preds"] = np.array(fr.f_locals["preds"], np.float64)
+                return local
+            return local
+        return None
+
+    cwd = os.getcwd()
+    os.makedirs(os.path.join(workdir, "data", "cell_seg"), exist_ok=True)
+    os.chdir(workdir)
+    sys.settrace(tracer)
+    try:
+        R.eval.predict_reg(model, data, 0)
+    finally:
+        sys.settrace(None)
+        os.chdir(cwd)
+    return captured["preds"]

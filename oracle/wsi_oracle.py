@@ -344,6 +344,18 @@ def predict_wsis(sd, raster, mask, ph, pw, sh, sw, m=1.0, batch=16, tiles=None):
     return {"tiles": tiles, "canvas": canvas, "pred": pred, "classes": classes}
 
 
+def predict_reg_tta(sd, x: "torch.Tensor", arch: str = "unet_reg") -> np.ndarray:
+    """utils/eval.py:303-334 (predict_reg) / :384-405 (predict_breastpathq): the regressor evaluated on the 4 views
+    [x, x.transpose(2,3), x.flip(2), x.transpose(2,3).flip(3)], summed in that order and divided by 4."""
+    views = [x, x.transpose(2, 3), x.flip(2), x.transpose(2, 3).flip(3)]
+    acc = None
+    for v in views:
+        p = model_forward(sd, arch, v.contiguous())
+        p = p.reshape(p.shape[0], -1)
+        acc = p if acc is None else acc + p
+    return (acc / len(views)).numpy()
+
+
 # --------------------------------------------------------------------------------------------
 # random-init weights with the reference's state_dict keys (SURVEY §8d)
 #

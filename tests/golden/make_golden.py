@@ -8,6 +8,7 @@ Scenarios
   cls_small   predict_tumorbed(mode='cls'), reference resnets_shift.ResNet via the config-1 adapter
   cls_m4      same with scan_level=1 (m = 0.25: int(m*x) truncation, level-2 canvas)
   seg_small   predict_tumorbed(mode='seg'), reference ResNet encoder + restated smp decoder
+  reg_tta     predict_reg: 4-view TTA mean of the regression head (captured from the function's frame)
   wsis_l2/l1  predict_wsis up to the argmax (scan_level 2: resize is the identity; scan_level 1: cv2.resize 4x down)
   resnet_fwd  resnets_shift.ResNet.forward (multi-patch) on a [2,16,3,64,64] batch
   normalise   standard_augmentor(True) on a PIL tile
@@ -127,6 +128,19 @@ def predict_wsis(name, ih, iw, ph, pw, sh, sw, scan_level, seed):
     print(name, "tiles", len(r["tiles"]), "pred", pred.shape, "classes hist", np.bincount(np.argmax(pred, 0).ravel(), minlength=4))
 
 
+def reg_tta():
+    """predict_reg (utils/eval.py:288-352): 4-view TTA mean of the Regressor head, 7 synthetic 96x96 tiles."""
+    sd = O.random_state_dict("unet", 8)
+    model = H.UnetAdapter(sd)
+    raster = synth.synth_slide(300, 400, 31)
+    tiles = [(3, 5), (100, 20), (200, 60), (290, 150), (17, 190), (120, 101), (250, 7)]
+    x = O.gather_tiles(raster, tiles, 96, 96)
+    with tempfile.TemporaryDirectory() as td:
+        preds = H.run_reference_predict_reg(model, x, td, batch=3)
+    np.savez_compressed(os.path.join(OUT, "reg_tta.npz"), tiles=np.array(tiles, np.int32), preds=preds.astype(np.float32), seed=np.array(8))
+    print("reg_tta preds", preds)
+
+
 def resnet_fwd():
     sd = O.random_state_dict("resnet18", 3, with_fc=True)
     net = H.make_reference_resnet(sd)
@@ -156,5 +170,6 @@ if __name__ == "__main__":
     predict("cls_small", "resnet18_cls", 352, 416, 64, 64, 32, 32, "cls")
     predict("cls_m4", "resnet18_cls", 640, 768, 128, 128, 64, 64, "cls", scan_level=1, seed=1)
     predict("seg_small", "unet_seg", 160, 192, 64, 64, 32, 32, "seg", seed=2)
+    reg_tta()
     predict_wsis("wsis_l2", 160, 192, 64, 64, 32, 32, 2, 4)
     predict_wsis("wsis_l1", 256, 320, 64, 64, 32, 32, 1, 5)

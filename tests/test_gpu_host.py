@@ -137,3 +137,32 @@ def test_ensemble_head_matches_torch_fp32():
     assert y.shape == (P * B, 4) and out.shape == (B, 4)
     assert torch.equal(y, y_ref)
     assert (out - out_ref).abs().max().item() <= 1e-4 * max(out_ref.abs().max().item(), 1.0)
+
+
+def test_predict_reg_tta_mirror(golden_dir):
+    """BASELINE configs[3] / SURVEY 8f rank 3: predict_reg's 4-view TTA of the regression head (utils/eval.py:288-352)
+    through wsi_forward_batch_tta — views folded into the operand pack kernel, mean accumulated on the device in the
+    reference's order — against the reference's own `preds` (golden) and the bf16-emulating oracle."""
+    g = np.load(os.path.join(golden_dir, "reg_tta.npz"))
+    sd = O.random_state_dict("unet", int(g["seed"]))
+    net = models.unet_resnet18()
+    net.load_state_dict(sd, strict=False)
+    net = net.cuda().eval()
+    x = O.gather_tiles(synth.synth_slide(300, 400, 31), [tuple(t) for t in g["tiles"]], 96, 96)
+    got = ev.predict_reg(net, [(x[:3],) + (None,) * 5, (x[3:],) + (None,) * 5], 0)
+    assert got.shape == g["preds"].shape
+    with O.bf16_emulation():
+        emu = O.predict_reg_tta(sd, x).ravel()
+    noise = np.abs(emu - g["preds"]).max()
+    err = np.abs(got - g["preds"]).max()
+    print(f"reg tta: err vs reference {err:.3e} (bf16 emulation {noise:.3e}), vs emulation {np.abs(got - emu).max():.3e}")
+    assert err <= 1.5 * noise + 2e-3
+    # each view really is evaluated: the TTA mean differs from the single-view prediction, and equals the mean of the
+    # four single-view engine calls on torch-built views
+    ctx = net.ctx
+    xc = x.cuda()
+    views = [xc, xc.transpose(2, 3), xc.flip(2), xc.transpose(2, 3).flip(3)]
+    single = [ctx.forward_batch(v.contiguous(), capi.HEAD_REG).view(-1) for v in views]
+    ref_mean = (((single[0] + single[1]) + single[2]) + single[3]) / 4
+    np.testing.assert_array_equal(got, ref_mean.cpu().numpy())
+    assert np.abs(got - single[0].cpu().numpy()).max() > 0

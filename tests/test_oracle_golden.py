@@ -94,6 +94,14 @@ def test_predict_wsis_matches_reference(golden_dir, name):
     assert (r["classes"] == g["classes"]).mean() >= 0.999
 
 
+def test_predict_reg_tta_matches_reference(golden_dir):
+    """predict_reg (utils/eval.py:288-352): the oracle's 4-view TTA mean equals the reference's `preds`."""
+    g = _load(golden_dir, "reg_tta")
+    sd = O.random_state_dict("unet", int(g["seed"]))
+    x = O.gather_tiles(synth.synth_slide(300, 400, 31), [tuple(t) for t in g["tiles"]], 96, 96)
+    np.testing.assert_allclose(O.predict_reg_tta(sd, x).ravel(), g["preds"], rtol=0, atol=1e-6)
+
+
 def test_synth_checksum_is_stable():
     s = synth.synth_slide(2048, 2048, 1234, y0=100, y1=164)
     assert s.shape == (64, 2048, 3)

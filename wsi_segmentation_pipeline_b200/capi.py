@@ -30,6 +30,7 @@ SYMBOLS = (
     "wsi_synth_slide", "wsi_debug_conv", "wsi_debug_gather", "wsi_debug_stem", "wsi_debug_maxpool",
     "wsi_stage_stats", "wsi_stage_reset", "wsi_resize_argmax",
     "wsi_find_nuclei", "wsi_plan_tiles_gpu", "wsi_forward_patches",
+    "wsi_forward_batch_tta",
 )
 
 
@@ -95,6 +96,7 @@ def lib() -> C.CDLL:
         "wsi_stage_stats": (C.c_int, [vp, C.c_char_p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)]),
         "wsi_stage_reset": (C.c_int, [vp]),
         "wsi_resize_argmax": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, vp, C.c_int, vp]),
+        "wsi_forward_batch_tta": (C.c_int, [vp, vp, i64, i32, i32, C.c_int, vp, C.c_int, vp]),
         "wsi_forward_patches": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp, C.c_int, vp]),
         "wsi_find_nuclei": (C.c_int, [vp, vp, i64, C.c_int, i64, i64, dbl, vp, C.c_int, vp]),
         "wsi_plan_tiles_gpu": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, C.c_int, i64, i64, dbl, C.POINTER(C.POINTER(i32)),
@@ -375,6 +377,16 @@ class Context:
         _check(self._lib.wsi_resize_argmax(self._h, C.c_void_p(canvas.data_ptr()), H, W, int(H2), int(W2), C.c_void_p(classes.data_ptr()),
                                            C.c_void_p(pred.data_ptr()) if want_pred else None, mem, _stream_ptr(stream)), self._h)
         return classes, pred
+
+    def forward_batch_tta(self, x, head: int, stream=None):
+        """Mean of the REG / CLS head over the 4 TTA views of predict_reg (utils/eval.py:303-334).  x: f32 [n,3,h,h]."""
+        import torch
+        x = x.contiguous().float()
+        n, _, h, w = x.shape
+        y = torch.empty((n, 1 if head == HEAD_REG else 4), dtype=torch.float32, device=x.device)
+        _check(self._lib.wsi_forward_batch_tta(self._h, C.c_void_p(x.data_ptr()), n, h, w, int(head), C.c_void_p(y.data_ptr()),
+                                               MEM_DEVICE if x.is_cuda else MEM_HOST, _stream_ptr(stream)), self._h)
+        return y
 
     def forward_patches(self, xs_patch_major, B: int, P: int, stream=None):
         """resnets_shift.ResNet.forward (:189-217).  xs_patch_major: f32 [P*B,3,h,w] (torch CPU or CUDA).  Returns

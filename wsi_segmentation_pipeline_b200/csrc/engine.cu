@@ -909,6 +909,43 @@ int wsi_forward_batch(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_
   WSI_API_END(ctx)
 }
 
+int wsi_forward_batch_tta(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_t w, int head, float* out, int mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && x && out && n > 0 && n < (1 << 20), WSI_ERR_INVALID, "bad argument");
+  WSI_REQUIRE(head == WSI_HEAD_REG || head == WSI_HEAD_CLS, WSI_ERR_UNSUPPORTED, "TTA averages a per-tile vector head (CLS or REG)");
+  WSI_REQUIRE(h == w, WSI_ERR_UNSUPPORTED, "TTA views transpose the tile: %dx%d is not square", h, w);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  NetPlan* plan = get_plan(ctx, head, (int)n, h, w);
+  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
+  const float* xd = x;
+  const size_t in_bytes = (size_t)n * 3 * h * w * sizeof(float);
+  DevBuf tmp, acc;
+  if (mem == WSI_MEM_HOST) {
+    tmp.alloc(in_bytes);
+    CUDA_CHECK(cudaMemcpyAsync(tmp.p, x, in_bytes, cudaMemcpyHostToDevice, s));
+    xd = tmp.as<float>();
+  }
+  const int64_t out_elems = n * plan->out_dim;
+  float* dst = out;
+  if (mem == WSI_MEM_HOST) {
+    acc.alloc((size_t)out_elems * sizeof(float));
+    dst = acc.as<float>();
+  }
+  for (int view = 0; view < 4; ++view) {                                 // utils/eval.py:305-318 / :386-399
+    {
+      StageScope scope(ctx, s, ST_GATHER, (double)n * h * w * 18.0);
+      launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc, view);
+    }
+    plan->run(ctx, s);
+    launch_tta_accumulate(dst, plan->logits.as<float>(), out_elems, view == 0, view == 3 ? 4.f : 0.f, s, &ctx->lc);
+  }
+  if (mem == WSI_MEM_HOST) CUDA_CHECK(cudaMemcpyAsync(out, dst, (size_t)out_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+  check_device_flag(ctx, s);
+  resolve_spans(ctx);
+  WSI_API_END(ctx)
+}
+
 int wsi_forward_patches(wsi_ctx* ctx, const float* xs, int64_t B, int32_t P, int32_t h, int32_t w, float* y, float* ens, int mem,
                         void* stream) {
   WSI_API_BEGIN

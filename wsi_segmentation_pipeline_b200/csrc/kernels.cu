@@ -62,15 +62,23 @@ void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const i
   if (lc) lc->n++;
 }
 
-__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ x, int h, int w, bf16* __restrict__ padded) {
+// view: the test-time-augmentation views of predict_reg / predict_breastpathq (utils/eval.py:305-310, square tiles):
+//   0 image, 1 image.transpose(2, 3), 2 image.flip(2), 3 image.transpose(2, 3).flip(3) — folded into the read address
+__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ x, int h, int w, int view, bf16* __restrict__ padded) {
   const int t = blockIdx.x / h, r = blockIdx.x % h;
   const int64_t plane = (int64_t)h * w;
-  const float* src = x + (int64_t)t * 3 * plane + (int64_t)r * w;
+  const float* img = x + (int64_t)t * 3 * plane;
   const int64_t pitch = (int64_t)(w + 8) * 4;
   bf16* dst = padded + ((int64_t)t * (h + 6) + (r + 3)) * pitch + 3 * 4;
   for (int c = threadIdx.x; c < w; c += blockDim.x) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(src[c], src[plane + c]);
-    __nv_bfloat162 b = __floats2bfloat162_rn(src[2 * plane + c], 0.f);
+    // output pixel (r, c) <- source pixel (sy, sx)
+    int sy = r, sx = c;
+    if (view == 1) { sy = c; sx = r; }
+    else if (view == 2) { sy = h - 1 - r; }
+    else if (view == 3) { sy = w - 1 - c; sx = r; }
+    const float* src = img + (int64_t)sy * w + sx;
+    __nv_bfloat162 a = __floats2bfloat162_rn(src[0], src[plane]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(src[2 * plane], 0.f);
     uint2 o;
     o.x = *reinterpret_cast<uint32_t*>(&a);
     o.y = *reinterpret_cast<uint32_t*>(&b);
@@ -78,9 +86,27 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict_
   }
 }
 
-void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc) {
+void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc, int view) {
   if (n <= 0) return;
-  pack_nchw_kernel<<<(unsigned)((int64_t)n * h), 256, 0, s>>>(x, h, w, padded);
+  WSI_REQUIRE(view == 0 || h == w, WSI_ERR_UNSUPPORTED, "TTA views need square tiles (%dx%d)", h, w);
+  pack_nchw_kernel<<<(unsigned)((int64_t)n * h), 256, 0, s>>>(x, h, w, view, padded);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// TTA mean (utils/eval.py:311-334): acc = v0; acc += v1; acc += v2; acc += v3; out = acc / 4 — same fp32 order
+__global__ void __launch_bounds__(256) tta_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ v, int64_t n, int first,
+                                                              float final_div) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float a = first ? v[i] : acc[i] + v[i];
+    if (final_div != 0.f) a = a / final_div;
+    acc[i] = a;
+  }
+}
+
+void launch_tta_accumulate(float* acc, const float* v, int64_t n, bool first, float final_div, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return;
+  tta_accumulate_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 1024), 256, 0, s>>>(acc, v, n, first ? 1 : 0, final_div);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }

@@ -33,7 +33,9 @@ void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const i
                    int ph, int pw, const float* lut_dev /*f32 [3][256]*/, bf16* padded_or_null, float* norm_out_or_null,
                    cudaStream_t s, LaunchCounter* lc);
 // normalised f32 NCHW -> padded bf16 tiles (nn.Module shim forward)
-void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc);
+void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc, int view = 0);
+// TTA mean over views in the reference's fp32 order (utils/eval.py:311-334)
+void launch_tta_accumulate(float* acc, const float* v, int64_t n, bool first, float final_div, cudaStream_t s, LaunchCounter* lc);
 // 3x3/s2/p1 max pool, NHWC bf16, C multiple of 8
 void launch_maxpool(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc);
 // global average pool + up to two Linear layers: feat[512] -> (W1,b1)[n1] (-> ReLU -> (W2,b2)[n2])

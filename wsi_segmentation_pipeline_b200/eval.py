@@ -124,6 +124,26 @@ def predict_wsis(model, dataset, ep, args=None):
     return outputs
 
 
+def predict_reg(model, dataset, ep, clamp: bool = False) -> np.ndarray:
+    """utils/eval.py:288-352 (predict_reg) and, with ``clamp``, the per-image arithmetic of predict_breastpathq
+    (:384-409): the regression head averaged over the 4 test-time-augmentation views of every (square) tile, one
+    ``wsi_forward_batch_tta`` call per batch.  ``dataset`` yields tuples whose first element is the normalised image
+    batch f32 [n,3,h,h].  Returns the predictions f32 [N]; the reference's overlay PNGs and printed l1/mse are left to
+    the caller."""
+    ctx = _engine_of(model)
+    if hasattr(model, "eval"):
+        model.eval()
+    preds = []
+    for batch in dataset:
+        image = batch[0] if isinstance(batch, (tuple, list)) else batch
+        p = ctx.forward_batch_tta(image.cuda() if hasattr(image, "cuda") else image, capi.HEAD_REG).view(-1)
+        preds.append(p.cpu().numpy())
+    if hasattr(model, "train"):
+        model.train()
+    out = np.concatenate(preds) if preds else np.zeros((0,), np.float32)
+    return np.minimum(np.maximum(out, 0.0), 1.0) if clamp else out
+
+
 def band_plan(ih: int, ph: int, sh: int, tiles: np.ndarray, m: float, world: int):
     """Per rank: (own0, own1, row0, row1, tile indices).  SURVEY 8e: boundaries on the tile grid;
     a rank evaluates every tile intersecting its band, so nothing is exchanged during compute."""
