@@ -178,6 +178,9 @@ WSI_API int wsi_synth_slide(wsi_ctx* ctx, int64_t ih, int64_t iw, uint32_t seed,
  * w f32 OIHW (host), scale/bias f32 [cout] (host, may be NULL = 1/0), res bf16 NHWC or NULL,
  * y bf16 NHWC [n,oh,ow,cout] (device).  up2: x is nearest-upsampled x2 and concatenated with
  * `skip` (bf16 NHWC [n,2h,2w,cskip] or NULL) before a 3x3/s1 conv (smp DecoderBlock).           */
+/* hardware probe (dev tool, tools/umma_shift_probe.py): one MMA on a shifted window of a TMA-written SWIZZLE_128B tile */
+WSI_API int wsi_debug_umma_shift(wsi_ctx* ctx, const void* A_dev, const void* B_dev, int r, int s, int pitch,
+                         int use_base_offset, float* D_dev, void* stream);
 WSI_API int wsi_debug_conv(wsi_ctx* ctx, const void* x, int n, int h, int w, int cin,
                    const float* wt, int cout, int ksize, int stride, int pad,
                    const float* scale, const float* bias, const void* res, int relu,

@@ -116,6 +116,11 @@ CONV_CASES = [
     (2, 2, 2, 512, 512, 3, 1, 1, False, True),       # 2x2 feature map (64 px tiles at /32)
     (5, 8, 8, 256, 128, 3, 1, 1, True, True),        # CTA-pair kernel, odd M-tile count (out-of-range tail tile)
     (9, 16, 16, 128, 128, 3, 1, 1, True, True),      # CTA-pair kernel, BLOCK_N 128
+    # halo-resident pair kernel (3x3/s1, C % 64 == 0, Cout % 128 == 0, H >= 16, W >= 8): 16x8 pixel tiles
+    (3, 40, 20, 128, 128, 3, 1, 1, True, True),      # ragged in both directions (40 = 2.5 tiles, 20 = 2.5 tiles)
+    (1, 16, 24, 128, 128, 3, 1, 1, False, True),     # 3 tiles: odd count, out-of-range peer tile
+    (2, 32, 32, 256, 256, 3, 1, 1, True, False),     # BLOCK_N 256, 4 K chunks, no ReLU
+    (2, 17, 9, 64, 512, 3, 1, 1, False, True),       # one K chunk, two N tiles, one-pixel ragged edges
     (20, 48, 48, 64, 256, 3, 1, 1, True, True),      # BLOCK_N 256 (enough M tiles for every SM), residual
     (6, 64, 64, 256, 512, 3, 1, 1, False, True),     # BLOCK_N 256, two N tiles, K = 2304
     # row-tile / row-stream kernels (cout 16/32/64, <=64 channels per operand): halo-resident taps, cp.async producers

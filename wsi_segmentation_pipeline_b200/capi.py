@@ -30,7 +30,7 @@ SYMBOLS = (
     "wsi_synth_slide", "wsi_debug_conv", "wsi_debug_gather", "wsi_debug_stem", "wsi_debug_maxpool",
     "wsi_stage_stats", "wsi_stage_reset", "wsi_resize_argmax",
     "wsi_find_nuclei", "wsi_plan_tiles_gpu", "wsi_forward_patches",
-    "wsi_forward_batch_tta",
+    "wsi_forward_batch_tta", "wsi_debug_umma_shift",
 )
 
 
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         "wsi_stage_stats": (C.c_int, [vp, C.c_char_p, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)]),
         "wsi_stage_reset": (C.c_int, [vp]),
         "wsi_resize_argmax": (C.c_int, [vp, vp, i64, i64, i64, i64, vp, vp, C.c_int, vp]),
+        "wsi_debug_umma_shift": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "wsi_forward_batch_tta": (C.c_int, [vp, vp, i64, i32, i32, C.c_int, vp, C.c_int, vp]),
         "wsi_forward_patches": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp, C.c_int, vp]),
         "wsi_find_nuclei": (C.c_int, [vp, vp, i64, C.c_int, i64, i64, dbl, vp, C.c_int, vp]),

@@ -1,0 +1,273 @@
+// conv_halo.cuh — halo-resident CTA-pair implicit GEMM for 3x3 / stride-1 convolutions on >= 64-channel NHWC tensors.
+//
+// Measured (profiles/r01_notes.md): the 128/256-channel layers of the TMA implicit-GEMM kernels are bound by the
+// L2 -> SM fill of their A tiles — unique per CTA, ~25 B/clk/SM whatever the layout — because every input pixel is
+// loaded once per filter tap (9x).  Probe (tools/umma_shift_probe.py): the tensor core applies the 128-byte swizzle
+// to ABSOLUTE shared-memory address bits, so a K-major SWIZZLE_128B operand may start at any 128-byte row of a
+// TMA-written tile and its 8-row groups may be any multiple of 128 bytes apart (no descriptor base_offset needed).
+// Hence:
+//   * the M tile is 16 rows x 8 columns of output pixels of one image; per 64-channel K chunk ONE TMA box
+//     {64 ch, 10 px, 18 rows} brings the 18 x 10 halo (23 KB; out-of-bounds = the conv zero padding);
+//   * the A operand of tap (r, s) is that tile read from row r * 10 + s on, 8-pixel groups 10 rows apart
+//     (SBO = 1280 B): nine descriptor offsets instead of nine 16 KB loads — per-CTA-unique traffic drops 6.4x;
+//   * weights stream through the stage ring one tap at a time ([Cout][K] with K = (chunk, tap, 64 ch)); they are
+//     shared by all CTAs (L2 broadcast) and, as in conv_pair.cuh, each CTA of a pair stages only half of the rows;
+//   * everything else (cta_group::2 MMAs with M = 256, multicast commits, 16-arrival tmem_empty, the epilogue) is
+//     the protocol of conv_pair.cuh.
+#pragma once
+#include "conv_pair.cuh"
+
+namespace wsi {
+
+constexpr int kHaloW = 10, kHaloH = 18, kHaloTileW = 8, kHaloTileH = 16;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;                      // 23 040
+constexpr int kHaloBuf = (kHaloBytes + 1023) / 1024 * 1024;            // 23 552: buffers stay 1024-byte aligned
+
+template <int BN>
+struct HaloSmem {
+  static constexpr int kBBytes = (BN / 2) * 128;                        // this CTA's half of one tap's weight rows
+  static constexpr int kStagesWanted = (150 * 1024) / kBBytes;
+  static constexpr int kStages = kStagesWanted > 12 ? 12 : kStagesWanted;
+  static constexpr int kRing = 2 * kHaloBuf + kStages * kBBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kScaleBytes = 2 * 512 * (int)sizeof(float);
+  static constexpr int kTotal = 1024 + kRing + kBarBytes + kScaleBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static_assert(kTmemCols <= 512, "TMEM");
+  static_assert(kBBytes % 1024 == 0, "swizzle atom alignment");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
+  using S = HaloSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* halo_base = smem;                            // 2 halo buffers
+  uint8_t* stage_base = smem + 2 * kHaloBuf;            // weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kRing);
+  uint64_t* full = bars;                               // [kStages]  leader only: one tap's weight rows of both CTAs landed
+  uint64_t* empty = bars + S::kStages;                 // [kStages]  per CTA
+  uint64_t* a_full = bars + 2 * S::kStages;            // [2]        leader only: the halo tiles of both CTAs landed
+  uint64_t* a_empty = bars + 2 * S::kStages + 2;       // [2]        per CTA
+  uint64_t* tmem_full = bars + 2 * S::kStages + 4;     // [2]        per CTA
+  uint64_t* tmem_empty = bars + 2 * S::kStages + 6;    // [2]        leader only (16 warp arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 8);
+  float* s_scale = reinterpret_cast<float*>(smem + S::kRing + S::kBarBytes);
+  float* s_bias = s_scale + 512;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kc = p.num_kb;                         // 64-channel K chunks
+  const uint32_t rank = pptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) { s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i]; }
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < S::kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], 1);
+      ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 16);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&bmap);
+    ptx::prefetch_tmap(&amap);
+  }
+  if (warp == 1) pptx::tmem_alloc_pair(tmem_holder, S::kTmemCols);
+  ptx::tc_fence_before();
+  pptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int tiles_m = p.tiles_n * p.tiles_h * p.tiles_w;
+  const int pairs_m = (tiles_m + 1) >> 1;
+  const int total_tiles = pairs_m * p.tiles_co;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (ptx::elect_one()) {
+      int stage = 0, abuf = 0;
+      uint32_t phase = 0, aphase = 0;
+      const uint32_t full0 = pptx::mapa(ptx::smem_u32(&full[0]), 0);
+      const uint32_t afull0 = pptx::mapa(ptx::smem_u32(&a_full[0]), 0);
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        int r = tile;
+        const int ct = r % p.tiles_co; r /= p.tiles_co;
+        int mt = 2 * r + (int)rank;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h; mt /= p.tiles_h;
+        const int tn = mt;                                   // == tiles_n for the out-of-range tail tile
+        const int x0 = tw * kHaloTileW - 1, y0 = th * kHaloTileH - 1;
+        const int co0 = ct * BN + (int)rank * (BN / 2);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          ptx::mbar_wait(&a_empty[abuf], aphase ^ 1u, p.error_flag, 61);
+          if (rank == 0) ptx::mbar_expect_tx(&a_full[abuf], 2u * (uint32_t)kHaloBytes);
+          pptx::tma_load_4d_pair(halo_base + abuf * kHaloBuf, &amap, afull0 + (uint32_t)(abuf * 8), kc * 64, x0, y0, tn);
+          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+          for (int tap = 0; tap < 9; ++tap) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 62);
+            if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2u * (uint32_t)S::kBBytes);
+            pptx::tma_load_2d_pair(stage_base + stage * S::kBBytes, &bmap, full0 + (uint32_t)(stage * 8), (kc * 9 + tap) * 64, co0);
+            if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader only) ================================
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      // A: SWIZZLE_128B K-major, 8-pixel groups one halo row (10 px = 1280 B) apart; the tap offset is added below
+      uint64_t adesc0 = 0;
+      adesc0 |= (uint64_t)1 << 16;
+      adesc0 |= (uint64_t)((kHaloW * 128) >> 4) << 32;
+      adesc0 |= (uint64_t)1 << 46;
+      adesc0 |= (uint64_t)2 << 61;
+      int stage = 0, abuf = 0;
+      uint32_t phase = 0, aphase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        pptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 63);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          pptx::mbar_wait_cluster(&a_full[abuf], aphase, p.error_flag, 65);
+          const uint32_t a_addr = ptx::smem_u32(halo_base + abuf * kHaloBuf);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            pptx::mbar_wait_cluster(&full[stage], phase, p.error_flag, 66);
+            ptx::tc_fence_after();
+            const int tr = tap / 3, ts = tap - 3 * tr;
+            const uint64_t adesc = adesc0 | (uint64_t)(((a_addr + (uint32_t)((tr * kHaloW + ts) * 128)) & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = make_kmajor_desc<64>(ptx::smem_u32(stage_base + stage * S::kBBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              pptx::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kc | tap | k) != 0));
+            pptx::umma_commit_pair(&empty[stage]);
+            if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+          }
+          pptx::umma_commit_pair(&a_empty[abuf]);       // the halo buffers of both CTAs are free when these MMAs retire
+          if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
+        }
+        pptx::umma_commit_pair(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ================================ epilogue (8 warps, both CTAs) ===========================
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    constexpr int CH = BN / 2;
+    constexpr int STEP = 32;
+    const int c_lo = hsel * CH;
+    const uint32_t tmem_empty0 = pptx::mapa(ptx::smem_u32(&tmem_empty[0]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      int r = tile;
+      const int ct = r % p.tiles_co; r /= p.tiles_co;
+      constexpr int par = 0;
+      int mt = 2 * r + (int)rank;
+      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int th = mt % p.tiles_h; mt /= p.tiles_h;
+      const int tn = mt;
+      const int co0 = ct * BN;
+      const int wl = row % p.bw;
+      const int hl = (row / p.bw) % p.bh;
+      const int nl = row / (p.bw * p.bh);
+      const int n = tn * p.bn + nl, a = th * p.bh + hl, b = tw * p.bw + wl;
+      const bool valid = (n < p.N) && (a < p.A_h) && (b < p.A_w);
+      const int oh = p.sigma * a + (par >> 1), ow = p.sigma * b + (par & 1);
+      const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
+      const size_t off0 = pix * p.Cout + co0 + c_lo;
+      const bool has_res = (p.res != nullptr) && valid;
+
+      uint4 rcur[STEP / 8], rnext[STEP / 8];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < STEP / 8; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0) + j);
+      }
+
+      ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 64);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c_lo);
+#pragma unroll 1
+      for (int c = 0; c < CH; c += STEP) {
+        uint32_t v[STEP];
+#pragma unroll
+        for (int j = 0; j < STEP; j += 16) ptx::tmem_ld16(t_row + (uint32_t)(c + j), *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
+        if (has_res && c + STEP < CH) {
+#pragma unroll
+          for (int j = 0; j < STEP / 8; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0 + c + STEP) + j);
+        }
+        ptx::tmem_ld_wait();
+        float y[STEP];
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + co0 + c_lo + c);
+        const float4* bi4 = reinterpret_cast<const float4*>(s_bias + co0 + c_lo + c);
+#pragma unroll
+        for (int j = 0; j < STEP / 4; ++j) {
+          const float4 sc = sc4[j], bb = bi4[j];
+          y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, bb.x);
+          y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, bb.y);
+          y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, bb.z);
+          y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, bb.w);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < STEP / 8; ++j) {
+            const uint32_t w[4] = {rcur[j].x, rcur[j].y, rcur[j].z, rcur[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              y[8 * j + 2 * t + 0] += __uint_as_float(w[t] << 16);
+              y[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < STEP / 8; ++j) rcur[j] = rnext[j];
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < STEP; ++j) y[j] = fmaxf(y[j], 0.f);
+        }
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c);
+#pragma unroll
+          for (int j = 0; j < STEP / 8; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+              w[t] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      // this warp's TMEM reads are done: one arrival per warp on the leader's barrier
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pptx::mbar_arrive_remote(tmem_empty0 + (uint32_t)(acc * 8));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  // neither CTA may exit (or free TMEM) while the other can still signal its barriers or read its smem
+  ptx::tc_fence_before();
+  pptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    pptx::tmem_dealloc_pair(tmem_base, S::kTmemCols);
+  }
+}
+
+}  // namespace wsi

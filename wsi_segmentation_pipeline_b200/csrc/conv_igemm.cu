@@ -1,6 +1,7 @@
 // conv_igemm.cu — host side of the tcgen05 implicit-GEMM convolution (see conv_igemm.cuh).
 #include "conv_igemm.cuh"
 #include "conv_pair.cuh"
+#include "conv_halo.cuh"
 #include "conv_upstream.cuh"
 
 #include <algorithm>
@@ -146,6 +147,11 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
               WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC tensors and writes NHWC or plain planar ones");
   out_planar_ = (out_layout == LAYOUT_PLANAR);
   for (auto& q : parts) WSI_REQUIRE(q.t.layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC operands");
+  halo_ = false;
+  if (halo_eligible(parts, spec, out_layout, head_out != nullptr, num_sms)) {
+    build_halo(parts[0], spec, w_oihw, scale, bias, residual, out, error_flag, num_sms);
+    return;
+  }
   bool any_up = false;
   for (auto& q : parts) any_up |= q.up2;
   const int k = spec.ksize;
@@ -410,6 +416,83 @@ static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams
   CUDA_CHECK(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------
+// halo-resident pair kernel (conv_halo.cuh): 3x3 / s1 convs on >= 64-channel NHWC tensors, Cout % 128 == 0
+// ---------------------------------------------------------------------------------------------
+bool ConvOp::halo_eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, int out_layout, bool head, int num_sms) {
+  if (getenv("WSI_NO_HALO") != nullptr || num_sms < 2 || head || out_layout != LAYOUT_NHWC) return false;
+  if (spec.ksize != 3 || spec.stride != 1 || spec.pad != 1 || parts.size() != 1 || parts[0].up2) return false;
+  const TensorView& t = parts[0].t;
+  // 16 x 8 pixel tiles: smaller maps waste most of the tile, the TMA kernel keeps those
+  return t.layout == LAYOUT_NHWC && t.C % 64 == 0 && t.C >= 64 && spec.cout % 128 == 0 && t.H >= kHaloTileH && t.W >= kHaloTileW;
+}
+
+void ConvOp::build_halo(const ConvInputPart& part, const ConvSpec& spec, const float* w_oihw, const float* scale, const float* bias,
+                        const void* residual, void* out, int* error_flag, int num_sms) {
+  const TensorView& t = part.t;
+  const int N = t.N, H = t.H, W = t.W, C = t.C, cout = spec.cout;
+  halo_ = true;
+  pair_ = false; resb_ = false; out_planar_ = false;
+  block_n_ = (cout % 256 == 0) ? 256 : 128;
+  block_k_ = 64;
+  ConvParams& p = p_;
+  p = ConvParams{};
+  p.N = N; p.OH = H; p.OW = W; p.Cout = cout;
+  p.sigma = 1; p.num_parity = 1; p.A_h = H; p.A_w = W;
+  p.bw = kHaloTileW; p.bh = kHaloTileH; p.bn = 1;
+  p.tiles_w = (int)ceil_div(W, kHaloTileW);
+  p.tiles_h = (int)ceil_div(H, kHaloTileH);
+  p.tiles_n = N;
+  p.tiles_co = cout / block_n_;
+  p.num_kb = C / 64;                                  // 64-channel K chunks (9 taps each)
+  p.relu = spec.relu ? 1 : 0;
+  p.res = static_cast<const bf16*>(residual);
+  p.out = static_cast<bf16*>(out);
+  p.error_flag = error_flag;
+  // weights [Cout][K], K = (chunk, tap, 64 channels): the order in which the kernel walks the resident halo tile
+  const int K = C * 9;
+  std::vector<uint16_t> wp((size_t)cout * K);
+  for (int co = 0; co < cout; ++co)
+    for (int kc = 0; kc < C / 64; ++kc)
+      for (int tap = 0; tap < 9; ++tap)
+        for (int j = 0; j < 64; ++j)
+          wp[(size_t)co * K + ((size_t)kc * 9 + tap) * 64 + j] =
+              f32_to_bf16_bits(w_oihw[(((size_t)co * C + kc * 64 + j) * 3 + tap / 3) * 3 + tap % 3]);
+  upload(w_, wp);
+  std::vector<float> sc(cout, 1.f), bi(cout, 0.f);
+  if (scale) sc.assign(scale, scale + cout);
+  if (bias) bi.assign(bias, bias + cout);
+  upload(scale_, sc); upload(bias_, bi);
+  p.scale = scale_.as<float>(); p.bias = bias_.as<float>();
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t st[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    const uint32_t box[4] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, 1};
+    encode4(&amaps_.m[0], t.ptr, dims, st, box, 64);
+    for (int i = 1; i < kMaxAMaps; ++i) amaps_.m[i] = amaps_.m[0];
+  }
+  encode2(&bmap_, w_.p, (uint64_t)K, (uint64_t)cout, (uint64_t)K * 2, 64, (uint32_t)(block_n_ / 2), 64);
+  const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  const long long pair_tiles = (tiles_m + 1) / 2 * p.tiles_co;
+  WSI_REQUIRE(pair_tiles < (1LL << 30), WSI_ERR_UNSUPPORTED, "conv: too many tiles");
+  grid_ = 2 * (int)std::min<long long>(pair_tiles, num_sms / 2);
+  flops_ = 2.0 * N * H * W * (double)cout * C * 9;
+  CUDA_CHECK(cudaStreamSynchronize(0));
+}
+
+template <int BN>
+static void launch_halo(const CUtensorMap& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
+  using S = HaloSmem<BN>;
+  static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  conv_halo_pair_kernel<BN><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);   // __cluster_dims__(2, 1, 1)
+  CUDA_CHECK(cudaGetLastError());
+}
+
 template <int BN>
 static void launch_pair(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
   using S = PairSmem<BN>;
@@ -428,6 +511,12 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (upstream_) { upstream_->launch(stream, lc); return; }
   if (row_) { row_->launch(stream, lc); return; }
   if (stem_) { stem_->launch(stream, lc); return; }
+  if (halo_) {
+    if (block_n_ == 256) launch_halo<256>(amaps_.m[0], bmap_, p_, grid_, stream);
+    else launch_halo<128>(amaps_.m[0], bmap_, p_, grid_, stream);
+    if (lc) lc->n++;
+    return;
+  }
   if (pair_) {
     if (block_n_ == 256) launch_pair<256>(amaps_, bmap_, p_, grid_, stream);
     else launch_pair<128>(amaps_, bmap_, p_, grid_, stream);
@@ -447,6 +536,83 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   WSI_CASE(128, 16) WSI_CASE(64, 16) WSI_CASE(32, 16) WSI_CASE(16, 16)
 #undef WSI_CASE
   WSI_THROW(WSI_ERR_UNSUPPORTED, "conv: no kernel instance for BLOCK_N=%d BLOCK_K=%d", block_n_, block_k_);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hardware probe (dev tool, tools/umma_shift_probe.py): can a SWIZZLE_128B K-major A operand start at an arbitrary
+// 128-byte row of a TMA-written tile?  A halo tile [18 rows][pitch px][64 ch] is loaded once; the MMA reads the
+// 16 x 8 pixel window shifted by (r, s): start = tile + (r*pitch + s) * 128 B, 8-row groups `pitch` rows apart
+// (SBO = pitch * 128 B), descriptor base_offset = (start >> 7) & 7 or 0.  If this works, the 9 taps of a 3x3 conv
+// can share ONE halo load (the per-CTA-unique A traffic of the mid layers drops 4-6x).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_shift_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                                                                   int r, int s, int pitch, int use_base_offset, float* __restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = 18 * pitch * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ((a_bytes + 1023) & ~1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2048);
+  uint32_t* holder = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(holder, 32);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *holder;
+  if (threadIdx.x == 0) {
+    ptx::mbar_expect_tx(&bars[0], (uint32_t)a_bytes + 2048u);
+    ptx::tma_load_4d(sA, &amap, &bars[0], 0, 0, 0, 0);
+    ptx::tma_load_2d(sB, &bmap, &bars[0], 0, 0);
+  }
+  ptx::mbar_wait(&bars[0], 0, nullptr, 90);
+  ptx::tc_fence_after();
+  if (warp == 0 && ptx::elect_one()) {
+    const uint32_t start = ptx::smem_u32(sA) + (uint32_t)((r * pitch + s) * 128);
+    uint64_t adesc = 0;
+    adesc |= (uint64_t)((start & 0x3FFFFu) >> 4);
+    adesc |= (uint64_t)1 << 16;
+    adesc |= (uint64_t)(((uint32_t)pitch * 128u) >> 4) << 32;          // SBO: next 8-pixel group = next image row
+    adesc |= (uint64_t)1 << 46;
+    if (use_base_offset) adesc |= (uint64_t)((start >> 7) & 7u) << 49;
+    adesc |= (uint64_t)2 << 61;                                        // SWIZZLE_128B
+    const uint64_t bdesc = make_kmajor_desc<64>(ptx::smem_u32(sB));
+    constexpr uint32_t idesc = make_idesc_bf16<16>();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+    ptx::umma_commit(&bars[1]);
+  }
+  ptx::mbar_wait(&bars[1], 0, nullptr, 91);
+  ptx::tc_fence_after();
+  uint32_t v[16];
+  ptx::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+  ptx::tmem_ld_wait();
+  for (int j = 0; j < 16; ++j) D[(warp * 32 + lane) * 16 + j] = __uint_as_float(v[j]);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 32);
+  }
+}
+
+void debug_umma_shift(const void* A_dev, const void* B_dev, int r, int s, int pitch, int use_base_offset, float* D_dev, cudaStream_t st) {
+  WSI_REQUIRE(pitch >= 10 && pitch <= 16 && r >= 0 && r <= 2 && s >= 0 && s <= 2, WSI_ERR_INVALID, "probe: bad arguments");
+  CUtensorMap amap, bmap;
+  const uint64_t dims[4] = {64, (uint64_t)pitch, 18, 1};
+  const uint64_t strides[3] = {128, (uint64_t)pitch * 128, (uint64_t)pitch * 128 * 18};
+  const uint32_t box[4] = {64, (uint32_t)pitch, 18, 1};
+  encode4(&amap, A_dev, dims, strides, box, 64);
+  encode2(&bmap, B_dev, 64, 16, 128, 64, 16, 64);
+  const int smem = 1024 + ((18 * pitch * 128 + 1023) & ~1023) + 2048 + 64;
+  CUDA_CHECK(cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_shift_probe_kernel<<<1, 128, smem, st>>>(amap, bmap, r, s, pitch, use_base_offset, D_dev);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace wsi

@@ -551,7 +551,8 @@ class ConvOp {
   double flops() const { return flops_; }
   int block_n() const { return block_n_; }
   int block_k() const { return block_k_; }
-  bool is_pair() const { return pair_; }
+  bool is_pair() const { return pair_ || halo_; }
+  bool is_halo() const { return halo_; }
 
  private:
   void finish(const std::vector<KBlock>& table, int num_parity, const std::vector<uint16_t>& wpacked, int K,
@@ -567,10 +568,16 @@ class ConvOp {
   int block_n_ = 0, block_k_ = 0, grid_ = 0;
   bool resb_ = false;         // weights resident in smem (see conv_igemm_kernel RESB)
   bool pair_ = false;         // CTA-pair kernel (conv_pair.cuh)
+  bool halo_ = false;         // halo-resident CTA-pair kernel (conv_halo.cuh)
+  static bool halo_eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, int out_layout, bool head, int num_sms);
+  void build_halo(const ConvInputPart& part, const ConvSpec& spec, const float* w_oihw, const float* scale, const float* bias,
+                  const void* residual, void* out, int* error_flag, int num_sms);
   bool out_planar_ = false;   // TMA kernel writing the planar layout for a row-kernel consumer
   double flops_ = 0;
 };
 
-void init_tensor_map_api();   // resolves cuTensorMapEncodeTiled through the runtime (no -lcuda link)
+void init_tensor_map_api();
+// hardware probe (dev tool): shifted SWIZZLE_128B A operand inside a TMA-written halo tile, see conv_igemm.cu
+void debug_umma_shift(const void* A_dev, const void* B_dev, int r, int s, int pitch, int use_base_offset, float* D_dev, cudaStream_t st);   // resolves cuTensorMapEncodeTiled through the runtime (no -lcuda link)
 
 }  // namespace wsi

@@ -276,7 +276,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
     for (auto& q : parts) cin_t += q.t.C;
     snprintf(d, sizeof(d), "conv%dx%d/s%d %4d->%-4d @%dx%d%s%s BN%d BK%d%s", spec.ksize, spec.ksize, spec.stride, cin_t, spec.cout,
              parts[0].up2 ? 2 * parts[0].t.H : parts[0].t.H, parts[0].up2 ? 2 * parts[0].t.W : parts[0].t.W, parts[0].up2 ? " up2" : "",
-             res ? " +res" : "", op->block_n(), op->block_k(), op->is_pair() ? " x2" : "");
+             res ? " +res" : "", op->block_n(), op->block_k(), op->is_halo() ? " x2 halo" : (op->is_pair() ? " x2" : ""));
     op_stats.push_back(OpStat{d, 0, op->flops(), 0});
   };
 
@@ -1136,6 +1136,16 @@ int wsi_plan_tiles_gpu(wsi_ctx* ctx, int64_t ih, int64_t iw, int32_t ph, int32_t
   if (!keep.empty()) memcpy(buf, keep.data(), keep.size() * sizeof(int32_t));
   *xy_out = buf;
   *n_out = (int64_t)keep.size() / 2;
+  WSI_API_END(ctx)
+}
+
+int wsi_debug_umma_shift(wsi_ctx* ctx, const void* A_dev, const void* B_dev, int r, int s, int pitch, int use_base_offset, float* D_dev,
+                         void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && A_dev && B_dev && D_dev, WSI_ERR_INVALID, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  debug_umma_shift(A_dev, B_dev, r, s, pitch, use_base_offset, D_dev, (cudaStream_t)stream);
+  CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   WSI_API_END(ctx)
 }
 
