@@ -121,6 +121,8 @@ CONV_CASES = [
     (1, 16, 24, 128, 128, 3, 1, 1, False, True),     # 3 tiles: odd count, out-of-range peer tile
     (2, 32, 32, 256, 256, 3, 1, 1, True, False),     # BLOCK_N 256, 4 K chunks, no ReLU
     (2, 17, 9, 64, 512, 3, 1, 1, False, True),       # one K chunk, two N tiles, one-pixel ragged edges
+    (2, 40, 36, 64, 128, 3, 2, 1, False, True),      # halo kernel, stride 2 through the 4 parity planes (lattice 20x18)
+    (1, 33, 17, 128, 256, 3, 2, 1, False, True),     # halo kernel, stride 2, odd input extents (lattice 17x9)
     (20, 48, 48, 64, 256, 3, 1, 1, True, True),      # BLOCK_N 256 (enough M tiles for every SM), residual
     (6, 64, 64, 256, 512, 3, 1, 1, False, True),     # BLOCK_N 256, two N tiles, K = 2304
     # row-tile / row-stream kernels (cout 16/32/64, <=64 channels per operand): halo-resident taps, cp.async producers
@@ -171,6 +173,11 @@ UP_CASES = [
     (3, 40, 200, 32, 0, 16),      # no skip, ragged second strip
     (12, 16, 16, 64, 64, 32),     # many 1-2 row units per CTA: an epilogue group's first job comes several steps in
     (12, 32, 32, 32, 0, 16),      #   (a per-step completion barrier deadlocked here; per-slot barriers do not)
+    # halo-resident pair kernel, x2 groups (lattice >= 16x8, >= 64 channels per operand)
+    (2, 16, 16, 128, 64, 64),     # decoder level 3 shape (192 -> 64), BLOCK_N 64
+    (1, 16, 24, 256, 128, 128),   # decoder level 2 shape (384 -> 128)
+    (1, 32, 8, 64, 0, 128),       # no skip operand
+    (1, 20, 13, 64, 64, 64),      # ragged lattice, odd width
 ]
 
 

@@ -19,19 +19,35 @@
 
 namespace wsi {
 
+// The kernel is table driven (HaloGroup: one halo load + the taps that read it), which also covers
+//   * stride-2 convs: the input's 4 (row, col)-parity views are 4 groups per K chunk (4 loads instead of 9);
+//   * the decoder's x2-upsample + concat convs, per output parity class as in conv_igemm.cuh: the upsampled operand
+//     is ONE group of 4 collapsed taps per K chunk, the skip operand one group per parity plane it touches.
 constexpr int kHaloW = 10, kHaloH = 18, kHaloTileW = 8, kHaloTileH = 16;
+constexpr int kHaloMaxGroups = 40;            // per parity class
+
+struct HaloGroup {        // one halo tile of one 64-channel chunk and the filter taps that read it
+  int8_t map;             // which A tensor map (box {64 ch, 10 px, 18 rows, 1})
+  int8_t oy, ox;          // box origin relative to the tile's lattice origin (-1, 0)
+  int8_t ntaps;
+  int32_t c0;             // channel origin in that map
+  int32_t wk;             // K offset of the first tap's 64 weights (taps are consecutive blocks of 64)
+  uint8_t tap_off[12];    // per tap: (row * kHaloW + col) of its 16 x 8 window inside the halo tile
+};
+static_assert(sizeof(HaloGroup) == 24, "HaloGroup layout");
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;                      // 23 040
 constexpr int kHaloBuf = (kHaloBytes + 1023) / 1024 * 1024;            // 23 552: buffers stay 1024-byte aligned
 
 template <int BN>
 struct HaloSmem {
   static constexpr int kBBytes = (BN / 2) * 128;                        // this CTA's half of one tap's weight rows
-  static constexpr int kStagesWanted = (150 * 1024) / kBBytes;
+  static constexpr int kStagesWanted = (144 * 1024) / kBBytes;
   static constexpr int kStages = kStagesWanted > 12 ? 12 : kStagesWanted;
   static constexpr int kRing = 2 * kHaloBuf + kStages * kBBytes;
   static constexpr int kBarBytes = 512;
   static constexpr int kScaleBytes = 2 * 512 * (int)sizeof(float);
-  static constexpr int kTotal = 1024 + kRing + kBarBytes + kScaleBytes;
+  static constexpr int kTableBytes = 4 * kHaloMaxGroups * (int)sizeof(HaloGroup);
+  static constexpr int kTotal = 1024 + kRing + kBarBytes + kScaleBytes + kTableBytes;
   static constexpr int kTmemCols = 2 * BN;
   static_assert(kTmemCols <= 512, "TMEM");
   static_assert(kBBytes % 1024 == 0, "swizzle atom alignment");
@@ -39,7 +55,7 @@ struct HaloSmem {
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
+conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
   using S = HaloSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -55,14 +71,16 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 8);
   float* s_scale = reinterpret_cast<float*>(smem + S::kRing + S::kBarBytes);
   float* s_bias = s_scale + 512;
+  HaloGroup* tbl = reinterpret_cast<HaloGroup*>(smem + S::kRing + S::kBarBytes + S::kScaleBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kc = p.num_kb;                         // 64-channel K chunks
+  const int ngroups = p.num_kb;                        // halo groups per parity class
   const uint32_t rank = pptx::cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) { s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i]; }
+  for (int i = threadIdx.x; i < p.num_parity * ngroups; i += blockDim.x) tbl[i] = p.hgroups[i];
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < S::kStages; ++i) {
@@ -77,7 +95,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&bmap);
-    ptx::prefetch_tmap(&amap);
+    ptx::prefetch_tmap(&amaps.m[0]);
   }
   if (warp == 1) pptx::tmem_alloc_pair(tmem_holder, S::kTmemCols);
   ptx::tc_fence_before();
@@ -87,7 +105,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
 
   const int tiles_m = p.tiles_n * p.tiles_h * p.tiles_w;
   const int pairs_m = (tiles_m + 1) >> 1;
-  const int total_tiles = pairs_m * p.tiles_co;
+  const int total_tiles = pairs_m * p.num_parity * p.tiles_co;
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
@@ -99,21 +117,33 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         int r = tile;
         const int ct = r % p.tiles_co; r /= p.tiles_co;
+        const int par = r % p.num_parity; r /= p.num_parity;
         int mt = 2 * r + (int)rank;
         const int tw = mt % p.tiles_w; mt /= p.tiles_w;
         const int th = mt % p.tiles_h; mt /= p.tiles_h;
         const int tn = mt;                                   // == tiles_n for the out-of-range tail tile
-        const int x0 = tw * kHaloTileW - 1, y0 = th * kHaloTileH - 1;
+        const int b0 = tw * kHaloTileW, a0 = th * kHaloTileH;
         const int co0 = ct * BN + (int)rank * (BN / 2);
-        for (int kc = 0; kc < num_kc; ++kc) {
+        const int wpar = par * p.b_parity_stride;
+        const HaloGroup* gt = tbl + par * ngroups;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          const HaloGroup g = gt[gi];
           ptx::mbar_wait(&a_empty[abuf], aphase ^ 1u, p.error_flag, 61);
           if (rank == 0) ptx::mbar_expect_tx(&a_full[abuf], 2u * (uint32_t)kHaloBytes);
-          pptx::tma_load_4d_pair(halo_base + abuf * kHaloBuf, &amap, afull0 + (uint32_t)(abuf * 8), kc * 64, x0, y0, tn);
+          const CUtensorMap* am = &amaps.m[0];
+          switch (g.map) {
+            case 1: am = &amaps.m[1]; break;
+            case 2: am = &amaps.m[2]; break;
+            case 3: am = &amaps.m[3]; break;
+            case 4: am = &amaps.m[4]; break;
+            default: break;
+          }
+          pptx::tma_load_4d_pair(halo_base + abuf * kHaloBuf, am, afull0 + (uint32_t)(abuf * 8), g.c0, b0 + g.ox, a0 + g.oy, tn);
           if (++abuf == 2) { abuf = 0; aphase ^= 1u; }
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < g.ntaps; ++tap) {
             ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 62);
             if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2u * (uint32_t)S::kBBytes);
-            pptx::tma_load_2d_pair(stage_base + stage * S::kBBytes, &bmap, full0 + (uint32_t)(stage * 8), (kc * 9 + tap) * 64, co0);
+            pptx::tma_load_2d_pair(stage_base + stage * S::kBBytes, &bmap, full0 + (uint32_t)(stage * 8), wpar + g.wk + tap * 64, co0);
             if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -137,19 +167,24 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
         pptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 63);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kc = 0; kc < num_kc; ++kc) {
+        const int par = (tile / p.tiles_co) % p.num_parity;
+        const HaloGroup* gt = tbl + par * ngroups;
+        uint32_t started = 0;
+        for (int gi = 0; gi < ngroups; ++gi) {
+          const HaloGroup g = gt[gi];
           pptx::mbar_wait_cluster(&a_full[abuf], aphase, p.error_flag, 65);
           const uint32_t a_addr = ptx::smem_u32(halo_base + abuf * kHaloBuf);
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < g.ntaps; ++tap) {
             pptx::mbar_wait_cluster(&full[stage], phase, p.error_flag, 66);
             ptx::tc_fence_after();
-            const int tr = tap / 3, ts = tap - 3 * tr;
-            const uint64_t adesc = adesc0 | (uint64_t)(((a_addr + (uint32_t)((tr * kHaloW + ts) * 128)) & 0x3FFFFu) >> 4);
+            const uint64_t adesc = adesc0 | (uint64_t)(((a_addr + (uint32_t)g.tap_off[tap] * 128u) & 0x3FFFFu) >> 4);
             const uint64_t bdesc = make_kmajor_desc<64>(ptx::smem_u32(stage_base + stage * S::kBBytes));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              pptx::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kc | tap | k) != 0));
+            for (int k = 0; k < 4; ++k) {
+              pptx::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started);
+              started = 1u;
+            }
             pptx::umma_commit_pair(&empty[stage]);
             if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
           }
@@ -175,7 +210,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
     for (int tile = pair; tile < total_tiles; tile += npairs) {
       int r = tile;
       const int ct = r % p.tiles_co; r /= p.tiles_co;
-      constexpr int par = 0;
+      const int par = r % p.num_parity; r /= p.num_parity;
       int mt = 2 * r + (int)rank;
       const int tw = mt % p.tiles_w; mt /= p.tiles_w;
       const int th = mt % p.tiles_h; mt /= p.tiles_h;
@@ -189,6 +224,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
       const int oh = p.sigma * a + (par >> 1), ow = p.sigma * b + (par & 1);
       const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
       const size_t off0 = pix * p.Cout + co0 + c_lo;
+      const size_t pl_off = (size_t)n * (size_t)p.pl_img + (size_t)(oh + 1) * (size_t)p.pl_row + (size_t)(ow + 8) * 16;
       const bool has_res = (p.res != nullptr) && valid;
 
       uint4 rcur[STEP / 8], rnext[STEP / 8];
@@ -239,7 +275,10 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
           for (int j = 0; j < STEP; ++j) y[j] = fmaxf(y[j], 0.f);
         }
         if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c);
+          // NHWC: 2 * STEP contiguous bytes; planar (consumer = a row kernel): one 16-byte entry per 8-channel chunk row
+          uint8_t* ob = p.out_planar ? reinterpret_cast<uint8_t*>(p.out) + pl_off + (size_t)((co0 + c_lo + c) >> 3) * (size_t)p.pl_chunk
+                                     : reinterpret_cast<uint8_t*>(p.out + off0 + c);
+          const size_t ostep = p.out_planar ? (size_t)p.pl_chunk : 16;
 #pragma unroll
           for (int j = 0; j < STEP / 8; ++j) {
             uint32_t w[4];
@@ -248,7 +287,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_con
               __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
               w[t] = *reinterpret_cast<uint32_t*>(&h2);
             }
-            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(ob + (size_t)j * ostep) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }

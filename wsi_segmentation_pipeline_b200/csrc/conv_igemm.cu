@@ -149,7 +149,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   for (auto& q : parts) WSI_REQUIRE(q.t.layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC operands");
   halo_ = false;
   if (halo_eligible(parts, spec, out_layout, head_out != nullptr, num_sms)) {
-    build_halo(parts[0], spec, w_oihw, scale, bias, residual, out, error_flag, num_sms);
+    build_halo(parts, spec, w_oihw, scale, bias, residual, out, out_layout, error_flag, num_sms);
     return;
   }
   bool any_up = false;
@@ -420,68 +420,194 @@ static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams
 // halo-resident pair kernel (conv_halo.cuh): 3x3 / s1 convs on >= 64-channel NHWC tensors, Cout % 128 == 0
 // ---------------------------------------------------------------------------------------------
 bool ConvOp::halo_eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, int out_layout, bool head, int num_sms) {
-  if (getenv("WSI_NO_HALO") != nullptr || num_sms < 2 || head || out_layout != LAYOUT_NHWC) return false;
-  if (spec.ksize != 3 || spec.stride != 1 || spec.pad != 1 || parts.size() != 1 || parts[0].up2) return false;
-  const TensorView& t = parts[0].t;
-  // 16 x 8 pixel tiles: smaller maps waste most of the tile, the TMA kernel keeps those
-  return t.layout == LAYOUT_NHWC && t.C % 64 == 0 && t.C >= 64 && spec.cout % 128 == 0 && t.H >= kHaloTileH && t.W >= kHaloTileW;
+  if (getenv("WSI_NO_HALO") != nullptr || num_sms < 2 || head) return false;
+  if (out_layout != LAYOUT_NHWC && out_layout != LAYOUT_PLANAR) return false;
+  if (spec.ksize != 3 || spec.pad != 1 || parts.empty() || parts.size() > 2) return false;
+  if (spec.cout % 128 != 0 && spec.cout != 64) return false;
+  for (auto& q : parts)
+    if (q.t.layout != LAYOUT_NHWC || q.t.C % 64 != 0 || q.t.C < 64) return false;
+  int A_h, A_w;                                       // output lattice of one parity class
+  if (parts[0].up2) {
+    if (spec.stride != 1 || (parts.size() == 2 && parts[1].up2)) return false;
+    if (getenv("WSI_NO_HALO_UP2") != nullptr) return false;
+    A_h = parts[0].t.H; A_w = parts[0].t.W;
+  } else {
+    if (parts.size() != 1) return false;
+    if (spec.stride == 2) {
+      if (getenv("WSI_NO_HALO_S2") != nullptr) return false;
+      A_h = (parts[0].t.H - 1) / 2 + 1; A_w = (parts[0].t.W - 1) / 2 + 1;
+    } else if (spec.stride == 1) {
+      A_h = parts[0].t.H; A_w = parts[0].t.W;
+    } else {
+      return false;
+    }
+  }
+  // 16 x 8 lattice tiles: smaller maps waste most of the tile, the TMA kernel keeps those
+  return A_h >= kHaloTileH && A_w >= kHaloTileW;
 }
 
-void ConvOp::build_halo(const ConvInputPart& part, const ConvSpec& spec, const float* w_oihw, const float* scale, const float* bias,
-                        const void* residual, void* out, int* error_flag, int num_sms) {
-  const TensorView& t = part.t;
-  const int N = t.N, H = t.H, W = t.W, C = t.C, cout = spec.cout;
+void ConvOp::build_halo(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw, const float* scale, const float* bias,
+                        const void* residual, void* out, int out_layout, int* error_flag, int num_sms) {
+  const bool up2 = parts[0].up2, s2 = (spec.stride == 2);
+  const int N = parts[0].t.N, cout = spec.cout;
+  int cin = 0;
+  for (auto& q : parts) cin += q.t.C;
+  const int Hin = up2 ? 2 * parts[0].t.H : parts[0].t.H, Win = up2 ? 2 * parts[0].t.W : parts[0].t.W;
+  const int OH = s2 ? (Hin - 1) / 2 + 1 : Hin, OW = s2 ? (Win - 1) / 2 + 1 : Win;
   halo_ = true;
-  pair_ = false; resb_ = false; out_planar_ = false;
-  block_n_ = (cout % 256 == 0) ? 256 : 128;
+  pair_ = false; resb_ = false;
+  out_planar_ = (out_layout == LAYOUT_PLANAR);
+  block_n_ = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
   block_k_ = 64;
   ConvParams& p = p_;
   p = ConvParams{};
-  p.N = N; p.OH = H; p.OW = W; p.Cout = cout;
-  p.sigma = 1; p.num_parity = 1; p.A_h = H; p.A_w = W;
+  p.N = N; p.OH = OH; p.OW = OW; p.Cout = cout;
+  p.sigma = up2 ? 2 : 1;
+  p.num_parity = up2 ? 4 : 1;
+  p.A_h = up2 ? OH / 2 : OH; p.A_w = up2 ? OW / 2 : OW;
   p.bw = kHaloTileW; p.bh = kHaloTileH; p.bn = 1;
-  p.tiles_w = (int)ceil_div(W, kHaloTileW);
-  p.tiles_h = (int)ceil_div(H, kHaloTileH);
+  p.tiles_w = (int)ceil_div(p.A_w, kHaloTileW);
+  p.tiles_h = (int)ceil_div(p.A_h, kHaloTileH);
   p.tiles_n = N;
   p.tiles_co = cout / block_n_;
-  p.num_kb = C / 64;                                  // 64-channel K chunks (9 taps each)
   p.relu = spec.relu ? 1 : 0;
   p.res = static_cast<const bf16*>(residual);
   p.out = static_cast<bf16*>(out);
   p.error_flag = error_flag;
-  // weights [Cout][K], K = (chunk, tap, 64 channels): the order in which the kernel walks the resident halo tile
-  const int K = C * 9;
-  std::vector<uint16_t> wp((size_t)cout * K);
-  for (int co = 0; co < cout; ++co)
-    for (int kc = 0; kc < C / 64; ++kc)
-      for (int tap = 0; tap < 9; ++tap)
+  if (out_planar_) {
+    const PlanarDims od = PlanarDims::make(OH, OW, cout, LAYOUT_PLANAR);
+    p.out_planar = 1;
+    p.pl_chunk = (long long)od.Wrow * 16;
+    p.pl_row = (long long)od.KC * p.pl_chunk;
+    p.pl_img = (long long)(OH + 2) * p.pl_row;
+  }
+  // tensor maps: every halo load is a box {64 ch, 10 px, 18 rows, 1 image}
+  if (up2) {
+    map_plain(&amaps_.m[0], parts[0].t, 64, kHaloW, kHaloH, 1);
+    if (parts.size() == 2)
+      for (int hp = 0; hp < 2; ++hp)
+        for (int wp = 0; wp < 2; ++wp) map_parity(&amaps_.m[1 + hp * 2 + wp], parts[1].t, hp, wp, 64, kHaloW, kHaloH, 1);
+  } else if (s2) {
+    for (int hp = 0; hp < 2; ++hp)
+      for (int wp = 0; wp < 2; ++wp) map_parity(&amaps_.m[hp * 2 + wp], parts[0].t, hp, wp, 64, kHaloW, kHaloH, 1);
+  } else {
+    map_plain(&amaps_.m[0], parts[0].t, 64, kHaloW, kHaloH, 1);
+  }
+  for (int i = 0; i < kMaxAMaps; ++i)
+    if (i >= (up2 ? (parts.size() == 2 ? 5 : 1) : (s2 ? 4 : 1))) amaps_.m[i] = amaps_.m[0];
+
+  // groups and weights.  Weight matrix [Cout][num_parity * Kpar], per parity class the (group, tap) blocks of 64 in
+  // table order; taps of a x2-upsampled operand are pre-summed in fp32 (as in the TMA kernel).
+  auto w_at = [&](int co, int ci, int r, int s) { return w_oihw[(((size_t)co * cin + ci) * 3 + r) * 3 + s]; };
+  std::vector<HaloGroup> table;
+  std::vector<std::vector<float>> wblocks;          // per parity: [block][co][64] fp32, flattened
+  int groups_per_parity = -1;
+  size_t Kpar = 0;
+  for (int par = 0; par < p.num_parity; ++par) {
+    const int py = par >> 1, px = par & 1;
+    std::vector<float> wb;
+    int ng = 0, wk = 0;
+    auto add_block = [&](auto&& weight_of /* (co, j) -> float */) {
+      const size_t base = wb.size();
+      wb.resize(base + (size_t)cout * 64);
+      for (int co = 0; co < cout; ++co)
+        for (int j = 0; j < 64; ++j) wb[base + (size_t)co * 64 + j] = weight_of(co, j);
+    };
+    int part_off = 0;
+    for (size_t pi = 0; pi < parts.size(); ++pi) {
+      const auto& q = parts[pi];
+      for (int c0 = 0; c0 < q.t.C; c0 += 64) {
+        if (up2 && q.up2) {
+          // upsampled operand: the 3x3 taps of this parity class fall on 2 x 2 half-resolution pixels
+          HaloGroup g{};
+          g.map = 0; g.c0 = c0; g.wk = wk;
+          g.oy = (int8_t)floor_div2(py - 1); g.ox = (int8_t)floor_div2(px - 1);
+          for (int pos = 0; pos < 4; ++pos) {
+            g.tap_off[g.ntaps++] = (uint8_t)((pos >> 1) * kHaloW + (pos & 1));
+            add_block([&](int co, int j) {
+              float v = 0.f;
+              for (int r = 0; r < 3; ++r)
+                for (int s2_ = 0; s2_ < 3; ++s2_) {
+                  const int dy = floor_div2(py + r - 1) - floor_div2(py - 1), dx = floor_div2(px + s2_ - 1) - floor_div2(px - 1);
+                  if (dy * 2 + dx == pos) v += w_at(co, part_off + c0 + j, r, s2_);
+                }
+              return v;
+            });
+            wk += 64;
+          }
+          table.push_back(g); ++ng;
+        } else if (up2 || s2) {
+          // full-resolution operand seen through its (row, col) parity planes: source row = 2 * (a + ry) + hp
+          const int qy = up2 ? py : 0, qx = up2 ? px : 0;      // stride 2: output (a, b) reads rows 2a + r - 1
+          for (int hp = 0; hp < 2; ++hp)
+            for (int wp = 0; wp < 2; ++wp) {
+              HaloGroup g{};
+              g.map = (int8_t)((up2 ? 1 : 0) + hp * 2 + wp); g.c0 = c0; g.wk = wk;
+              int min_ry = 9, min_cx = 9;
+              for (int r = 0; r < 3; ++r) if (((qy + r - 1) & 1) == hp) min_ry = std::min(min_ry, floor_div2(qy + r - 1));
+              for (int s_ = 0; s_ < 3; ++s_) if (((qx + s_ - 1) & 1) == wp) min_cx = std::min(min_cx, floor_div2(qx + s_ - 1));
+              if (min_ry == 9 || min_cx == 9) continue;
+              g.oy = (int8_t)min_ry; g.ox = (int8_t)min_cx;
+              for (int r = 0; r < 3; ++r)
+                for (int s_ = 0; s_ < 3; ++s_) {
+                  if (((qy + r - 1) & 1) != hp || ((qx + s_ - 1) & 1) != wp) continue;
+                  g.tap_off[g.ntaps++] = (uint8_t)((floor_div2(qy + r - 1) - min_ry) * kHaloW + (floor_div2(qx + s_ - 1) - min_cx));
+                  add_block([&](int co, int j) { return w_at(co, part_off + c0 + j, r, s_); });
+                  wk += 64;
+                }
+              table.push_back(g); ++ng;
+            }
+        } else {
+          HaloGroup g{};
+          g.map = 0; g.c0 = c0; g.wk = wk; g.oy = -1; g.ox = -1;
+          for (int tap = 0; tap < 9; ++tap) {
+            g.tap_off[g.ntaps++] = (uint8_t)((tap / 3) * kHaloW + tap % 3);
+            add_block([&](int co, int j) { return w_at(co, part_off + c0 + j, tap / 3, tap % 3); });
+            wk += 64;
+          }
+          table.push_back(g); ++ng;
+        }
+      }
+      part_off += q.t.C;
+    }
+    WSI_REQUIRE(ng <= kHaloMaxGroups, WSI_ERR_UNSUPPORTED, "halo conv: %d groups > %d", ng, kHaloMaxGroups);
+    WSI_REQUIRE(groups_per_parity < 0 || groups_per_parity == ng, WSI_ERR_UNSUPPORTED, "halo conv: parity classes differ in group count");
+    groups_per_parity = ng;
+    Kpar = (size_t)wk;
+    wblocks.push_back(std::move(wb));
+  }
+  p.num_kb = groups_per_parity;
+  p.b_parity_stride = (p.num_parity > 1) ? (int)Kpar : 0;
+  const size_t Ktot = Kpar * p.num_parity;
+  std::vector<uint16_t> wp((size_t)cout * Ktot);
+  for (int par = 0; par < p.num_parity; ++par) {
+    const std::vector<float>& wb = wblocks[par];
+    const size_t nblk = Kpar / 64;
+    for (size_t blk = 0; blk < nblk; ++blk)
+      for (int co = 0; co < cout; ++co)
         for (int j = 0; j < 64; ++j)
-          wp[(size_t)co * K + ((size_t)kc * 9 + tap) * 64 + j] =
-              f32_to_bf16_bits(w_oihw[(((size_t)co * C + kc * 64 + j) * 3 + tap / 3) * 3 + tap % 3]);
+          wp[(size_t)co * Ktot + (size_t)par * Kpar + blk * 64 + j] = f32_to_bf16_bits(wb[(blk * cout + co) * 64 + j]);
+  }
   upload(w_, wp);
+  upload(hgroups_, table);
+  p.hgroups = hgroups_.as<HaloGroup>();
   std::vector<float> sc(cout, 1.f), bi(cout, 0.f);
   if (scale) sc.assign(scale, scale + cout);
   if (bias) bi.assign(bias, bias + cout);
   upload(scale_, sc); upload(bias_, bi);
   p.scale = scale_.as<float>(); p.bias = bias_.as<float>();
-  {
-    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    const uint64_t st[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    const uint32_t box[4] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, 1};
-    encode4(&amaps_.m[0], t.ptr, dims, st, box, 64);
-    for (int i = 1; i < kMaxAMaps; ++i) amaps_.m[i] = amaps_.m[0];
-  }
-  encode2(&bmap_, w_.p, (uint64_t)K, (uint64_t)cout, (uint64_t)K * 2, 64, (uint32_t)(block_n_ / 2), 64);
+  encode2(&bmap_, w_.p, (uint64_t)Ktot, (uint64_t)cout, (uint64_t)Ktot * 2, 64, (uint32_t)(block_n_ / 2), 64);
   const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
-  const long long pair_tiles = (tiles_m + 1) / 2 * p.tiles_co;
+  const long long pair_tiles = (tiles_m + 1) / 2 * p.tiles_co * p.num_parity;
   WSI_REQUIRE(pair_tiles < (1LL << 30), WSI_ERR_UNSUPPORTED, "conv: too many tiles");
   grid_ = 2 * (int)std::min<long long>(pair_tiles, num_sms / 2);
-  flops_ = 2.0 * N * H * W * (double)cout * C * 9;
+  const int taps = 9;
+  flops_ = 2.0 * N * OH * OW * (double)cout * cin * taps;
   CUDA_CHECK(cudaStreamSynchronize(0));
 }
 
 template <int BN>
-static void launch_halo(const CUtensorMap& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
+static void launch_halo(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
   using S = HaloSmem<BN>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   static bool configured = false;
@@ -512,8 +638,9 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (row_) { row_->launch(stream, lc); return; }
   if (stem_) { stem_->launch(stream, lc); return; }
   if (halo_) {
-    if (block_n_ == 256) launch_halo<256>(amaps_.m[0], bmap_, p_, grid_, stream);
-    else launch_halo<128>(amaps_.m[0], bmap_, p_, grid_, stream);
+    if (block_n_ == 256) launch_halo<256>(amaps_, bmap_, p_, grid_, stream);
+    else if (block_n_ == 128) launch_halo<128>(amaps_, bmap_, p_, grid_, stream);
+    else launch_halo<64>(amaps_, bmap_, p_, grid_, stream);
     if (lc) lc->n++;
     return;
   }

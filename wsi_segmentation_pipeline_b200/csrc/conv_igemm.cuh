@@ -67,6 +67,7 @@ struct ConvParams {
   int* error_flag;            // set to 1 by a timed-out barrier wait
   int out_planar;             // 1: `out` is the zero-padded channel-chunk-planar layout of conv_rowtile.cuh (consumer = a row kernel)
   long long pl_img, pl_row, pl_chunk;   // its byte strides: image, image row, 8-channel chunk row (entry = x + 8, 16 B each)
+  const struct HaloGroup* hgroups;   // halo-resident kernel (conv_halo.cuh): [num_parity][num_kb] groups
   int dbg;                    // timing experiments only (WSI_IGEMM_DBG; results are garbage): 1 no MMAs, 2 no TMA loads,
                               // 3 A loads only, 4 B loads only
 };
@@ -570,8 +571,9 @@ class ConvOp {
   bool pair_ = false;         // CTA-pair kernel (conv_pair.cuh)
   bool halo_ = false;         // halo-resident CTA-pair kernel (conv_halo.cuh)
   static bool halo_eligible(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, int out_layout, bool head, int num_sms);
-  void build_halo(const ConvInputPart& part, const ConvSpec& spec, const float* w_oihw, const float* scale, const float* bias,
-                  const void* residual, void* out, int* error_flag, int num_sms);
+  void build_halo(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw, const float* scale, const float* bias,
+                  const void* residual, void* out, int out_layout, int* error_flag, int num_sms);
+  DevBuf hgroups_;
   bool out_planar_ = false;   // TMA kernel writing the planar layout for a row-kernel consumer
   double flops_ = 0;
 };
