@@ -429,12 +429,14 @@ bool ConvOp::halo_eligible(const std::vector<ConvInputPart>& parts, const ConvSp
   int A_h, A_w;                                       // output lattice of one parity class
   if (parts[0].up2) {
     if (spec.stride != 1 || (parts.size() == 2 && parts[1].up2)) return false;
-    if (getenv("WSI_NO_HALO_UP2") != nullptr) return false;
+    // measured (same box A/B): with only 4 taps per halo load the x2 convs are 3-10 % SLOWER than on the TMA pair
+    // kernel (a 23 KB halo per group vs 16 KB per tap, two halo buffers deep) — opt-in for experiments and tests
+    if (getenv("WSI_HALO_UP2") == nullptr) return false;
     A_h = parts[0].t.H; A_w = parts[0].t.W;
   } else {
     if (parts.size() != 1) return false;
     if (spec.stride == 2) {
-      if (getenv("WSI_NO_HALO_S2") != nullptr) return false;
+      if (getenv("WSI_HALO_S2") == nullptr) return false;      // 1-4 taps per parity-plane halo: 8-17 % slower, opt-in
       A_h = (parts[0].t.H - 1) / 2 + 1; A_w = (parts[0].t.W - 1) / 2 + 1;
     } else if (spec.stride == 1) {
       A_h = parts[0].t.H; A_w = parts[0].t.W;
