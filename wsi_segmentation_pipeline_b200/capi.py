@@ -12,7 +12,7 @@ from typing import Mapping, Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwsi_b200.so")
+LIB_PATH = os.environ.get("WSI_B200_LIB") or os.path.join(HERE, "libwsi_b200.so")
 
 WSI_OK = 0
 ERR_NAMES = {-1: "WSI_ERR_INVALID", -2: "WSI_ERR_CUDA", -3: "WSI_ERR_NOMODEL", -4: "WSI_ERR_DEGENERATE",

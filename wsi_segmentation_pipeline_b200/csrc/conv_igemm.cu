@@ -579,6 +579,7 @@ void ConvOp::build_halo(const std::vector<ConvInputPart>& parts, const ConvSpec&
     wblocks.push_back(std::move(wb));
   }
   p.num_kb = groups_per_parity;
+  p.halo_plain = (!up2 && !s2) ? 1 : 0;
   p.b_parity_stride = (p.num_parity > 1) ? (int)Kpar : 0;
   const size_t Ktot = Kpar * p.num_parity;
   std::vector<uint16_t> wp((size_t)cout * Ktot);
@@ -608,16 +609,16 @@ void ConvOp::build_halo(const std::vector<ConvInputPart>& parts, const ConvSpec&
   CUDA_CHECK(cudaStreamSynchronize(0));
 }
 
-template <int BN>
+template <int BN, bool PLAIN>
 static void launch_halo(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
   using S = HaloSmem<BN>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel<BN, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  conv_halo_pair_kernel<BN><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);   // __cluster_dims__(2, 1, 1)
+  conv_halo_pair_kernel<BN, PLAIN><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);   // __cluster_dims__(2, 1, 1)
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -640,9 +641,10 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (row_) { row_->launch(stream, lc); return; }
   if (stem_) { stem_->launch(stream, lc); return; }
   if (halo_) {
-    if (block_n_ == 256) launch_halo<256>(amaps_, bmap_, p_, grid_, stream);
-    else if (block_n_ == 128) launch_halo<128>(amaps_, bmap_, p_, grid_, stream);
-    else launch_halo<64>(amaps_, bmap_, p_, grid_, stream);
+    const bool plain = p_.halo_plain && !p_.out_planar;
+    if (block_n_ == 256) { if (plain) launch_halo<256, true>(amaps_, bmap_, p_, grid_, stream); else launch_halo<256, false>(amaps_, bmap_, p_, grid_, stream); }
+    else if (block_n_ == 128) { if (plain) launch_halo<128, true>(amaps_, bmap_, p_, grid_, stream); else launch_halo<128, false>(amaps_, bmap_, p_, grid_, stream); }
+    else launch_halo<64, false>(amaps_, bmap_, p_, grid_, stream);
     if (lc) lc->n++;
     return;
   }

@@ -68,6 +68,7 @@ struct ConvParams {
   int out_planar;             // 1: `out` is the zero-padded channel-chunk-planar layout of conv_rowtile.cuh (consumer = a row kernel)
   long long pl_img, pl_row, pl_chunk;   // its byte strides: image, image row, 8-channel chunk row (entry = x + 8, 16 B each)
   const struct HaloGroup* hgroups;   // halo-resident kernel (conv_halo.cuh): [num_parity][num_kb] groups
+  int halo_plain;             // ... plain 3x3/s1 conv: every group is one 64-channel chunk with the 9 taps in (r, s) order
   int dbg;                    // timing experiments only (WSI_IGEMM_DBG; results are garbage): 1 no MMAs, 2 no TMA loads,
                               // 3 A loads only, 4 B loads only
 };
