@@ -4,5 +4,5 @@ mkdir -p gpurun_out
 for lib in "" "$PWD/gpurun_out_old_lib.so" "" "$PWD/gpurun_out_old_lib.so"; do
   echo "=== lib [$lib]"
   WSI_B200_LIB=$lib WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/conv_trace_ab.log 2>&1; echo "exit $?"
-  grep -E "iter 2|128->128  @64x64|256->256  @32x32 BN256 BK64 x2 halo  " gpurun_out/conv_trace_ab.log | cut -c1-100
+  grep -E "iter 2|conv3x3/s2|conv1x1|up2 BN(64|128|256)" gpurun_out/conv_trace_ab.log | cut -c1-100
 done

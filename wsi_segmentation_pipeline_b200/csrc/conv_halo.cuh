@@ -58,7 +58,7 @@ struct HaloSmem {
 // = channels [64 gi, 64 gi + 64), origin (-1, -1), taps in (r, s) order), so neither the producer nor the MMA issuer
 // reads the table, and the epilogue has no parity / planar addressing: 25 % faster on the 128-channel layers than the
 // table-driven instance (same-box A/B).
-template <int BN, bool PLAIN>
+template <int BN, bool PLAIN, bool PLAIN_EPI = PLAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
   using S = HaloSmem<BN>;
@@ -227,8 +227,8 @@ conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant
     for (int tile = pair; tile < total_tiles; tile += npairs) {
       int r = tile;
       const int ct = r % p.tiles_co; r /= p.tiles_co;
-      const int par = PLAIN ? 0 : r % p.num_parity;
-      if (!PLAIN) r /= p.num_parity;
+      const int par = PLAIN_EPI ? 0 : r % p.num_parity;
+      if (!PLAIN_EPI) r /= p.num_parity;
       int mt = 2 * r + (int)rank;
       const int tw = mt % p.tiles_w; mt /= p.tiles_w;
       const int th = mt % p.tiles_h; mt /= p.tiles_h;
@@ -239,7 +239,7 @@ conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant
       const int nl = row / (p.bw * p.bh);
       const int n = tn * p.bn + nl, a = th * p.bh + hl, b = tw * p.bw + wl;
       const bool valid = (n < p.N) && (a < p.A_h) && (b < p.A_w);
-      const int oh = PLAIN ? a : p.sigma * a + (par >> 1), ow = PLAIN ? b : p.sigma * b + (par & 1);
+      const int oh = PLAIN_EPI ? a : p.sigma * a + (par >> 1), ow = PLAIN_EPI ? b : p.sigma * b + (par & 1);
       const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
       const size_t off0 = pix * p.Cout + co0 + c_lo;
       const size_t pl_off = (size_t)n * (size_t)p.pl_img + (size_t)(oh + 1) * (size_t)p.pl_row + (size_t)(ow + 8) * 16;
@@ -294,7 +294,7 @@ conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant
         }
         if (valid) {
           // NHWC: 2 * STEP contiguous bytes; planar (consumer = a row kernel): one 16-byte entry per 8-channel chunk row
-          const bool planar = !PLAIN && p.out_planar;
+          const bool planar = !PLAIN_EPI && p.out_planar;
           uint8_t* ob = planar ? reinterpret_cast<uint8_t*>(p.out) + pl_off + (size_t)((co0 + c_lo + c) >> 3) * (size_t)p.pl_chunk
                                : reinterpret_cast<uint8_t*>(p.out + off0 + c);
           const size_t ostep = planar ? (size_t)p.pl_chunk : 16;

@@ -609,16 +609,16 @@ void ConvOp::build_halo(const std::vector<ConvInputPart>& parts, const ConvSpec&
   CUDA_CHECK(cudaStreamSynchronize(0));
 }
 
-template <int BN, bool PLAIN>
+template <int BN, bool PLAIN, bool PLAIN_EPI = PLAIN>
 static void launch_halo(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
   using S = HaloSmem<BN>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel<BN, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel<BN, PLAIN, PLAIN_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  conv_halo_pair_kernel<BN, PLAIN><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);   // __cluster_dims__(2, 1, 1)
+  conv_halo_pair_kernel<BN, PLAIN, PLAIN_EPI><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);   // __cluster_dims__(2, 1, 1)
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -643,6 +643,13 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (halo_) {
     const bool plain = p_.halo_plain && !p_.out_planar;
     if (block_n_ == 256) { if (plain) launch_halo<256, true>(amaps_, bmap_, p_, grid_, stream); else launch_halo<256, false>(amaps_, bmap_, p_, grid_, stream); }
+    else if (block_n_ == 128 && plain && getenv("WSI_HALO_VARIANT")) {     // experiment: which half of PLAIN matters
+      const int v = atoi(getenv("WSI_HALO_VARIANT"));
+      if (v == 0) launch_halo<128, false, false>(amaps_, bmap_, p_, grid_, stream);
+      else if (v == 1) launch_halo<128, true, false>(amaps_, bmap_, p_, grid_, stream);
+      else if (v == 2) launch_halo<128, false, true>(amaps_, bmap_, p_, grid_, stream);
+      else launch_halo<128, true, true>(amaps_, bmap_, p_, grid_, stream);
+    }
     else if (block_n_ == 128) { if (plain) launch_halo<128, true>(amaps_, bmap_, p_, grid_, stream); else launch_halo<128, false>(amaps_, bmap_, p_, grid_, stream); }
     else launch_halo<64, false>(amaps_, bmap_, p_, grid_, stream);
     if (lc) lc->n++;

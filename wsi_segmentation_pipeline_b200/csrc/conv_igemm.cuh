@@ -294,6 +294,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
         const int n0 = tn * p.bn, a0 = th * p.bh, b0 = tw * p.bw, co0 = ct * BLOCK_N;
         const KBlock* kb_tbl = tbl + par * num_kb;
         for (int kb = 0; kb < num_kb; ++kb) {
+          const KBlock e = kb_tbl[kb];      // read BEFORE the wait (asm volatile + memory clobber would pin it after)
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 1);
           if (p.dbg >= 2) {
             const bool la = (p.dbg == 3), lb = (p.dbg == 4) && !RESB;
@@ -305,7 +306,6 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             continue;
           }
           ptx::mbar_expect_tx(&full[stage], RESB ? S::kABytes : S::kABytes + S::kBBytesRaw);
-          const KBlock e = kb_tbl[kb];
           uint8_t* sA = stage_base + stage * S::kStageBytes;
           uint8_t* sB = sA + S::kABytes;
           const CUtensorMap* am = &amaps.m[0];
@@ -316,8 +316,8 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             case 4: am = &amaps.m[4]; break;
             default: break;
           }
-          ptx::tma_load_4d(sA, am, &full[stage], e.c0, b0 + e.db, a0 + e.da, n0);
           if (!RESB) ptx::tma_load_2d(sB, &bmap, &full[stage], par * p.b_parity_stride + kb * BLOCK_K, co0);
+          ptx::tma_load_4d(sA, am, &full[stage], e.c0, b0 + e.db, a0 + e.da, n0);
           if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
         }
       }

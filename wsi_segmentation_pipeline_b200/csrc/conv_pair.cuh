@@ -186,6 +186,7 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
         const int co0 = ct * BN + (int)rank * (BN / 2);
         const KBlock* kb_tbl = tbl + par * num_kb;
         for (int kb = 0; kb < num_kb; ++kb) {
+          const KBlock e = kb_tbl[kb];      // read BEFORE the wait (asm volatile + memory clobber would pin it after)
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 11);
           if (p.dbg >= 3) {      // timing experiments (see ConvParams::dbg): 3 A only, 4 B only (2 would let the leader lap the peer)
             const bool la = (p.dbg == 3), lb = (p.dbg == 4);
@@ -198,9 +199,11 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
             continue;
           }
           if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2u * (uint32_t)S::kStageBytes);
-          const KBlock e = kb_tbl[kb];
           uint8_t* sA = stage_base + stage * S::kStageBytes;
           uint8_t* sB = sA + S::kABytes;
+          const uint32_t fbar = full0 + (uint32_t)(stage * 8);
+          // the weight tile does not depend on the table: issue it first; the table entry was read before the wait
+          pptx::tma_load_2d_pair(sB, &bmap, fbar, par * p.b_parity_stride + kb * BLOCK_K, co0);
           const CUtensorMap* am = &amaps.m[0];
           switch (e.map) {
             case 1: am = &amaps.m[1]; break;
@@ -209,9 +212,7 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
             case 4: am = &amaps.m[4]; break;
             default: break;
           }
-          const uint32_t fbar = full0 + (uint32_t)(stage * 8);
           pptx::tma_load_4d_pair(sA, am, fbar, e.c0, b0 + e.db, a0 + e.da, n0);
-          pptx::tma_load_2d_pair(sB, &bmap, fbar, par * p.b_parity_stride + kb * BLOCK_K, co0);
           if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
         }
       }
