@@ -288,11 +288,12 @@ def test_plan_tiles_gpu_matches_host_planner(ctx, golden_dir):
 
 def test_halo_groups_stride2_and_up2(ctx, monkeypatch):
     """The halo-resident kernel's group table also covers stride-2 convs (4 parity-plane halos per K chunk) and the
-    x2-upsample(+skip) convs (one 4-tap group for the upsampled operand, one group per skip parity plane).  Those
-    routes are opt-in (measured slower than the TMA pair kernel); exercise them here so the table code stays correct."""
+    x2-upsample(+skip) convs (one 4-tap group for the upsampled operand, one group per skip parity plane).  The
+    stride-2 route is opt-in (no gain over the TMA pair kernel); exercise it here so the table code stays correct, and
+    run the x2 cases on BOTH kernels."""
     monkeypatch.setenv("WSI_HALO_S2", "1")
-    monkeypatch.setenv("WSI_HALO_UP2", "1")
     for case in [(2, 40, 36, 64, 128, 3, 2, 1, False, True), (1, 33, 17, 128, 256, 3, 2, 1, False, True)]:
         test_conv_igemm(ctx, case)
+    monkeypatch.setenv("WSI_NO_HALO_UP2", "1")                 # the TMA pair / single-CTA kernels on the same shapes
     for case in [(2, 16, 16, 128, 64, 64), (1, 16, 24, 256, 128, 128), (1, 32, 8, 64, 0, 128), (1, 20, 13, 64, 64, 64)]:
         test_conv_upsample_concat(ctx, case)

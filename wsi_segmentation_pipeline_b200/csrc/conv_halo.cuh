@@ -25,7 +25,6 @@ namespace wsi {
 //     is ONE group of 4 collapsed taps per K chunk, the skip operand one group per parity plane it touches.
 constexpr int kHaloW = 10, kHaloH = 18, kHaloTileW = 8, kHaloTileH = 16;
 constexpr int kHaloMaxGroups = 40;            // per parity class
-constexpr int kHaloBufs = 2;                  // halo tiles in flight per CTA (2 vs 3: no measurable difference)
 
 struct HaloGroup {        // one halo tile of one 64-channel chunk and the filter taps that read it
   int8_t map;             // which A tensor map (box {64 ch, 10 px, 18 rows, 1})
@@ -39,12 +38,16 @@ static_assert(sizeof(HaloGroup) == 24, "HaloGroup layout");
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;                      // 23 040
 constexpr int kHaloBuf = (kHaloBytes + 1023) / 1024 * 1024;            // 23 552: buffers stay 1024-byte aligned
 
-template <int BN>
+template <int BN, bool PLAIN>
 struct HaloSmem {
+  // The ring is a latency buffer (Little's law: bytes in flight / ~2 us of loaded TMA latency).  A plain group keeps the
+  // tensor cores busy for 36 MMAs (~3 500 cycles), so 2 halo tiles in flight are enough and the weight ring gets the
+  // rest; the groups of stride-2 / x2 convs have 1-4 taps (<= 1 500 cycles), they need more halo tiles in flight.
+  static constexpr int kBufs = PLAIN ? 2 : (BN == 64 ? 6 : (BN == 128 ? 5 : 4));
   static constexpr int kBBytes = (BN / 2) * 128;                        // this CTA's half of one tap's weight rows
-  static constexpr int kStagesWanted = (144 * 1024) / kBBytes;
+  static constexpr int kStagesWanted = ((PLAIN ? 144 : (BN == 128 ? 80 : 96)) * 1024) / kBBytes;
   static constexpr int kStages = kStagesWanted > 12 ? 12 : kStagesWanted;
-  static constexpr int kRing = kHaloBufs * kHaloBuf + kStages * kBBytes;
+  static constexpr int kRing = kBufs * kHaloBuf + kStages * kBBytes;
   static constexpr int kBarBytes = 512;
   static constexpr int kScaleBytes = 2 * 512 * (int)sizeof(float);
   static constexpr int kTableBytes = 4 * kHaloMaxGroups * (int)sizeof(HaloGroup);
@@ -61,7 +64,8 @@ struct HaloSmem {
 template <int BN, bool PLAIN, bool PLAIN_EPI = PLAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
-  using S = HaloSmem<BN>;
+  using S = HaloSmem<BN, PLAIN>;
+  constexpr int kHaloBufs = S::kBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* halo_base = smem;                            // kHaloBufs halo buffers

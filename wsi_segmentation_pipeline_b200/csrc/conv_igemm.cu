@@ -429,14 +429,14 @@ bool ConvOp::halo_eligible(const std::vector<ConvInputPart>& parts, const ConvSp
   int A_h, A_w;                                       // output lattice of one parity class
   if (parts[0].up2) {
     if (spec.stride != 1 || (parts.size() == 2 && parts[1].up2)) return false;
-    // measured (same box A/B): with only 4 taps per halo load the x2 convs are 3-10 % SLOWER than on the TMA pair
-    // kernel (a 23 KB halo per group vs 16 KB per tap, two halo buffers deep) — opt-in for experiments and tests
-    if (getenv("WSI_HALO_UP2") == nullptr) return false;
+    // measured (same box A/B): 5-7 % faster than the TMA pair kernel once 4+ halo tiles are in flight (with two they
+    // were 3-10 % slower: a 4-tap group is ~1 500 cycles of MMAs, less than the TMA latency)
+    if (getenv("WSI_NO_HALO_UP2") != nullptr) return false;
     A_h = parts[0].t.H; A_w = parts[0].t.W;
   } else {
     if (parts.size() != 1) return false;
     if (spec.stride == 2) {
-      if (getenv("WSI_HALO_S2") == nullptr) return false;      // 1-4 taps per parity-plane halo: 8-17 % slower, opt-in
+      if (getenv("WSI_HALO_S2") == nullptr) return false;      // 1-4 taps per parity-plane halo: no gain (+-2 %), opt-in
       A_h = (parts[0].t.H - 1) / 2 + 1; A_w = (parts[0].t.W - 1) / 2 + 1;
     } else if (spec.stride == 1) {
       A_h = parts[0].t.H; A_w = parts[0].t.W;
@@ -611,7 +611,7 @@ void ConvOp::build_halo(const std::vector<ConvInputPart>& parts, const ConvSpec&
 
 template <int BN, bool PLAIN, bool PLAIN_EPI = PLAIN>
 static void launch_halo(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
-  using S = HaloSmem<BN>;
+  using S = HaloSmem<BN, PLAIN>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
@@ -643,13 +643,6 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
   if (halo_) {
     const bool plain = p_.halo_plain && !p_.out_planar;
     if (block_n_ == 256) { if (plain) launch_halo<256, true>(amaps_, bmap_, p_, grid_, stream); else launch_halo<256, false>(amaps_, bmap_, p_, grid_, stream); }
-    else if (block_n_ == 128 && plain && getenv("WSI_HALO_VARIANT")) {     // experiment: which half of PLAIN matters
-      const int v = atoi(getenv("WSI_HALO_VARIANT"));
-      if (v == 0) launch_halo<128, false, false>(amaps_, bmap_, p_, grid_, stream);
-      else if (v == 1) launch_halo<128, true, false>(amaps_, bmap_, p_, grid_, stream);
-      else if (v == 2) launch_halo<128, false, true>(amaps_, bmap_, p_, grid_, stream);
-      else launch_halo<128, true, true>(amaps_, bmap_, p_, grid_, stream);
-    }
     else if (block_n_ == 128) { if (plain) launch_halo<128, true>(amaps_, bmap_, p_, grid_, stream); else launch_halo<128, false>(amaps_, bmap_, p_, grid_, stream); }
     else launch_halo<64, false>(amaps_, bmap_, p_, grid_, stream);
     if (lc) lc->n++;
