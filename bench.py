@@ -276,7 +276,7 @@ def main():
         conv = stats["conv"]
         conv_tflops = conv["work"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         per_launch_flops = conv["work"] / max(conv["launches"], 1)
-        roofline = {"kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv + BN/ReLU/residual epilogue)", "bound": "tensor",
+        roofline = {"kernel": "conv stage: conv_halo_pair / conv_igemm(_pair) / conv_rowstream(2) / conv_upstream kernels (tcgen05 implicit-GEMM convs + BN/ReLU/residual epilogues)", "bound": "tensor",
                     "achieved": conv_tflops, "peak": tf_sus, "unit": "TFLOP/s", "frac": conv_tflops / tf_sus,
                     "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None,
                     "launches": conv["launches"], "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),

@@ -11,6 +11,6 @@ timeout 600 $CMD > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list exit $?"
 timeout 600 $CMD > gpurun_out/plain2.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 36 -c 8 -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_halo|conv_igemm" -s 36 -c 10 -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"; tail -n 5 gpurun_out/ncu_full.log
 fi
