@@ -1,8 +1,8 @@
 #!/bin/bash
-# scratch: same-box A/B of two builds of the library (WSI_B200_LIB selects the .so)
+# scratch A/B on one box: programmatic dependent launch on / off (whole-iteration throughput)
 mkdir -p gpurun_out
-for lib in "" "$PWD/gpurun_out_old_lib.so" "" "$PWD/gpurun_out_old_lib.so"; do
-  echo "=== lib [$lib]"
-  WSI_B200_LIB=$lib WSI_CONV_TRACE=1 timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/conv_trace_ab.log 2>&1; echo "exit $?"
-  grep -E "iter 2|128->128  @64x64|up2 BN(64|128) " gpurun_out/conv_trace_ab.log | cut -c1-100
+for v in "WSI_NONE=1" "WSI_NO_PDL=1" "WSI_NONE=1" "WSI_NO_PDL=1"; do
+  echo "=== [$v]"
+  env $v timeout 300 python tools/perf_probe.py 4096 512 128 unet > gpurun_out/probe_ab.log 2>&1; echo "exit $?"
+  grep -E "iter [12]|conv  |classes_hist" gpurun_out/probe_ab.log | cut -c1-100
 done
