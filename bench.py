@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args.gpus, ih, iw, len(tiles)),
             "cpu_baseline": {"value": v, "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(n_gpus, ih, iw, n_tiles):
@@ -152,6 +152,29 @@ def workload_config(n_gpus, ih, iw, n_tiles):
             "tiles": int(n_tiles), "tile": TILE, "stride": STRIDE, "slide_wh": [iw, ih],
             "parallelism": f"row-bands x{n_gpus} (halo = tile overlap, no data-path collective, final NCCL gather of u8 outputs)",
             "l2_policy": "inputs larger than L2 (band raster 1.2 GB, canvas 6.4 GB per GPU)"}
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version at
+    NCCL_DEBUG=WARN, torchrun children inherit the fd), so file descriptor 1 is pointed at stderr for the whole run
+    and the JSON line is written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -164,6 +187,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -301,7 +325,7 @@ def main():
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "tile_mpx_per_s": value * len(tiles) * TILE * TILE / (ih * iw),
                 "unet_tflops_whole_step": len(tiles) * TILE * TILE / 1e6 * UNET_GFLOP_PER_TILE_MPX / 1e3 / (ms_step * 1e-3)}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()
