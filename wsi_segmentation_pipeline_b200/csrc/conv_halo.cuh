@@ -302,6 +302,18 @@ conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant
           uint8_t* ob = planar ? reinterpret_cast<uint8_t*>(p.out) + pl_off + (size_t)((co0 + c_lo + c) >> 3) * (size_t)p.pl_chunk
                                : reinterpret_cast<uint8_t*>(p.out + off0 + c);
           const size_t ostep = planar ? (size_t)p.pl_chunk : 16;
+          if (!planar) {
+#pragma unroll
+            for (int j = 0; j < STEP / 16; ++j) {      // NHWC: 256-bit stores, one full sector each
+              uint32_t w[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(y[16 * j + 2 * t], y[16 * j + 2 * t + 1]);
+                w[t] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              ptx::st_global_256(ob + (size_t)j * 32, w);
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < STEP / 8; ++j) {
             uint32_t w[4];
@@ -311,6 +323,7 @@ conv_halo_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constant
               w[t] = *reinterpret_cast<uint32_t*>(&h2);
             }
             *reinterpret_cast<uint4*>(ob + (size_t)j * ostep) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
           }
         }
       }

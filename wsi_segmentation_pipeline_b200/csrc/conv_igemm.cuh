@@ -175,6 +175,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 256-bit global store / read-only load (sm_100: STG.256 / LDG.256): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
@@ -456,6 +462,18 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             uint8_t* ob = p.out_planar ? reinterpret_cast<uint8_t*>(p.out) + pl_off + (size_t)((co0 + c_lo + c) >> 3) * (size_t)p.pl_chunk
                                        : reinterpret_cast<uint8_t*>(p.out + off0 + c);
             const size_t ostep = p.out_planar ? (size_t)p.pl_chunk : 16;
+            if (STEP == 32 && !p.out_planar) {
+#pragma unroll
+              for (int j = 0; j < STEP / 16; ++j) {
+                uint32_t w[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(y[16 * j + 2 * t], y[16 * j + 2 * t + 1]);
+                  w[t] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                ptx::st_global_256(ob + (size_t)j * 32, w);
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < STEP / 8; ++j) {
               uint32_t w[4];
@@ -465,6 +483,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
                 w[t] = *reinterpret_cast<uint32_t*>(&h2);
               }
               *reinterpret_cast<uint4*>(ob + (size_t)j * ostep) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
             }
           }
         }

@@ -326,16 +326,16 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
           for (int j = 0; j < STEP; ++j) y[j] = fmaxf(y[j], 0.f);
         }
         if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c);
+          uint8_t* ob = reinterpret_cast<uint8_t*>(p.out + off0 + c);
 #pragma unroll
-          for (int j = 0; j < STEP / 8; ++j) {
-            uint32_t w[4];
+          for (int j = 0; j < STEP / 16; ++j) {        // 256-bit stores, one full sector each
+            uint32_t w[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+            for (int t = 0; t < 8; ++t) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(y[16 * j + 2 * t], y[16 * j + 2 * t + 1]);
               w[t] = *reinterpret_cast<uint32_t*>(&h2);
             }
-            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            ptx::st_global_256(ob + (size_t)j * 32, w);
           }
         }
       }

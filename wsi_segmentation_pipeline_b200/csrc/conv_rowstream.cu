@@ -332,6 +332,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
             }
           }
           if (valid && p.out != nullptr) {
+            if (!planar_out) {
+              // NHWC: the 16 channels of this step are 32 contiguous bytes — one 256-bit store (a full sector)
+              uint32_t w[8];
+#pragma unroll
+              for (int tt = 0; tt < 8; ++tt) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(yv[2 * tt], yv[2 * tt + 1]);
+                w[tt] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              ptx::st_global_256(p.out + o_off + (size_t)c * 2, w);
+            } else {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               uint32_t w[4];
@@ -341,6 +351,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
                 w[tt] = *reinterpret_cast<uint32_t*>(&h2);
               }
               *reinterpret_cast<uint4*>(p.out + o_off + (size_t)(c / 8 + k) * o_step) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
             }
           }
         }
