@@ -181,6 +181,11 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8])
                "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
 }
+__device__ __forceinline__ void ld_global_nc_256(const void* ptr, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(ptr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 

@@ -281,7 +281,7 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
       uint4 rcur[STEP / 8], rnext[STEP / 8];
       if (has_res) {
 #pragma unroll
-        for (int j = 0; j < STEP / 8; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0) + j);
+        for (int j = 0; j < STEP / 8; j += 2) ptx::ld_global_nc_256(p.res + off0 + 8 * j, rcur[j], rcur[j + 1]);
       }
 
       ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 14);
@@ -294,7 +294,7 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
         for (int j = 0; j < STEP; j += 16) ptx::tmem_ld16(t_row + (uint32_t)(c + j), *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
         if (has_res && c + STEP < CH) {
 #pragma unroll
-          for (int j = 0; j < STEP / 8; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0 + c + STEP) + j);
+          for (int j = 0; j < STEP / 8; j += 2) ptx::ld_global_nc_256(p.res + off0 + c + STEP + 8 * j, rnext[j], rnext[j + 1]);
         }
         ptx::tmem_ld_wait();
         float y[STEP];

@@ -339,9 +339,9 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_upstream_kernel(const __gr
                 w1[tt] = *reinterpret_cast<uint32_t*>(&o);
               }
               if (valid) {
-                uint4* op = reinterpret_cast<uint4*>(orow + (size_t)(c / 8 + kk) * chunk_step);
-                op[0] = make_uint4(w0[0], w0[1], w0[2], w0[3]);      // pixel 2b
-                op[1] = make_uint4(w1[0], w1[1], w1[2], w1[3]);      // pixel 2b + 1
+                // pixels 2b and 2b + 1 of this channel chunk: 32 contiguous bytes, one 256-bit store
+                const uint32_t w[8] = {w0[0], w0[1], w0[2], w0[3], w1[0], w1[1], w1[2], w1[3]};
+                ptx::st_global_256(orow + (size_t)(c / 8 + kk) * chunk_step, w);
               }
             }
           }
