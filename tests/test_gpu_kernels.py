@@ -65,6 +65,26 @@ def test_gather_normalise_bit_exact(ctx):
     assert border.abs().max().item() == 0.0, "padding / 4th channel must be zero"
 
 
+@pytest.mark.parametrize("pw", [48, 64, 130, 512])
+def test_gather_engine_path_bit_exact(ctx, pw):
+    """The engine's gather as the engine calls it (padded bf16 operand only, no fp32 debug output): every byte
+    misalignment of the row start (3*x0 + y*stride mod 4), tiles that end on the raster's last pixels, host and
+    device-resident rasters — bit-exact with the oracle.  (A variant staging rows through shared memory with aligned
+    4-byte loads and 16-byte pixel-pair stores passed this test but was 25 % slower; see profiles/r01_notes.md.)"""
+    ih, iw, ph = 70, 2 * pw + 137, 8
+    raster = synth.synth_slide(ih, iw, 7 + pw)
+    xs = [0, 1, 2, 3, 5, 10, iw - pw - 1, iw - pw]                    # the last one touches the final pixel of every row
+    tiles = np.array([[x, y] for x in xs for y in (0, 1, ih - ph)], np.int32)
+    ref = _bf16_round(O.gather_tiles(raster, [tuple(t) for t in tiles], ph, pw))
+    for src in (raster, torch.from_numpy(raster).cuda()):
+        sl = ctx.slide_desc(src, ih, iw, ph, pw)
+        pad = ctx.debug_gather(sl, tiles, want_padded=True, want_norm=False).cpu().to(torch.float32)
+        assert torch.equal(pad[:, 3:3 + ph, 3:3 + pw, :3].permute(0, 3, 1, 2), ref)
+        border = pad.clone()
+        border[:, 3:3 + ph, 3:3 + pw, :3] = 0
+        assert border.abs().max().item() == 0.0
+
+
 def test_gather_from_device_raster_and_band(ctx):
     ih, iw, ph, pw = 256, 320, 64, 64
     raster = synth.synth_slide(ih, iw, 5)

@@ -444,15 +444,18 @@ class Context:
             C.c_void_p(y.data_ptr()), _stream_ptr(None)), self._h)
         return y
 
-    def debug_gather(self, slide: SlideDesc, tiles_xy, want_padded=False):
+    def debug_gather(self, slide: SlideDesc, tiles_xy, want_padded=False, want_norm=True):
+        """want_norm=False runs the kernel exactly as the engine does (padded bf16 operand only: the staged fast path)."""
         import torch
         tiles_xy = np.ascontiguousarray(tiles_xy, dtype=np.int32).reshape(-1, 2)
         n = tiles_xy.shape[0]
         dev = torch.device("cuda", self.device)
-        norm = torch.empty((n, 3, slide.ph, slide.pw), dtype=torch.float32, device=dev)
+        norm = torch.empty((n, 3, slide.ph, slide.pw), dtype=torch.float32, device=dev) if want_norm else None
         padded = torch.empty((n, slide.ph + 6, slide.pw + 8, 4), dtype=torch.bfloat16, device=dev) if want_padded else None
-        _check(self._lib.wsi_debug_gather(self._h, C.byref(slide), _np_ptr(tiles_xy), n, C.c_void_p(norm.data_ptr()),
+        _check(self._lib.wsi_debug_gather(self._h, C.byref(slide), _np_ptr(tiles_xy), n, C.c_void_p(norm.data_ptr()) if want_norm else None,
                                           C.c_void_p(padded.data_ptr()) if want_padded else None, _stream_ptr(None)), self._h)
+        if not want_norm:
+            return padded
         return (norm, padded) if want_padded else norm
 
     def debug_stem(self, slide: SlideDesc, tiles_xy, weight, scale=None, bias=None):
