@@ -53,6 +53,16 @@ typedef enum { WSI_HEAD_SEG = 0, WSI_HEAD_CLS = 1, WSI_HEAD_REG = 2, WSI_HEAD_FE
 
 typedef enum { WSI_MEM_HOST = 0, WSI_MEM_DEVICE = 1 } wsi_mem_kind;
 
+/* Arithmetic of the network (wsi_set_option "precision").  The reference runs fp32 end to end (utils/eval.py:196-200;
+ * AMP is commented out, train.py:14-15,101-102).
+ *   WSI_PRECISION_BF16  bf16 operands (activations and weights rounded once), fp32 accumulation in TMEM, fp32 BN /
+ *                       residual / ReLU epilogues: the throughput mode (north_star tolerance 1e-2 / 99.9 % argmax).
+ *   WSI_PRECISION_FP32  fp32 emulated on the same bf16 tensor cores: every activation and weight is the exact sum of
+ *                       three bf16 planes (8+8+8 mantissa bits = the fp32 value) and every K block issues the six plane
+ *                       products of weight >= 2^-24; fp32 accumulation.  Matches an fp32 evaluation to fp32 rounding
+ *                       noise (north_star tolerance 1e-4 on probabilities); ~6x the MMA work, 3x the activation bytes. */
+typedef enum { WSI_PRECISION_BF16 = 0, WSI_PRECISION_FP32 = 1 } wsi_precision;
+
 /* One fp32 state_dict entry (host memory), named exactly as in the reference's checkpoints
  * (utils/networks.py:6-10 -> model.load_state_dict(state['state_dict'])). */
 typedef struct {
@@ -95,10 +105,13 @@ WSI_API int wsi_ctx_create(int device, wsi_ctx** out);
 WSI_API int wsi_ctx_destroy(wsi_ctx* ctx);
 WSI_API const char* wsi_last_error(wsi_ctx* ctx);           /* ctx may be NULL: last global error       */
 WSI_API const char* wsi_version(void);
-/* knobs: "batch_tiles" (tiles per forward batch, 0 = auto), "stage_timing" (0/1)               */
+/* knobs: "batch_tiles" (tiles per forward batch, 0 = auto), "stage_timing" (0/1), "precision" (wsi_precision) */
 WSI_API int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value);
 WSI_API int wsi_set_class_probs(wsi_ctx* ctx, const float* p, int n);   /* myargs.py:15 class_probs     */
 WSI_API int64_t wsi_kernel_launches(wsi_ctx* ctx);          /* kernels launched by this ctx so far      */
+/* Synchronise `stream` and report a device-side failure of an earlier asynchronous call (the conv kernels' pipeline
+ * barriers time out instead of hanging and raise a sticky flag).  Calls with WSI_MEM_HOST outputs do this themselves. */
+WSI_API int wsi_check(wsi_ctx* ctx, void* stream);
 
 /* ---- model (replaces model.load_state_dict + .cuda(), eval_tumorbed.py:30-46) ---------------- */
 WSI_API int wsi_model_load(wsi_ctx* ctx, int arch, const wsi_tensor_desc* tensors, int n, int num_classes);
@@ -185,6 +198,12 @@ WSI_API int wsi_debug_conv(wsi_ctx* ctx, const void* x, int n, int h, int w, int
                    const float* wt, int cout, int ksize, int stride, int pad,
                    const float* scale, const float* bias, const void* res, int relu,
                    int up2, const void* skip, int cskip, void* y, void* stream);
+/* the same conv in the fp32-emulated precision (WSI_PRECISION_FP32): x / res / skip / y are f32 NHWC device tensors
+ * (split into three bf16 planes, convolved with the six plane products, merged back) — per-layer accuracy tests */
+WSI_API int wsi_debug_conv_f32(wsi_ctx* ctx, const float* x, int n, int h, int w, int cin,
+                       const float* wt, int cout, int ksize, int stride, int pad,
+                       const float* scale, const float* bias, const float* res, int relu,
+                       int up2, const float* skip, int cskip, float* y, void* stream);
 /* K0 alone: tiles cut from the raster by the fused gather + normalise kernel.
  * norm_out: f32 [n,3,ph,pw] (device) = standard_augmentor(True) output, bit-exact
  * (utils/preprocessing.py:209-212); padded_out: bf16 [n,ph+6,pw+8,4] (device) = the stem operand

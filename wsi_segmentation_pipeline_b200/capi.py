@@ -20,6 +20,7 @@ ERR_NAMES = {-1: "WSI_ERR_INVALID", -2: "WSI_ERR_CUDA", -3: "WSI_ERR_NOMODEL", -
 ARCH_RESNET18, ARCH_UNET_R18 = 0, 1
 HEAD_SEG, HEAD_CLS, HEAD_REG, HEAD_FEATURES = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
+PRECISION_BF16, PRECISION_FP32 = 0, 1
 STAGES = ("gather", "stem", "maxpool", "conv", "head", "stitch", "finalise", "h2d", "d2h")
 
 # every symbol include/wsi_b200.h declares (tests check the library exports exactly these)
@@ -30,7 +31,7 @@ SYMBOLS = (
     "wsi_synth_slide", "wsi_debug_conv", "wsi_debug_gather", "wsi_debug_stem", "wsi_debug_maxpool",
     "wsi_stage_stats", "wsi_stage_reset", "wsi_resize_argmax",
     "wsi_find_nuclei", "wsi_plan_tiles_gpu", "wsi_forward_patches",
-    "wsi_forward_batch_tta", "wsi_debug_umma_shift",
+    "wsi_forward_batch_tta", "wsi_debug_umma_shift", "wsi_check", "wsi_debug_conv_f32",
 )
 
 
@@ -90,6 +91,9 @@ def lib() -> C.CDLL:
         "wsi_synth_slide": (C.c_int, [vp, i64, i64, C.c_uint32, i64, i64, vp, vp, i64, vp, vp]),
         "wsi_debug_conv": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                      vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
+        "wsi_debug_conv_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
+        "wsi_check": (C.c_int, [vp, vp]),
         "wsi_debug_gather": (C.c_int, [vp, C.POINTER(SlideDesc), vp, C.c_int, vp, vp, vp]),
         "wsi_debug_stem": (C.c_int, [vp, C.POINTER(SlideDesc), vp, C.c_int, vp, vp, vp, vp, vp]),
         "wsi_debug_maxpool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
@@ -210,6 +214,14 @@ class Context:
     # ---- knobs -------------------------------------------------------------------------
     def set_option(self, key: str, value: int):
         _check(self._lib.wsi_set_option(self._h, key.encode(), int(value)), self._h)
+
+    def set_precision(self, precision: int):
+        """PRECISION_BF16 (throughput) or PRECISION_FP32 (fp32 emulated on the bf16 tensor cores; include/wsi_b200.h)."""
+        self.set_option("precision", int(precision))
+
+    def check(self, stream=None):
+        """Synchronise and raise if an earlier asynchronous (device-output) call failed on the device."""
+        _check(self._lib.wsi_check(self._h, _stream_ptr(stream)), self._h)
 
     def set_class_probs(self, probs):
         arr = (C.c_float * 4)(*[float(p) for p in probs])
@@ -438,6 +450,24 @@ class Context:
         sc = None if scale is None else np.ascontiguousarray(scale.detach().cpu().numpy(), dtype=np.float32)
         bi = None if bias is None else np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
         _check(self._lib.wsi_debug_conv(
+            self._h, C.c_void_p(x_nhwc.data_ptr()), n, h, w, cin, _np_ptr(wt), cout, k, stride, pad, _np_ptr(sc), _np_ptr(bi),
+            C.c_void_p(res.data_ptr()) if res is not None else None, int(relu), int(up2),
+            C.c_void_p(skip.data_ptr()) if skip is not None else None, 0 if skip is None else skip.shape[-1],
+            C.c_void_p(y.data_ptr()), _stream_ptr(None)), self._h)
+        return y
+
+    def debug_conv_f32(self, x_nhwc, weight, stride=1, pad=1, scale=None, bias=None, res=None, relu=False, up2=False, skip=None):
+        """The fp32-emulated conv (PRECISION_FP32).  x_nhwc / res / skip: f32 CUDA NHWC; weight f32 CPU OIHW.  Returns f32 CUDA NHWC."""
+        import torch
+        n, h, w, cin = x_nhwc.shape
+        cout, _, k, _ = weight.shape
+        hin, win = (2 * h, 2 * w) if up2 else (h, w)
+        oh, ow = (hin + 2 * pad - k) // stride + 1, (win + 2 * pad - k) // stride + 1
+        y = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x_nhwc.device)
+        wt = np.ascontiguousarray(weight.detach().cpu().numpy(), dtype=np.float32)
+        sc = None if scale is None else np.ascontiguousarray(scale.detach().cpu().numpy(), dtype=np.float32)
+        bi = None if bias is None else np.ascontiguousarray(bias.detach().cpu().numpy(), dtype=np.float32)
+        _check(self._lib.wsi_debug_conv_f32(
             self._h, C.c_void_p(x_nhwc.data_ptr()), n, h, w, cin, _np_ptr(wt), cout, k, stride, pad, _np_ptr(sc), _np_ptr(bi),
             C.c_void_p(res.data_ptr()) if res is not None else None, int(relu), int(up2),
             C.c_void_p(skip.data_ptr()) if skip is not None else None, 0 if skip is None else skip.shape[-1],

@@ -42,6 +42,14 @@ void set_global_error(const std::string& m);
     if (!(cond)) WSI_THROW((status), __VA_ARGS__); \
   } while (0)
 
+// Timing-only experiment switches inside the conv kernels (WSI_STREAM_DBG / WSI_UP_DBG: skip MMAs, skip loads ... —
+// results are garbage) exist only in builds with -DWSI_DEBUG_SWITCHES; release builds compile them out.
+#ifdef WSI_DEBUG_SWITCHES
+#define WSI_DBG(p) ((p).dbg)
+#else
+#define WSI_DBG(p) 0
+#endif
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

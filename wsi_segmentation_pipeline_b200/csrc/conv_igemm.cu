@@ -77,21 +77,33 @@ static void choose_box(int A_h, int A_w, int* bw, int* bh, int* bn) {
   *bn = kBlockM / (*bw * *bh);
 }
 
-// plain NHWC view
-static void map_plain(CUtensorMap* m, const TensorView& t, int block_k, int bw, int bh, int bn) {
-  const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)t.W, (uint64_t)t.H, (uint64_t)t.N};
-  const uint64_t st[3] = {(uint64_t)t.C * 2, (uint64_t)t.W * t.C * 2, (uint64_t)t.H * t.W * t.C * 2};
+// plain NHWC view (planes: 1, or 3 channel blocks [a | b | c] of the fp32 emulation)
+static void map_plain(CUtensorMap* m, const TensorView& t, int block_k, int bw, int bh, int bn, int planes = 1) {
+  const uint64_t C = (uint64_t)t.C * planes;
+  const uint64_t dims[4] = {C, (uint64_t)t.W, (uint64_t)t.H, (uint64_t)t.N};
+  const uint64_t st[3] = {C * 2, (uint64_t)t.W * C * 2, (uint64_t)t.H * t.W * C * 2};
   const uint32_t box[4] = {(uint32_t)block_k, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
   encode4(m, t.ptr, dims, st, box, block_k);
 }
 // (hp, wp) parity view: element (a, b) = t[2a+hp, 2b+wp]
-static void map_parity(CUtensorMap* m, const TensorView& t, int hp, int wp, int block_k, int bw, int bh, int bn) {
-  const char* base = static_cast<const char*>(t.ptr) + ((size_t)hp * t.W + wp) * t.C * 2;
-  const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)((t.W - wp + 1) / 2), (uint64_t)((t.H - hp + 1) / 2), (uint64_t)t.N};
-  const uint64_t st[3] = {(uint64_t)t.C * 4, (uint64_t)t.W * t.C * 4, (uint64_t)t.H * t.W * t.C * 2};
+static void map_parity(CUtensorMap* m, const TensorView& t, int hp, int wp, int block_k, int bw, int bh, int bn, int planes = 1) {
+  const uint64_t C = (uint64_t)t.C * planes;
+  const char* base = static_cast<const char*>(t.ptr) + ((size_t)hp * t.W + wp) * C * 2;
+  const uint64_t dims[4] = {C, (uint64_t)((t.W - wp + 1) / 2), (uint64_t)((t.H - hp + 1) / 2), (uint64_t)t.N};
+  const uint64_t st[3] = {C * 4, (uint64_t)t.W * C * 4, (uint64_t)t.H * t.W * C * 2};
   const uint32_t box[4] = {(uint32_t)block_k, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
   encode4(m, base, dims, st, box, block_k);
 }
+
+// fp32 -> three bf16 planes a + b + c == v exactly (8 + 8 + 8 mantissa bits)
+static inline void split3(float v, uint16_t out[3]) {
+  float r = v;
+  for (int j = 0; j < 3; ++j) {
+    out[j] = f32_to_bf16_bits(r);
+    r -= bf16_bits_to_f32(out[j]);
+  }
+}
+static const int kSplitBHost[6] = {0, 1, 0, 1, 2, 0};   // weight plane of product pr (kSplitB in conv_igemm.cuh)
 
 static inline int floor_div2(int t) { return (t >= 0) ? t / 2 : -((-t + 1) / 2); }
 
@@ -107,11 +119,20 @@ bool ConvOp::routes_to_upstream(const std::vector<ConvInputPart>& parts, const C
 void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
                    const float* scale, const float* bias, const void* residual, void* out,
                    const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms, int out_layout,
-                   int res_layout) {
+                   int res_layout, int split) {
   WSI_REQUIRE(!parts.empty() && parts.size() <= 2, WSI_ERR_INVALID, "conv: 1 or 2 input parts");
   stream_.reset();
   upstream_.reset();
-  if (head_out == nullptr && routes_to_upstream(parts, spec, residual, out_layout)) {
+  split_ = split ? 1 : 0;
+  const int planes = split_ ? 3 : 1, nprod = split_ ? 6 : 1;
+  if (split_) {
+    // fp32 emulation: always the table-driven TMA kernel on NHWC [a | b | c] tensors
+    WSI_REQUIRE(out_layout == LAYOUT_NHWC && res_layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv (fp32 emulation): NHWC only");
+    row_.reset();
+    stem_.reset();
+    halo_ = false;
+  }
+  if (!split_ && head_out == nullptr && routes_to_upstream(parts, spec, residual, out_layout)) {
     upstream_.reset(new UpStreamOp());
     upstream_->build(parts, spec, w_oihw, scale, bias, out, error_flag, num_sms);
     flops_ = upstream_->flops();
@@ -121,7 +142,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
     stem_.reset();
     return;
   }
-  if (routes_to_rowtile(parts, spec, residual) && RowStreamOp::eligible(parts, spec) && getenv("WSI_NO_ROWSTREAM") == nullptr) {
+  if (!split_ && routes_to_rowtile(parts, spec, residual) && RowStreamOp::eligible(parts, spec) && getenv("WSI_NO_ROWSTREAM") == nullptr) {
     stream_.reset(new RowStreamOp());
     stream_->build(parts[0], spec, w_oihw, scale, bias, residual, res_layout, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
     flops_ = stream_->flops();
@@ -131,7 +152,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
     stem_.reset();
     return;
   }
-  if (routes_to_rowtile(parts, spec, residual)) {
+  if (!split_ && routes_to_rowtile(parts, spec, residual)) {
     row_.reset(new RowConvOp());
     row_->build(parts, spec, w_oihw, scale, bias, residual, res_layout, out, out_layout, head_w, head_b, head_out, error_flag, num_sms);
     flops_ = row_->flops();
@@ -148,7 +169,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   out_planar_ = (out_layout == LAYOUT_PLANAR);
   for (auto& q : parts) WSI_REQUIRE(q.t.layout == LAYOUT_NHWC, WSI_ERR_UNSUPPORTED, "conv: the TMA kernel reads NHWC operands");
   halo_ = false;
-  if (halo_eligible(parts, spec, out_layout, head_out != nullptr, num_sms)) {
+  if (!split_ && halo_eligible(parts, spec, out_layout, head_out != nullptr, num_sms)) {
     build_halo(parts, spec, w_oihw, scale, bias, residual, out, out_layout, error_flag, num_sms);
     return;
   }
@@ -172,7 +193,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   // and there are still enough tiles for every SM.
   int bn_out = 128;
   while (spec.cout % bn_out) bn_out /= 2;
-  if (spec.cout % 256 == 0 && bk == 64 && getenv("WSI_NO_BN256") == nullptr) {
+  if (!split_ && spec.cout % 256 == 0 && bk == 64 && getenv("WSI_NO_BN256") == nullptr) {
     // a 128x256 tile does twice the math of a 128x128 one in ~1.6x the time (operand bytes 48 KB vs 32 KB per
     // K block); take it unless wave quantisation over the SMs eats that
     const long long m_tiles = ceil_div((long long)N * OH * OW, kBlockM);
@@ -189,7 +210,6 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   p.res = static_cast<const bf16*>(residual);
   p.out = static_cast<bf16*>(out);
   p.error_flag = error_flag;
-  if (const char* e = getenv("WSI_IGEMM_DBG")) p.dbg = atoi(e);
   if (out_planar_) {
     WSI_REQUIRE(spec.cout % 8 == 0, WSI_ERR_UNSUPPORTED, "conv: planar output needs Cout %% 8 == 0");
     const PlanarDims od = PlanarDims::make(OH, OW, spec.cout, LAYOUT_PLANAR);
@@ -215,15 +235,22 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
 
   // tensor maps
   if (any_up) {
-    map_plain(&amaps_.m[0], parts[0].t, bk, p.bw, p.bh, p.bn);
+    map_plain(&amaps_.m[0], parts[0].t, bk, p.bw, p.bh, p.bn, planes);
+    p.a_plane[0] = parts[0].t.C;
     if (parts.size() == 2)
       for (int hp = 0; hp < 2; ++hp)
-        for (int wp = 0; wp < 2; ++wp) map_parity(&amaps_.m[1 + hp * 2 + wp], parts[1].t, hp, wp, bk, p.bw, p.bh, p.bn);
+        for (int wp = 0; wp < 2; ++wp) {
+          map_parity(&amaps_.m[1 + hp * 2 + wp], parts[1].t, hp, wp, bk, p.bw, p.bh, p.bn, planes);
+          p.a_plane[1 + hp * 2 + wp] = parts[1].t.C;
+        }
   } else if (spec.stride == 1) {
-    for (size_t i = 0; i < parts.size(); ++i) map_plain(&amaps_.m[i], parts[i].t, bk, p.bw, p.bh, p.bn);
+    for (size_t i = 0; i < parts.size(); ++i) { map_plain(&amaps_.m[i], parts[i].t, bk, p.bw, p.bh, p.bn, planes); p.a_plane[i] = parts[i].t.C; }
   } else {
     for (int hp = 0; hp < 2; ++hp)
-      for (int wp = 0; wp < 2; ++wp) map_parity(&amaps_.m[hp * 2 + wp], parts[0].t, hp, wp, bk, p.bw, p.bh, p.bn);
+      for (int wp = 0; wp < 2; ++wp) {
+        map_parity(&amaps_.m[hp * 2 + wp], parts[0].t, hp, wp, bk, p.bw, p.bh, p.bn, planes);
+        p.a_plane[hp * 2 + wp] = parts[0].t.C;
+      }
   }
   for (int i = 0; i < kMaxAMaps; ++i)  // unused slots alias map 0 so every descriptor is valid
     if (i >= (any_up ? (parts.size() == 2 ? 5 : 1) : (spec.stride == 1 ? (int)parts.size() : 4))) amaps_.m[i] = amaps_.m[0];
@@ -236,8 +263,15 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   for (auto& q : parts) kb_per_par += (q.t.C / bk) * ((any_up && q.up2) ? 4 : taps);
   const int num_kb = kb_per_par;
   WSI_REQUIRE(num_kb <= 128, WSI_ERR_UNSUPPORTED, "conv: %d K blocks > 128", num_kb);
-  const int K = num_kb * bk;
+  const int K = num_kb * nprod * bk;               // per parity class; fp32 emulation: 6 plane products per K block
   const int wsets = any_up ? 4 : 1;
+  // weight element (co, K block kbi, j) = v: bf16(v), or its three planes laid out per product
+  auto put_w = [&](std::vector<uint16_t>& wp_, size_t row_base, int kbi, int j, float v) {
+    if (!split_) { wp_[row_base + (size_t)kbi * bk + j] = f32_to_bf16_bits(v); return; }
+    uint16_t pl[3];
+    split3(v, pl);
+    for (int pr = 0; pr < 6; ++pr) wp_[row_base + ((size_t)kbi * 6 + pr) * bk + j] = pl[kSplitBHost[pr]];
+  };
   std::vector<uint16_t> wp((size_t)spec.cout * K * wsets);
   const size_t Ktot = (size_t)K * wsets;          // row length of the packed [Cout][wsets*K] matrix
   auto w_at = [&](int co, int ci, int r, int s) { return w_oihw[(((size_t)co * cin + ci) * k + r) * k + s]; };
@@ -262,7 +296,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
                     const int dy = floor_div2(py + r - 1) - floor_div2(py - 1), dx = floor_div2(px + s2 - 1) - floor_div2(px - 1);
                     if (dy * 2 + dx == pos) v += w_at(co, part_off + c0 + j, r, s2);
                   }
-                wp[(size_t)co * Ktot + (size_t)par * K + (size_t)kbi * bk + j] = f32_to_bf16_bits(v);
+                put_w(wp, (size_t)co * Ktot + (size_t)par * K, kbi, j, v);
               }
             table.push_back(e);
             ++kbi;
@@ -286,7 +320,7 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
               }
               for (int co = 0; co < spec.cout; ++co)
                 for (int j = 0; j < bk; ++j)
-                  wp[(size_t)co * Ktot + (size_t)par * K + (size_t)kbi * bk + j] = f32_to_bf16_bits(w_at(co, part_off + c0 + j, r, s2));
+                  put_w(wp, (size_t)co * Ktot + (size_t)par * K, kbi, j, w_at(co, part_off + c0 + j, r, s2));
               table.push_back(e);
               ++kbi;
             }
@@ -308,14 +342,23 @@ void ConvOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec
   finish(table, num_parity, wp, K * wsets, scale, bias, num_sms);
 }
 
+void ConvOp::set_head_out(float* ptr) {
+  WSI_REQUIRE(ptr != nullptr, WSI_ERR_INVALID, "set_head_out: NULL");
+  if (stream_) { stream_->set_head_out(ptr); return; }
+  if (row_) { row_->set_head_out(ptr); return; }
+  WSI_REQUIRE(p_.head_out != nullptr, WSI_ERR_INVALID, "set_head_out: this conv has no fused head");
+  p_.head_out = ptr;
+}
+
 bool ConvOp::stem_routes_to_rowtile() { return getenv("WSI_NO_ROWTILE") == nullptr; }
 
 void ConvOp::build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw, const float* scale,
-                        const float* bias, void* out, int* error_flag, int num_sms, int out_layout) {
+                        const float* bias, void* out, int* error_flag, int num_sms, int out_layout, int split) {
   WSI_REQUIRE(ph % 2 == 0 && pw % 2 == 0, WSI_ERR_UNSUPPORTED, "stem: tile size must be even");
   row_.reset();
   stream_.reset();
-  if (stem_routes_to_rowtile()) {
+  split_ = split ? 1 : 0;
+  if (!split_ && stem_routes_to_rowtile()) {
     stem_.reset(new RowStemOp());
     stem_->build(padded_tiles, n, ph, pw, w_oihw, scale, bias, out, out_layout, error_flag, num_sms);
     flops_ = stem_->flops();
@@ -332,17 +375,21 @@ void ConvOp::build_stem(const void* padded_tiles, int n, int ph, int pw, const f
   p.relu = 1; p.out = static_cast<bf16*>(out); p.error_flag = error_flag;
   choose_box(p.A_h, p.A_w, &p.bw, &p.bh, &p.bn);
   const uint64_t pitch = (uint64_t)(pw + 8) * 8, tile_bytes = (uint64_t)(ph + 6) * pitch;
-  for (int hp = 0; hp < 2; ++hp) {
-    // overlapping-window view: dim0 = 32 elements (8 px x 4 ch) starting every 2 px (16 B)
-    const char* base = static_cast<const char*>(padded_tiles) + hp * pitch;
-    const uint64_t dims[4] = {32, (uint64_t)p.OW, (uint64_t)((ph + 6) / 2), (uint64_t)n};
-    const uint64_t st[3] = {16, 2 * pitch, tile_bytes};
-    const uint32_t box[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    encode4(&amaps_.m[hp], base, dims, st, box, 32);
-  }
-  for (int i = 2; i < kMaxAMaps; ++i) amaps_.m[i] = amaps_.m[0];
+  // fp32 emulation: the gather writes three padded-tile buffers (planes a, b, c) back to back; plane j = maps 2j, 2j+1
+  const int planes = split_ ? 3 : 1, nprod = split_ ? 6 : 1;
+  for (int pl = 0; pl < planes; ++pl)
+    for (int hp = 0; hp < 2; ++hp) {
+      // overlapping-window view: dim0 = 32 elements (8 px x 4 ch) starting every 2 px (16 B)
+      const char* base = static_cast<const char*>(padded_tiles) + (size_t)pl * n * tile_bytes + hp * pitch;
+      const uint64_t dims[4] = {32, (uint64_t)p.OW, (uint64_t)((ph + 6) / 2), (uint64_t)n};
+      const uint64_t st[3] = {16, 2 * pitch, tile_bytes};
+      const uint32_t box[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      encode4(&amaps_.m[pl * 2 + hp], base, dims, st, box, 32);
+    }
+  for (int i = 2 * planes; i < kMaxAMaps; ++i) amaps_.m[i] = amaps_.m[0];
+  p.split_map_step = split_ ? 2 : 0;
   std::vector<KBlock> table;
-  const int K = 7 * 32;
+  const int K = 7 * 32 * nprod;
   std::vector<uint16_t> wp((size_t)64 * K, 0);
   for (int r = 0; r < 7; ++r) {
     KBlock e{};
@@ -350,8 +397,13 @@ void ConvOp::build_stem(const void* padded_tiles, int n, int ph, int pw, const f
     table.push_back(e);
     for (int co = 0; co < 64; ++co)
       for (int s = 0; s < 7; ++s)
-        for (int c = 0; c < 3; ++c)
-          wp[(size_t)co * K + r * 32 + s * 4 + c] = f32_to_bf16_bits(w_oihw[(((size_t)co * 3 + c) * 7 + r) * 7 + s]);
+        for (int c = 0; c < 3; ++c) {
+          const float v = w_oihw[(((size_t)co * 3 + c) * 7 + r) * 7 + s];
+          if (!split_) { wp[(size_t)co * K + r * 32 + s * 4 + c] = f32_to_bf16_bits(v); continue; }
+          uint16_t pl3[3];
+          split3(v, pl3);
+          for (int pr = 0; pr < 6; ++pr) wp[(size_t)co * K + (r * 6 + pr) * 32 + s * 4 + c] = pl3[kSplitBHost[pr]];
+        }
   }
   p.num_kb = 7;
   flops_ = 2.0 * n * p.OH * p.OW * 64.0 * 147.0;
@@ -379,14 +431,14 @@ void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std:
   grid_ = (int)std::min<long long>(total, num_sms);
   {
     const int bbytes = (block_n_ * block_k_ * 2 + 1023) / 1024 * 1024;
-    resb_ = (p.tiles_co == 1) && (block_k_ == 64) && (block_n_ == 64 || block_n_ == 128) &&
+    resb_ = !split_ && (p.tiles_co == 1) && (block_k_ == 64) && (block_n_ == 64 || block_n_ == 128) &&
             ((long long)p.num_kb * bbytes <= kResidentBBytes) && p.b_parity_stride == 0 && getenv("WSI_NO_RESB") == nullptr;
   }
   // CTA pairs (conv_pair.cuh): a 128 x N x 16 MMA costs ~64 + N/2 cycles on one CTA and ~64 + N/4 per CTA of a pair
   // (operand-fetch bound, measured); take the pair kernel when that beats the single-CTA schedule after wave
   // quantisation (pairs run on num_sms / 2 SM pairs)
   pair_ = false;
-  if (block_k_ == 64 && p.Cout % 128 == 0 && !resb_ && p.head_out == nullptr && !p.out_planar && num_sms >= 2 && getenv("WSI_NO_PAIR") == nullptr) {
+  if (!split_ && block_k_ == 64 && p.Cout % 128 == 0 && !resb_ && p.head_out == nullptr && !p.out_planar && num_sms >= 2 && getenv("WSI_NO_PAIR") == nullptr) {
     const int bnp = (p.Cout % 256 == 0) ? 256 : 128;
     const long long pair_tiles = (tiles_m + 1) / 2 * (p.Cout / bnp) * num_parity;
     const long long cost_single = ceil_div(total, num_sms) * (64 + block_n_ / 2);
@@ -403,16 +455,16 @@ void ConvOp::finish(const std::vector<KBlock>& table, int num_parity, const std:
   CUDA_CHECK(cudaStreamSynchronize(0));   // uploads above used the default stream
 }
 
-template <int BN, int BK, bool RESB = false>
+template <int BN, int BK, bool RESB = false, int NSPLIT = 1>
 static void launch_inst(const AMaps& am, const CUtensorMap& bm, const ConvParams& p, int grid, cudaStream_t s) {
   using S = ConvSmem<BN, BK, RESB>;
   static_assert(S::kTotal <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, RESB, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  conv_igemm_kernel<BN, BK, RESB><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);
+  conv_igemm_kernel<BN, BK, RESB, NSPLIT><<<grid, kNumThreads, S::kTotal, s>>>(am, bm, p);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -653,6 +705,15 @@ void ConvOp::launch(cudaStream_t stream, LaunchCounter* lc) const {
     else launch_pair<128>(amaps_, bmap_, p_, grid_, stream);
     if (lc) lc->n++;
     return;
+  }
+  if (split_) {
+#define WSI_SPLIT_CASE(BN, BK) \
+  if (block_n_ == BN && block_k_ == BK) { launch_inst<BN, BK, false, 3>(amaps_, bmap_, p_, grid_, stream); if (lc) lc->n++; return; }
+    WSI_SPLIT_CASE(128, 64) WSI_SPLIT_CASE(64, 64) WSI_SPLIT_CASE(32, 64) WSI_SPLIT_CASE(16, 64)
+    WSI_SPLIT_CASE(128, 32) WSI_SPLIT_CASE(64, 32) WSI_SPLIT_CASE(32, 32) WSI_SPLIT_CASE(16, 32)
+    WSI_SPLIT_CASE(128, 16) WSI_SPLIT_CASE(64, 16) WSI_SPLIT_CASE(32, 16) WSI_SPLIT_CASE(16, 16)
+#undef WSI_SPLIT_CASE
+    WSI_THROW(WSI_ERR_UNSUPPORTED, "conv (fp32 emulation): no kernel instance for BLOCK_N=%d BLOCK_K=%d", block_n_, block_k_);
   }
   if (resb_) {
     if (block_n_ == 64) launch_inst<64, 64, true>(amaps_, bmap_, p_, grid_, stream);

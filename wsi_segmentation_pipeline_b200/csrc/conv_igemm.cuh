@@ -35,7 +35,7 @@
 
 namespace wsi {
 
-constexpr int kMaxAMaps = 5;
+constexpr int kMaxAMaps = 6;
 constexpr int kBlockM = 128;
 constexpr int kNumThreads = 320;     // TMA producer warp, MMA issuer warp, 8 epilogue warps
 
@@ -69,9 +69,19 @@ struct ConvParams {
   long long pl_img, pl_row, pl_chunk;   // its byte strides: image, image row, 8-channel chunk row (entry = x + 8, 16 B each)
   const struct HaloGroup* hgroups;   // halo-resident kernel (conv_halo.cuh): [num_parity][num_kb] groups
   int halo_plain;             // ... plain 3x3/s1 conv: every group is one 64-channel chunk with the 9 taps in (r, s) order
-  int dbg;                    // timing experiments only (WSI_IGEMM_DBG; results are garbage): 1 no MMAs, 2 no TMA loads,
-                              // 3 A loads only, 4 B loads only
+  // fp32-emulated precision (NSPLIT = 3): every bf16 tensor is three planes a + b + c = the fp32 value (8 + 8 + 8
+  // mantissa bits, exact), activations as channel blocks [a | b | c] of one NHWC tensor (stem: three tensors), weights
+  // as three packed matrices; each K block issues the 6 plane products whose weight is >= 2^-24:
+  // (a,a) (a,b) (b,a) (b,b) (a,c) (c,a).  A plane j of map m is reached by channel offset j * a_plane[m] and map
+  // offset j * split_map_step.
+  int a_plane[kMaxAMaps];
+  int split_map_step;
+  int dbg;                    // -DWSI_DEBUG_SWITCHES builds only (pair kernel timing experiments)
 };
+
+// plane pairs of the fp32 emulation, smallest weights last
+__device__ __constant__ const int8_t kSplitA[6] = {0, 0, 1, 1, 0, 2};
+__device__ __constant__ const int8_t kSplitB[6] = {0, 1, 0, 1, 2, 0};
 
 struct AMaps {
   CUtensorMap m[kMaxAMaps];
@@ -236,9 +246,11 @@ struct ConvSmem {
 // RESB: convs whose whole weight tensor fits in kResidentBBytes (one output-channel tile) load B ONCE per CTA
 // and the stage ring carries only A — the mainloop is bound by the TMA box-row rate, and B is a third (N=64)
 // to a half (N=128) of the rows of a K block.
-template <int BLOCK_N, int BLOCK_K, bool RESB = false>
+template <int BLOCK_N, int BLOCK_K, bool RESB = false, int NSPLIT = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap bmap, const ConvParams p) {
+  static_assert(NSPLIT == 1 || (NSPLIT == 3 && !RESB), "NSPLIT: 1 (bf16) or 3 (fp32 emulation, streamed weights)");
+  constexpr int NPROD = (NSPLIT == 3) ? 6 : 1;      // plane products per K block
   using S = ConvSmem<BLOCK_N, BLOCK_K, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -306,30 +318,27 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
         const KBlock* kb_tbl = tbl + par * num_kb;
         for (int kb = 0; kb < num_kb; ++kb) {
           const KBlock e = kb_tbl[kb];      // read BEFORE the wait (asm volatile + memory clobber would pin it after)
-          ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 1);
-          if (p.dbg >= 2) {
-            const bool la = (p.dbg == 3), lb = (p.dbg == 4) && !RESB;
-            ptx::mbar_expect_tx(&full[stage], (la ? S::kABytes : 0) + (lb ? S::kBBytesRaw : 0));
+#pragma unroll 1
+          for (int pr = 0; pr < NPROD; ++pr) {
+            int mi = e.map, c0 = e.c0;
+            if (NSPLIT == 3) { mi += kSplitA[pr] * p.split_map_step; c0 += kSplitA[pr] * p.a_plane[e.map]; }
+            ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 1);
+            ptx::mbar_expect_tx(&full[stage], RESB ? S::kABytes : S::kABytes + S::kBBytesRaw);
             uint8_t* sA = stage_base + stage * S::kStageBytes;
-            if (la) ptx::tma_load_4d(sA, &amaps.m[0], &full[stage], 0, b0, a0, n0);
-            if (lb) ptx::tma_load_2d(sA + S::kABytes, &bmap, &full[stage], par * p.b_parity_stride + kb * BLOCK_K, co0);
+            uint8_t* sB = sA + S::kABytes;
+            const CUtensorMap* am = &amaps.m[0];
+            switch (mi) {
+              case 1: am = &amaps.m[1]; break;
+              case 2: am = &amaps.m[2]; break;
+              case 3: am = &amaps.m[3]; break;
+              case 4: am = &amaps.m[4]; break;
+              case 5: am = &amaps.m[5]; break;
+              default: break;
+            }
+            if (!RESB) ptx::tma_load_2d(sB, &bmap, &full[stage], par * p.b_parity_stride + (kb * NPROD + pr) * BLOCK_K, co0);
+            ptx::tma_load_4d(sA, am, &full[stage], c0, b0 + e.db, a0 + e.da, n0);
             if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
-            continue;
           }
-          ptx::mbar_expect_tx(&full[stage], RESB ? S::kABytes : S::kABytes + S::kBBytesRaw);
-          uint8_t* sA = stage_base + stage * S::kStageBytes;
-          uint8_t* sB = sA + S::kABytes;
-          const CUtensorMap* am = &amaps.m[0];
-          switch (e.map) {
-            case 1: am = &amaps.m[1]; break;
-            case 2: am = &amaps.m[2]; break;
-            case 3: am = &amaps.m[3]; break;
-            case 4: am = &amaps.m[4]; break;
-            default: break;
-          }
-          if (!RESB) ptx::tma_load_2d(sB, &bmap, &full[stage], par * p.b_parity_stride + kb * BLOCK_K, co0);
-          ptx::tma_load_4d(sA, am, &full[stage], e.c0, b0 + e.db, a0 + e.da, n0);
-          if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -346,14 +355,13 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb * NPROD; ++kb) {
           ptx::mbar_wait(&full[stage], phase, p.error_flag, 3);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * S::kStageBytes);
           const uint32_t b_addr = RESB ? ptx::smem_u32(b_res + kb * S::kBBytes) : a_addr + S::kABytes;
           const uint64_t adesc = make_kmajor_desc<BLOCK_K>(a_addr);
           const uint64_t bdesc = make_kmajor_desc<BLOCK_K>(b_addr);
-          if (p.dbg != 1)
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advancing 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
@@ -397,13 +405,13 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
       const bool valid = (n < p.N) && (a < p.A_h) && (b < p.A_w) && !idle;
       const int oh = p.sigma * a + (par >> 1), ow = p.sigma * b + (par & 1);
       const size_t pix = ((size_t)n * p.OH + oh) * p.OW + ow;
-      const size_t off0 = pix * p.Cout + co0 + c_lo;
+      const size_t off0 = pix * (size_t)(NSPLIT * p.Cout) + co0 + c_lo;     // NSPLIT planes as channel blocks [a | b | c]
       const size_t pl_off = (size_t)n * (size_t)p.pl_img + (size_t)(oh + 1) * (size_t)p.pl_row + (size_t)(ow + 8) * 16;
       const bool has_res = (p.res != nullptr) && valid;
 
       // residual of the first chunk: issued before waiting for the accumulator
       uint4 rcur[STEP / 8], rnext[STEP / 8];
-      if (has_res) {
+      if (has_res && NSPLIT == 1) {
 #pragma unroll
         for (int j = 0; j < STEP / 8; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0) + j);
       }
@@ -419,9 +427,16 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
           uint32_t v[STEP];
 #pragma unroll
           for (int j = 0; j < STEP; j += 16) ptx::tmem_ld16(t_row + (uint32_t)(c + j), *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
-          if (has_res && c + STEP < CH) {
+          if (has_res && NSPLIT == 1 && c + STEP < CH) {
 #pragma unroll
             for (int j = 0; j < STEP / 8; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0 + c + STEP) + j);
+          }
+          uint4 rsp[NSPLIT == 3 ? 3 * (STEP / 8) : 1];
+          if (NSPLIT == 3 && has_res) {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+              for (int j = 0; j < STEP / 8; ++j) rsp[pl * (STEP / 8) + j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0 + (size_t)pl * p.Cout + c) + j);
           }
           ptx::tmem_ld_wait();
           float y[STEP];
@@ -435,7 +450,27 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
             y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, bb.z);
             y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, bb.w);
           }
-          if (has_res) {
+          if (NSPLIT == 3 && has_res) {
+            // residual = a + b + c, summed big to small: exact (the planes are a non-overlapping expansion of an fp32 value)
+#pragma unroll
+            for (int j = 0; j < STEP / 8; ++j) {
+              float rv[8];
+#pragma unroll
+              for (int pl = 0; pl < 3; ++pl) {
+                const uint4 q = rsp[pl * (STEP / 8) + j];
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
+                  rv[2 * t] = (pl == 0) ? lo : rv[2 * t] + lo;
+                  rv[2 * t + 1] = (pl == 0) ? hi : rv[2 * t + 1] + hi;
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 8; ++t) y[8 * j + t] += rv[t];
+            }
+          }
+          if (NSPLIT == 1 && has_res) {
 #pragma unroll
             for (int j = 0; j < STEP / 8; ++j) {
               const uint32_t w[4] = {rcur[j].x, rcur[j].y, rcur[j].z, rcur[j].w};
@@ -462,7 +497,26 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
               head_acc[k] += sacc;
             }
           }
-          if (valid && p.out != nullptr) {
+          if (NSPLIT == 3 && valid && p.out != nullptr) {
+            // three bf16 planes of the fp32 result: a = rn(y), b = rn(y - a), c = rn(y - a - b) (the last is exact)
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              uint8_t* ob = reinterpret_cast<uint8_t*>(p.out + off0 + (size_t)pl * p.Cout + c);
+#pragma unroll
+              for (int j = 0; j < STEP / 8; ++j) {
+                uint32_t w[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+                  w[t] = *reinterpret_cast<const uint32_t*>(&h2);
+                  y[8 * j + 2 * t] -= __low2float(h2);
+                  y[8 * j + 2 * t + 1] -= __high2float(h2);
+                }
+                *reinterpret_cast<uint4*>(ob + (size_t)j * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
+          if (NSPLIT == 1 && valid && p.out != nullptr) {
             // NHWC: 2 * STEP contiguous bytes; planar: one 16-byte entry per 8-channel chunk row
             uint8_t* ob = p.out_planar ? reinterpret_cast<uint8_t*>(p.out) + pl_off + (size_t)((co0 + c_lo + c) >> 3) * (size_t)p.pl_chunk
                                        : reinterpret_cast<uint8_t*>(p.out + off0 + c);
@@ -562,7 +616,7 @@ class ConvOp {
   void build(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const float* w_oihw,
              const float* scale, const float* bias, const void* residual, void* out,
              const float* head_w, const float* head_b, float* head_out, int* error_flag, int num_sms,
-             int out_layout = LAYOUT_NHWC, int res_layout = LAYOUT_NHWC);
+             int out_layout = LAYOUT_NHWC, int res_layout = LAYOUT_NHWC, int split = 0);
   bool is_rowtile() const { return (bool)row_; }
   // would build() route this conv to the row-tile kernel?  (lets the caller chain planar layouts)
   static bool routes_to_rowtile(const std::vector<ConvInputPart>& parts, const ConvSpec& spec, const void* residual);
@@ -571,9 +625,12 @@ class ConvOp {
   // out_layout: LAYOUT_NHWC or LAYOUT_PLANAR_PARITY (row-tile stem only; see stem_routes_to_rowtile)
   void build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw /*[64,3,7,7]*/,
                   const float* scale, const float* bias, void* out, int* error_flag, int num_sms,
-                  int out_layout = LAYOUT_NHWC);
+                  int out_layout = LAYOUT_NHWC, int split = 0);
   static bool stem_routes_to_rowtile();
   void launch(cudaStream_t stream, LaunchCounter* lc) const;
+  // re-point the fused-head output (fp32 logits [N,OH,OW,4]) of a conv built with one: the engine writes each batch
+  // straight into its slot of the logit ring
+  void set_head_out(float* p);
   double flops() const { return flops_; }
   int block_n() const { return block_n_; }
   int block_k() const { return block_k_; }
@@ -600,6 +657,7 @@ class ConvOp {
                   const void* residual, void* out, int out_layout, int* error_flag, int num_sms);
   DevBuf hgroups_;
   bool out_planar_ = false;   // TMA kernel writing the planar layout for a row-kernel consumer
+  int split_ = 0;             // fp32 emulation: three bf16 planes per tensor, 6 plane products per K block (NSPLIT = 3)
   double flops_ = 0;
 };
 

@@ -188,8 +188,8 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           const KBlock e = kb_tbl[kb];      // read BEFORE the wait (asm volatile + memory clobber would pin it after)
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 11);
-          if (p.dbg >= 3) {      // timing experiments (see ConvParams::dbg): 3 A only, 4 B only (2 would let the leader lap the peer)
-            const bool la = (p.dbg == 3), lb = (p.dbg == 4);
+          if (WSI_DBG(p) >= 3) {      // timing experiments (see ConvParams::dbg): 3 A only, 4 B only (2 would let the leader lap the peer)
+            const bool la = (WSI_DBG(p) == 3), lb = (WSI_DBG(p) == 4);
             if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2u * (uint32_t)((la ? S::kABytes : 0) + (lb ? S::kBBytes : 0)));
             uint8_t* sA = stage_base + stage * S::kStageBytes;
             const uint32_t fb = full0 + (uint32_t)(stage * 8);
@@ -236,7 +236,7 @@ conv_igemm_pair_kernel(const __grid_constant__ AMaps amaps, const __grid_constan
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * S::kStageBytes);
           const uint64_t adesc = make_kmajor_desc<BLOCK_K>(a_addr);
           const uint64_t bdesc = make_kmajor_desc<BLOCK_K>(a_addr + S::kABytes);
-          if (p.dbg != 1)
+          if (WSI_DBG(p) != 1)
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
             pptx::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));

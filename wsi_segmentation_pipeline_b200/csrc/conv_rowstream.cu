@@ -118,13 +118,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
       while (uc.next()) {
         const int b0 = uc.xb * 128;
         const uint32_t bytes = (uint32_t)min(kRowHaloCols, p.d.Wrow - b0) * 16u;
-        const uint32_t row_tx = (p.dbg == 2) ? 0u : (uint32_t)nruns * bytes;
+        const uint32_t row_tx = (WSI_DBG(p) == 2) ? 0u : (uint32_t)nruns * bytes;
         const uint8_t* rowp = p.in + p.d.row_off(uc.n, uc.y0 - 1, 0, 0) + (size_t)b0 * 16;
         const int rows = uc.Lu + 2;
         for (int t = 0; t < rows; ++t) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 31);
           ptx::mbar_expect_tx(&full[stage], row_tx);
-          if (p.dbg != 2) {
+          if (WSI_DBG(p) != 2) {
             const uint8_t* src = rowp;
             uint32_t d = dst;
 #pragma unroll 2
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
       constexpr uint32_t kWSlab = 3 * 2 * 3 * BN, kWShift = 2 * 3 * BN;   // B: next slab / next horizontal shift (16-byte units)
       const uint32_t id1 = stream_idesc(BN), id2 = stream_idesc(2 * BN), id3 = stream_idesc(3 * BN);
       const int nslabs = p.nslabs;
-      const bool no_mma = (p.dbg == 1);
+      const bool no_mma = (WSI_DBG(p) == 1);
       int stage = 0;
       uint32_t phase = 0, a_off = 0;                   // a_off: stage * stage_units
       uint32_t jb = 0;                                 // output-row jobs issued by this CTA before the current unit
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           ptx::tc_fence_after();
           const uint32_t slot_lo = (j - 2u) & RM;
           if (no_mma) {
-          } else if (p.dbg == 4 && BN == 16) {
+          } else if (WSI_DBG(p) == 4 && BN == 16) {
             // timing experiment: the same 4 MMAs, each into its own TMEM region -> no dependent chain inside a row
             ptx::umma_bf16(tmem_base, a_row, b_desc0 + (uint64_t)(2 * BN), id1, 1u);
             ptx::umma_bf16(tmem_base + 48, a_row, b_desc0, id2, 1u);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
         float4 hacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.dbg != 3)
+        if (WSI_DBG(p) != 3)
 #pragma unroll
         for (int c = 0; c < BN; c += 16) {
           uint32_t v[16];
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
       constexpr uint32_t kWSlab = 3 * 2 * 3 * BN, kWShift = 2 * 3 * BN;
       const uint32_t id1 = stream_idesc(BN), id2 = stream_idesc(2 * BN), id3 = stream_idesc(3 * BN);
       const int nslabs = p.nslabs;
-      const bool no_mma = (p.dbg == 1);
+      const bool no_mma = (WSI_DBG(p) == 1);
       int stage = 0;
       uint32_t phase = 0, a_off = 0;
       uint32_t jb = 0;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
           }
           ptx::umma_commit(&empty[stage]);                                   // stage back to the producer
           if (t >= 2) ptx::umma_commit(&row_done[(j - 2u) & RM]);            // output row t-2 is complete
-          if (p.dbg == 6) { ptx::umma_commit(dummy_bar); ptx::umma_commit(dummy_bar); }   // what does a commit cost?
+          if (WSI_DBG(p) == 6) { ptx::umma_commit(dummy_bar); ptx::umma_commit(dummy_bar); }   // what does a commit cost?
           a_off += stage_units;
           if (++stage == S) { stage = 0; phase ^= 1u; a_off = 0; }
         }
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)lane_sel * kLane + slot * BN;
         float4 hacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.dbg != 3)
+        if (WSI_DBG(p) != 3)
 #pragma unroll
         for (int c = 0; c < BN; c += 16) {
           uint32_t v[16];
@@ -755,7 +755,9 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   p.res = static_cast<const uint8_t*>(residual);
   p.res_layout = res_layout;
   p.error_flag = error_flag;
+#ifdef WSI_DEBUG_SWITCHES
   if (const char* e = getenv("WSI_STREAM_DBG")) p.dbg = atoi(e);
+#endif
   // stacked weights: [slab][s][2 chunks][3*BN][8], N order = vertical tap r = 2 | 1 | 0
   std::vector<uint16_t> wp((size_t)p.nslabs * 3 * 2 * 3 * BN * 8);
   for (int sl = 0; sl < p.nslabs; ++sl)

@@ -62,6 +62,7 @@ class RowStreamOp {
              float* head_out, int* error_flag, int num_sms);
   void launch(cudaStream_t stream, LaunchCounter* lc) const;
   double flops() const { return flops_; }
+  void set_head_out(float* p) { p_.head_out = p; }
 
  private:
   StreamParams p_{};

@@ -102,6 +102,7 @@ class RowConvOp {
   void launch(cudaStream_t stream, LaunchCounter* lc) const;
   double flops() const { return flops_; }
   int block_n() const { return p_.Cout; }
+  void set_head_out(float* p) { p_.head_out = p; }
 
  private:
   struct Relayout { const void* src; void* dst; int N, H, W, C, layout; };

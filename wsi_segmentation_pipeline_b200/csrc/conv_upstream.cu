@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_upstream_kernel(const __gr
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       const uint32_t id2 = uptx::idesc(2 * BN), id3 = uptx::idesc(3 * BN), id4 = uptx::idesc(4 * BN);
       const int nslabs_u = p.nslabs_u, nslabs_s = p.nslabs_s;
-      const bool no_mma = (p.dbg == 1);
+      const bool no_mma = (WSI_DBG(p) == 1);
       int stage = 0;
       uint32_t phase = 0, a_off = 0;
       uint32_t jb = 0;        // output-row jobs of the units before this one
@@ -422,7 +422,9 @@ void UpStreamOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& 
   p.out = static_cast<uint8_t*>(out);
   p.od = PlanarDims::make(p.OH, p.OW, BN, LAYOUT_PLANAR);
   p.error_flag = error_flag;
+#ifdef WSI_DEBUG_SWITCHES
   if (const char* e = getenv("WSI_UP_DBG")) p.dbg = atoi(e);
+#endif
 
   // weights (bf16, fp32 sums rounded once).  Input channel order = torch.cat([up(u), skip], 1).
   //   u blocks   [slab][parity p][tap tau][2 chunks][4*BN rows][8]: row blk*BN + n, blk <-> output row 2a-1+blk with

@@ -34,9 +34,10 @@ struct Act {  // bf16 activation in HBM: NHWC, or zero-padded channel-chunk-plan
   DevBuf buf;
   int N = 0, H = 0, W = 0, C = 0;
   int layout = LAYOUT_NHWC;
+  int planes = 1;          // 3 in the fp32-emulated precision: NHWC pixel = [a | b | c] bf16 planes of C channels each
   TensorView view() const { return TensorView{buf.p, N, H, W, C, layout}; }
   size_t bytes() const {
-    if (layout == LAYOUT_NHWC) return (size_t)N * H * W * C * 2;
+    if (layout == LAYOUT_NHWC) return (size_t)N * H * W * C * planes * 2;
     return PlanarDims::make(H, W, C, layout).bytes(N);
   }
 };
@@ -52,6 +53,24 @@ struct StageAcc {
 struct EventSpan {
   cudaEvent_t a, b;
   int stage;
+};
+
+struct PinnedBuf {   // page-locked host staging (RAII)
+  void* p = nullptr;
+  size_t bytes = 0;
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  void alloc(size_t n) {
+    if (n <= bytes && p) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr; bytes = 0;
+    if (n == 0) n = 64;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e != cudaSuccess) { p = nullptr; WSI_THROW(WSI_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", n, cudaGetErrorString(e)); }
+    bytes = n;
+  }
 };
 
 }  // namespace wsi
@@ -71,6 +90,7 @@ struct wsi_ctx {
   float class_probs[4] = {0.f, 0.f, 0.f, 0.f};
   int64_t batch_tiles = 0;
   int stage_timing = 0;
+  int precision = WSI_PRECISION_BF16;
   DevBuf lut;        // f32 [3][256] normalise table
   DevBuf err_flag;   // int, set by a timed-out barrier wait inside the conv kernel
   std::unique_ptr<NetPlan> plan;
@@ -79,7 +99,15 @@ struct wsi_ctx {
   std::vector<EventSpan> spans;
   std::vector<cudaEvent_t> event_pool;
   // scratch reused across slides
-  DevBuf raster, maskbuf, canvas, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, tile_logits, scratch_f32, counts;
+  DevBuf raster, maskbuf, logit_ring, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, tile_logits, scratch_f32, counts;
+  // copy streams: chunked raster upload / strip-wise output download overlap the compute on the caller's stream
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  // pinned staging for the per-slide index arrays (tile list, rect index): uploaded without a stream sync
+  PinnedBuf idx_host;
+  cudaEvent_t idx_event = nullptr;      // completion of the previous call's index upload (guards idx_host reuse)
+  bool idx_pending = false;
+  std::vector<cudaEvent_t> order_events;   // ordering events between the caller's stream and the copy streams
+  size_t order_used = 0;
   // multi-patch ensemble head `fc` (uploaded on first use after a model load)
   DevBuf ens_w1, ens_b1, ens_w2, ens_b2;
   bool ens_ready = false;
@@ -176,6 +204,9 @@ static const HostTensor& conv_weight(const wsi_ctx* c, const std::string& name, 
 // ---------------------------------------------------------------------------------------------
 struct NetPlan {
   int arch = -1, head = -1, cap = 0, ph = 0, pw = 0;
+  int precise = 0;               // WSI_PRECISION_FP32: three bf16 planes per tensor, every conv on the table-driven TMA kernel
+  int in_planes() const { return precise ? 3 : 1; }
+  int64_t in_plane_stride() const { return (int64_t)cap * (ph + 6) * (pw + 8) * 4; }   // elements between the stem operand's planes
   struct Step {
     int kind;  // 0 conv, 1 maxpool, 2 pool+head
     int stage;
@@ -191,6 +222,7 @@ struct NetPlan {
   DevBuf pooled;                 // CLS head: the pooled 512-vectors next to the logits (multi-patch ensemble head reads them)
   int n1 = 0, n2 = 0, out_dim = 0;
   Act* x4 = nullptr;
+  ConvOp* head_op = nullptr;     // SEG: the last decoder conv (fused 1x1 head); its fp32 logits output is re-pointed per batch
   double conv_flops = 0, stem_flops = 0;   // per batch of `cap` tiles (algorithmic: 2*MAC, no padding)
   std::vector<Act*> feats;                 // [x4, x3, x2, x1, x0]
   // WSI_CONV_TRACE=1: per-op device time (dev tool; events around every conv launch)
@@ -207,6 +239,7 @@ struct NetPlan {
     acts.emplace_back(new Act());
     Act* a = acts.back().get();
     a->N = N; a->H = H; a->W = W; a->C = C; a->layout = layout;
+    a->planes = precise ? 3 : 1;
     a->buf.alloc(a->bytes());
     if (layout != LAYOUT_NHWC) CUDA_CHECK(cudaMemset(a->buf.p, 0, a->buf.bytes));   // the zero border IS the conv padding
     return a;
@@ -216,12 +249,12 @@ struct NetPlan {
     return ops.back().get();
   }
 
-  void build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_);
+  void build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_, int precise_);
   void run(wsi_ctx* c, cudaStream_t s);
 };
 
-void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_) {
-  arch = arch_; head = head_; cap = cap_; ph = ph_; pw = pw_;
+void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_, int precise_) {
+  arch = arch_; head = head_; cap = cap_; ph = ph_; pw = pw_; precise = precise_ ? 1 : 0;
   WSI_REQUIRE(cap > 0 && ph > 0 && pw > 0, WSI_ERR_INVALID, "plan: empty batch");
   WSI_REQUIRE(ph % 2 == 0 && pw % 2 == 0 && ph >= 8 && pw >= 8, WSI_ERR_UNSUPPORTED, "tile size %dx%d: must be even and >= 8", ph, pw);
   if (head == WSI_HEAD_SEG) {
@@ -233,19 +266,19 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
   int* ef = c->err_flag.as<int>();
   const int sms = c->num_sms;
 
-  in_pad.alloc((size_t)cap * (ph + 6) * (pw + 8) * 4 * 2);
+  in_pad.alloc((size_t)in_planes() * cap * (ph + 6) * (pw + 8) * 4 * 2);
   CUDA_CHECK(cudaMemset(in_pad.p, 0, in_pad.bytes));
 
   // ---- stem: conv1 7x7/s2/p3 + bn1 + relu (resnets_shift.py:196-198) ----
   // the row-tile stem writes x0 column-parity-planar: the max-pool reads it directly and the decoder's level-4
   // conv takes it as its skip operand without a relayout
-  const int x0_layout = ConvOp::stem_routes_to_rowtile() ? LAYOUT_PLANAR_PARITY : LAYOUT_NHWC;
+  const int x0_layout = (!precise && ConvOp::stem_routes_to_rowtile()) ? LAYOUT_PLANAR_PARITY : LAYOUT_NHWC;
   Act* x0 = new_act(cap, ph / 2, pw / 2, 64, x0_layout);
   {
     const HostTensor& w = conv_weight(c, tp + "conv1.weight", 64, 3, 7);
     const Folded f = fold_bn(c, tp + "bn1", 64);
     ConvOp* op = new_op();
-    op->build_stem(in_pad.p, cap, ph, pw, w.data.data(), f.scale.data(), f.bias.data(), x0->buf.p, ef, sms, x0_layout);
+    op->build_stem(in_pad.p, cap, ph, pw, w.data.data(), f.scale.data(), f.bias.data(), x0->buf.p, ef, sms, x0_layout, precise);
     steps.push_back(Step{0, ST_STEM, op, nullptr, x0});
     stem_flops = op->flops();
     op_stats.push_back(OpStat{"stem 7x7/s2 3->64", 0, op->flops(), 0});
@@ -259,7 +292,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
   {
     ConvSpec sp; sp.ksize = 3; sp.stride = 1; sp.pad = 1; sp.cout = 64; sp.relu = true;
     const ConvInputPart probe{TensorView{nullptr, cap, (x0->H - 1) / 2 + 1, (x0->W - 1) / 2 + 1, 64, LAYOUT_NHWC}, false};
-    l1_row = (x0_layout == LAYOUT_PLANAR_PARITY) && ConvOp::routes_to_rowtile({probe}, sp, nullptr);
+    l1_row = !precise && (x0_layout == LAYOUT_PLANAR_PARITY) && ConvOp::routes_to_rowtile({probe}, sp, nullptr);
   }
   Act* p0 = new_act(cap, (x0->H - 1) / 2 + 1, (x0->W - 1) / 2 + 1, 64, l1_row ? LAYOUT_PLANAR : LAYOUT_NHWC);
   steps.push_back(Step{1, ST_MAXPOOL, nullptr, x0, p0});
@@ -268,7 +301,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
                       const Act* res, Act* out, const float* hw = nullptr, const float* hb = nullptr, float* hout = nullptr) {
     ConvOp* op = new_op();
     op->build(parts, spec, w, f ? f->scale.data() : nullptr, f ? f->bias.data() : nullptr, res ? res->buf.p : nullptr,
-              out ? out->buf.p : nullptr, hw, hb, hout, ef, sms, out ? out->layout : LAYOUT_NHWC, res ? res->layout : LAYOUT_NHWC);
+              out ? out->buf.p : nullptr, hw, hb, hout, ef, sms, out ? out->layout : LAYOUT_NHWC, res ? res->layout : LAYOUT_NHWC, precise);
     steps.push_back(Step{0, ST_CONV, op, nullptr, out});
     conv_flops += op->flops();
     char d[160];
@@ -347,8 +380,8 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
         a.sp.ksize = 3; a.sp.stride = 1; a.sp.pad = 1; a.sp.cout = co; a.sp.relu = true;
         b.parts.push_back(probe_part(cap, 2 * xh, 2 * xw, co, false));
         b.sp = a.sp; b.sp.head = (i == 5);
-        a.row = ConvOp::routes_to_rowtile(a.parts, a.sp, nullptr);
-        b.row = ConvOp::routes_to_rowtile(b.parts, b.sp, nullptr);
+        a.row = !precise && ConvOp::routes_to_rowtile(a.parts, a.sp, nullptr);
+        b.row = !precise && ConvOp::routes_to_rowtile(b.parts, b.sp, nullptr);
         plan.push_back(a); plan.push_back(b);
         xh *= 2; xw *= 2; xc = co;
       }
@@ -383,6 +416,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
         WSI_REQUIRE(fb.numel() == 4, WSI_ERR_NOMODEL, "decoder.final_conv.bias must have 4 entries");
         add_conv({ConvInputPart{a->view(), false}}, plan[ib].sp, w.data.data(), &f, nullptr, nullptr, fw.data.data(), fb.data.data(),
                  logits.as<float>());
+        head_op = ops.back().get();
       }
     }
     out_dim = 4;
@@ -475,7 +509,9 @@ void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
         }
         ++conv_idx;
       } else if (st.kind == 1) {
-        if (st.in->layout == LAYOUT_PLANAR_PARITY)
+        if (precise)
+          launch_maxpool_split(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
+        else if (st.in->layout == LAYOUT_PLANAR_PARITY)
           launch_maxpool_planar(st.in->buf.p, st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.p, st.out->layout, s, &c->lc);
         else
           launch_maxpool(st.in->buf.as<bf16>(), st.in->N, st.in->H, st.in->W, st.in->C, st.out->buf.as<bf16>(), s, &c->lc);
@@ -483,7 +519,7 @@ void NetPlan::run(wsi_ctx* c, cudaStream_t s) {
         const bool feat = (head == WSI_HEAD_FEATURES);
         float* feat_out = feat ? logits.as<float>() : (pooled.p ? pooled.as<float>() : nullptr);
         launch_pool_head(x4->buf.as<bf16>(), cap, x4->H * x4->W, x4->C, hw1.as<float>(), hb1.as<float>(), n1, hw2.as<float>(),
-                         hb2.as<float>(), n2, feat_out, logits.as<float>(), s, &c->lc);
+                         hb2.as<float>(), n2, feat_out, logits.as<float>(), s, &c->lc, precise ? 3 : 1);
       }
     }
   }
@@ -494,18 +530,24 @@ namespace wsi {
 static NetPlan* get_plan(wsi_ctx* c, int head, int n, int ph, int pw) {
   WSI_REQUIRE(c->arch >= 0, WSI_ERR_NOMODEL, "wsi_model_load has not been called");
   NetPlan* p = c->plan.get();
-  if (p && p->arch == c->arch && p->head == head && p->ph == ph && p->pw == pw && p->cap >= n && p->cap <= std::max(2 * n, 8)) return p;
+  const int precise = (c->precision == WSI_PRECISION_FP32) ? 1 : 0;
+  if (p && p->arch == c->arch && p->head == head && p->ph == ph && p->pw == pw && p->precise == precise && p->cap >= n && p->cap <= std::max(2 * n, 8)) return p;
   c->plan.reset();
   c->plan.reset(new NetPlan());
-  c->plan->build(c, c->arch, head, n, ph, pw);
+  c->plan->build(c, c->arch, head, n, ph, pw, precise);
   return c->plan.get();
 }
 
+// The device error flag (set by a conv pipeline barrier that timed out) is STICKY: no call clears it on entry, so a
+// failure inside an asynchronous (device-output) call is reported by the next synchronising call or by wsi_check.
 static void check_device_flag(wsi_ctx* c, cudaStream_t s) {
   int flag = 0;
   CUDA_CHECK(cudaMemcpyAsync(&flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
-  WSI_REQUIRE(flag == 0, WSI_ERR_CUDA, "conv kernel pipeline barrier timed out (code %d)", flag);
+  if (flag != 0) {
+    cudaMemsetAsync(c->err_flag.p, 0, sizeof(int), s);
+    WSI_THROW(WSI_ERR_CUDA, "conv kernel pipeline barrier timed out (code %d)", flag);
+  }
 }
 
 static int64_t auto_batch(const wsi_ctx* c, int ph, int pw, int64_t T) {
@@ -536,19 +578,69 @@ static void validate_slide(const wsi_slide_desc* sl) {
               (long long)sl->row0, (long long)sl->rows);
 }
 
-// raster (band) resident on the device; returns the device pointer and stride
-static const uint8_t* stage_raster(wsi_ctx* c, const wsi_slide_desc* sl, int64_t rows, int64_t* stride_out, cudaStream_t s) {
+// ordering events (no timing), reused call after call
+static cudaEvent_t order_event(wsi_ctx* c) {
+  if (c->order_used == c->order_events.size()) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->order_events.push_back(e);
+  }
+  return c->order_events[c->order_used++];
+}
+
+// Raster (band) resident on the device.  A host raster is uploaded in row chunks on the context's copy stream, one
+// event per chunk: the caller's stream waits only for the chunk a batch of tiles needs, so the first batches run
+// while the rest of the band is still crossing PCIe.  (SlideUpload::need is called with raster-local row bounds.)
+struct SlideUpload {
+  const uint8_t* rgb = nullptr;
+  int64_t stride = 0, chunk_rows = 0;
+  std::vector<cudaEvent_t> chunk_ev;
+  int waited = -1;
+  void need(cudaStream_t s, int64_t row_end) {
+    if (chunk_ev.empty() || row_end <= 0) return;
+    const int ch = (int)std::min<int64_t>((row_end - 1) / chunk_rows, (int64_t)chunk_ev.size() - 1);
+    if (ch > waited) {
+      CUDA_CHECK(cudaStreamWaitEvent(s, chunk_ev[ch], 0));
+      waited = ch;
+    }
+  }
+};
+
+static SlideUpload stage_raster(wsi_ctx* c, const wsi_slide_desc* sl, int64_t rows, cudaStream_t s) {
+  SlideUpload u;
   if (sl->rgb_mem == WSI_MEM_DEVICE) {
-    *stride_out = sl->row_stride;
-    return sl->rgb;
+    u.stride = sl->row_stride;
+    u.rgb = sl->rgb;
+    return u;
   }
   const int64_t tight = 3 * sl->iw;
-  StageScope scope(c, s, ST_H2D, (double)rows * tight);
   c->raster.alloc((size_t)rows * tight);
-  if (rows > 0)
-    CUDA_CHECK(cudaMemcpy2DAsync(c->raster.p, tight, sl->rgb, sl->row_stride, tight, rows, cudaMemcpyHostToDevice, s));
-  *stride_out = tight;
-  return c->raster.as<uint8_t>();
+  u.stride = tight;
+  u.rgb = c->raster.as<uint8_t>();
+  if (rows <= 0) return u;
+  u.chunk_rows = std::max<int64_t>(sl->ph, (int64_t)(48 << 20) / tight);
+  cudaEvent_t e0 = order_event(c);
+  CUDA_CHECK(cudaEventRecord(e0, s));                         // the copy stream starts after everything already queued on s
+  CUDA_CHECK(cudaStreamWaitEvent(c->h2d_stream, e0, 0));      // (an earlier call may still be reading c->raster)
+  StageScope scope(c, c->h2d_stream, ST_H2D, (double)rows * tight);
+  for (int64_t r0 = 0; r0 < rows; r0 += u.chunk_rows) {
+    const int64_t nr = std::min(u.chunk_rows, rows - r0);
+    CUDA_CHECK(cudaMemcpy2DAsync(c->raster.as<uint8_t>() + r0 * tight, tight, sl->rgb + r0 * sl->row_stride, sl->row_stride, tight, nr,
+                                 cudaMemcpyHostToDevice, c->h2d_stream));
+    cudaEvent_t e = order_event(c);
+    CUDA_CHECK(cudaEventRecord(e, c->h2d_stream));
+    u.chunk_ev.push_back(e);
+  }
+  return u;
+}
+
+// whole raster resident before anything else on s (single-batch entry points)
+static const uint8_t* stage_raster_all(wsi_ctx* c, const wsi_slide_desc* sl, int64_t rows, int64_t* stride_out, cudaStream_t s) {
+  c->order_used = 0;
+  SlideUpload u = stage_raster(c, sl, rows, s);
+  u.need(s, rows);
+  *stride_out = u.stride;
+  return u.rgb;
 }
 
 static void check_tiles(const wsi_slide_desc* sl, const int32_t* xy, int64_t n, int64_t rows) {
@@ -578,6 +670,9 @@ static void ensure_lut(wsi_ctx* c) {
 }
 
 // the hot path ------------------------------------------------------------------------------
+// Per slide / row band: sort the tiles by canvas origin; batches of tiles go gather -> network; SEG logits land in a
+// ring of the last few tile rows; whenever a run of canvas rows can receive no further tile (every later tile starts
+// below it) ONE kernel sums the covering tiles of each of its pixels and finalises them (K6 + K7 fused, no canvas).
 static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles_xy, int64_t T, int head, const wsi_out_desc* out,
                       cudaStream_t s) {
   validate_slide(sl);
@@ -587,7 +682,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   WSI_REQUIRE(sl->m > 0, WSI_ERR_INVALID, "m must be positive");
   const int64_t rows_r = (sl->rows == 0 && sl->row0 == 0) ? sl->ih : sl->rows;
   const int64_t H2 = sl->H2, W2 = sl->W2;
-  WSI_REQUIRE(H2 > 0 && W2 > 0 && W2 < (1LL << 31) && H2 < (1LL << 31), WSI_ERR_INVALID, "bad canvas size");
+  WSI_REQUIRE(H2 > 0 && W2 > 0 && W2 < (1LL << 31) - 512 && H2 < (1LL << 31), WSI_ERR_INVALID, "bad canvas size");
   const int64_t own0 = sl->own0, own1 = (sl->own0 == 0 && sl->own1 == 0) ? H2 : sl->own1;
   WSI_REQUIRE(own0 >= 0 && own1 >= own0 && own1 <= H2, WSI_ERR_INVALID, "bad owned rows");
   const int64_t orows = own1 - own0, plane = orows * W2;
@@ -598,11 +693,10 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   WSI_REQUIRE(dx > 0 && dy > 0, WSI_ERR_DEGENERATE, "tile rectangle is empty on the canvas");
   check_tiles(sl, tiles_xy, T, rows_r);
   ensure_lut(c);
-  CUDA_CHECK(cudaMemsetAsync(c->err_flag.p, 0, sizeof(int), s));
+  c->order_used = 0;
 
-  // ---- sort tiles by canvas origin (ty, tx): batches become spatially compact and the stitch
-  //      sums in a fixed order regardless of the order the caller (or a shuffling DataLoader,
-  //      utils/dataset.py:192) presents them in ----
+  // ---- sort tiles by canvas origin (ty, tx): batches become spatially compact and every pixel sums its tiles in
+  //      one fixed order, whatever order the caller (or a shuffling DataLoader, utils/dataset.py:192) presents ----
   std::vector<int32_t> order((size_t)T), tys((size_t)T), txs((size_t)T);
   for (int64_t i = 0; i < T; ++i) {
     order[i] = (int32_t)i;
@@ -613,23 +707,41 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
     if (tys[a] != tys[b]) return tys[a] < tys[b];
     return txs[a] < txs[b];
   });
-  std::vector<int32_t> sxy((size_t)2 * T), stx((size_t)T), rowy, rowstart;
+  std::vector<int32_t> sty((size_t)T), rowy, rowstart;
   for (int64_t i = 0; i < T; ++i) {
-    const int32_t o = order[i];
-    sxy[2 * i] = tiles_xy[2 * o];
-    sxy[2 * i + 1] = tiles_xy[2 * o + 1];
-    stx[i] = txs[o];
-    if (i == 0 || tys[o] != rowy.back()) {
-      rowy.push_back(tys[o]);
+    sty[i] = tys[order[i]];
+    if (i == 0 || sty[i] != rowy.back()) {
+      rowy.push_back(sty[i]);
       rowstart.push_back((int32_t)i);
     }
   }
   rowstart.push_back((int32_t)T);
-  upload(c->tiles_dev, sxy, s);
-  upload(c->rect_tx, stx, s);
-  upload(c->rect_rowy, rowy, s);
-  upload(c->rect_rowstart, rowstart, s);
-  CUDA_CHECK(cudaStreamSynchronize(s));   // the host vectors above die with this scope
+  // index arrays -> pinned staging -> device, stream-ordered (no host sync)
+  {
+    if (c->idx_pending) { CUDA_CHECK(cudaEventSynchronize(c->idx_event)); c->idx_pending = false; }
+    const size_t n_xy = (size_t)2 * T, n_tx = (size_t)T, n_ry = rowy.size(), n_rs = rowstart.size();
+    c->idx_host.alloc((n_xy + n_tx + n_ry + n_rs) * sizeof(int32_t));
+    int32_t* h = static_cast<int32_t*>(c->idx_host.p);
+    int32_t *h_xy = h, *h_tx = h + n_xy, *h_ry = h_tx + n_tx, *h_rs = h_ry + n_ry;
+    for (int64_t i = 0; i < T; ++i) {
+      const int32_t o = order[i];
+      h_xy[2 * i] = tiles_xy[2 * o];
+      h_xy[2 * i + 1] = tiles_xy[2 * o + 1];
+      h_tx[i] = txs[o];
+    }
+    if (n_ry) memcpy(h_ry, rowy.data(), n_ry * sizeof(int32_t));
+    memcpy(h_rs, rowstart.data(), n_rs * sizeof(int32_t));
+    auto up = [&](DevBuf& b, const int32_t* src, size_t n) {
+      b.alloc(std::max<size_t>(n, 1) * sizeof(int32_t));
+      if (n) CUDA_CHECK(cudaMemcpyAsync(b.p, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    };
+    up(c->tiles_dev, h_xy, n_xy);
+    up(c->rect_tx, h_tx, n_tx);
+    up(c->rect_rowy, h_ry, n_ry);
+    up(c->rect_rowstart, h_rs, n_rs);
+    CUDA_CHECK(cudaEventRecord(c->idx_event, s));
+    c->idx_pending = true;
+  }
   RectIndex ri;
   ri.tx = c->rect_tx.as<int32_t>();
   ri.row_y = c->rect_rowy.as<int32_t>();
@@ -638,8 +750,8 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   ri.dx = (int32_t)dx;
   ri.dy = (int32_t)dy;
 
-  int64_t rstride = 0;
-  const uint8_t* rgb = stage_raster(c, sl, rows_r, &rstride, s);
+  SlideUpload up_r;
+  if (T > 0) up_r = stage_raster(c, sl, rows_r, s);
 
   const uint8_t* mask_dev = nullptr;
   if (sl->mask) {
@@ -672,7 +784,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
 
   FinaliseArgs fa;
   fa.W2 = W2; fa.own0 = own0; fa.own1 = own1; fa.mask = mask_dev;
-  for (int i = 0; i < 4; ++i) fa.class_probs[i] = c->class_probs[i];
+  for (int i = 0; i < 4; ++i) fa.class_probs[i] = (double)c->class_probs[i];
   fa.heat_mode = (head == WSI_HEAD_CLS) ? 1 : 0;
   fa.classes = cls_dev; fa.heatmap = heat_dev; fa.canvas_out = canvas_out; fa.probs_out = probs_out;
 
@@ -680,57 +792,93 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   NetPlan* plan = (T > 0) ? get_plan(c, head, (int)B, ph, pw) : nullptr;
   const int cap = plan ? plan->cap : 1;
   const double tile_px = (double)ph * pw;
+  const int64_t tile_elems = (int64_t)ph * pw * 4;
 
-  if (head == WSI_HEAD_SEG) {
-    c->canvas.alloc((size_t)plane * sizeof(float4));
-    CUDA_CHECK(cudaMemsetAsync(c->canvas.p, 0, (size_t)plane * sizeof(float4), s));
-  } else {
+  // first sorted tile that can still touch canvas row y: ty + dy > y
+  auto first_needed = [&](int64_t y) { return (int64_t)(std::upper_bound(sty.begin(), sty.end(), (int32_t)std::max<int64_t>(y - dy, INT32_MIN)) - sty.begin()); };
+  // rows below which no unprocessed tile starts once the first e sorted tiles are done
+  auto ready_after = [&](int64_t e) { return (e >= T) ? own1 : std::min<int64_t>(std::max<int64_t>(sty[e], own0), own1); };
+
+  int64_t ring_cap = 0;
+  if (head == WSI_HEAD_SEG && T > 0) {
+    // size the ring: while batch [t0, e) is written, every earlier tile that a not-yet-final row needs must survive
+    int64_t y_done = own0, max_span = 1;
+    for (int64_t t0 = 0; t0 < T; t0 += cap) {
+      const int64_t e = std::min<int64_t>(T, t0 + cap);
+      max_span = std::max(max_span, e - std::min(first_needed(y_done), t0));
+      y_done = std::max(y_done, ready_after(e));
+    }
+    ring_cap = std::min<int64_t>(round_up(max_span, cap), round_up(T, cap));
+    c->logit_ring.alloc((size_t)ring_cap * tile_elems * sizeof(float));
+  } else if (head == WSI_HEAD_CLS) {
     c->tile_logits.alloc((size_t)std::max<int64_t>(T, 1) * 4 * sizeof(float));
     WSI_REQUIRE(!plan || plan->out_dim == 4, WSI_ERR_UNSUPPORTED, "CLS stitch needs 4 classes (got %d)", plan ? plan->out_dim : 0);
   }
 
+  // finished strips leave for the host on the download stream while later batches compute
+  cudaEvent_t last_d2h = nullptr;
+  auto download_rows = [&](int64_t y0, int64_t y1) {
+    if (!host_out || y1 <= y0) return;
+    cudaEvent_t e = order_event(c);
+    CUDA_CHECK(cudaEventRecord(e, s));
+    CUDA_CHECK(cudaStreamWaitEvent(c->d2h_stream, e, 0));
+    const size_t off = (size_t)(y0 - own0) * W2, n = (size_t)(y1 - y0) * W2;
+    StageScope scope(c, c->d2h_stream, ST_D2H, (double)n * 2.0);
+    CUDA_CHECK(cudaMemcpyAsync(out->classes + off, cls_dev + off, n, cudaMemcpyDeviceToHost, c->d2h_stream));
+    CUDA_CHECK(cudaMemcpyAsync(out->heatmap + off, heat_dev + off, n, cudaMemcpyDeviceToHost, c->d2h_stream));
+    last_d2h = order_event(c);
+    CUDA_CHECK(cudaEventRecord(last_d2h, c->d2h_stream));
+  };
+
+  int64_t y_done = own0;
+  double pending_logit_bytes = 0;
   for (int64_t t0 = 0; t0 < T; t0 += cap) {
     const int n = (int)std::min<int64_t>(cap, T - t0);
     {
+      int64_t row_end = 0;
+      for (int64_t i = t0; i < t0 + n; ++i) row_end = std::max<int64_t>(row_end, (int64_t)tiles_xy[2 * order[i] + 1] + ph - sl->row0);
+      up_r.need(s, row_end);
       StageScope scope(c, s, ST_GATHER, 9.0 * n * tile_px);
-      launch_gather(rgb, rstride, sl->row0, c->tiles_dev.as<int32_t>() + 2 * t0, n, ph, pw, c->lut.as<float>(), plan->in_pad.as<bf16>(),
-                    nullptr, s, &c->lc);
+      launch_gather(up_r.rgb, up_r.stride, sl->row0, c->tiles_dev.as<int32_t>() + 2 * t0, n, ph, pw, c->lut.as<float>(), plan->in_pad.as<bf16>(),
+                    nullptr, s, &c->lc, plan->in_planes(), plan->in_plane_stride());
     }
-    plan->run(c, s);
     if (head == WSI_HEAD_SEG) {
-      // algorithmic bytes: T*P*C*4 logits read + S*C*4 canvas written once
-      StageScope scope(c, s, ST_STITCH, (double)n * tile_px * 16.0 + (t0 == 0 ? (double)plane * 16.0 : 0.0));
-      // one launch per run of tiles sharing a canvas row: box = that row's rectangle union
-      int64_t a = t0;
-      while (a < t0 + n) {
-        const int32_t ty = tys[order[a]];
-        int64_t b = a;
-        int32_t xmin = stx[a], xmax = stx[a];
-        while (b < t0 + n && tys[order[b]] == ty) { xmax = stx[b]; ++b; }
-        launch_stitch_seg_box(c->canvas.as<float4>(), ri, plan->logits.as<float4>(), (int)a, (int)b, (int)t0, W2, own0, own1, ty,
-                              (int)(ty + dy), xmin, (int)(xmax + dx), s, &c->lc);
-        a = b;
+      plan->head_op->set_head_out(c->logit_ring.as<float>() + (t0 % ring_cap) * tile_elems);
+      plan->run(c, s);
+      pending_logit_bytes += (double)n * tile_px * 16.0;
+      const int64_t e = t0 + n, y_ready = ready_after(e);
+      if (y_ready > y_done) {
+        // algorithmic bytes (fused stitch + finalise): T*P*C*4 logits read once + S*2 written (+ S mask read)
+        StageScope scope(c, s, ST_STITCH, pending_logit_bytes + (double)(y_ready - y_done) * W2 * (mask_dev ? 3.0 : 2.0));
+        pending_logit_bytes = 0;
+        launch_stitch_finalise_seg(ri, c->logit_ring.as<float4>(), (int)ring_cap, (int)first_needed(y_done), (int)e, y_done, y_ready, fa, s, &c->lc);
       }
+      if (y_ready > y_done) { download_rows(y_done, y_ready); y_done = y_ready; }
     } else {
+      plan->run(c, s);
       CUDA_CHECK(cudaMemcpyAsync(c->tile_logits.as<float>() + 4 * t0, plan->logits.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
   }
 
-  {
-    if (head == WSI_HEAD_SEG) {
-      StageScope scope(c, s, ST_FINALISE, (double)plane * 18.0);
-      launch_finalise_seg(c->canvas.as<float4>(), fa, s, &c->lc);
-    } else {
-      StageScope scope(c, s, ST_STITCH, (double)T * 16.0 + (double)plane * 2.0);
+  if (head == WSI_HEAD_SEG) {
+    if (y_done < own1) {                       // T == 0 (or nothing owned was reached): uncovered rows
+      StageScope scope(c, s, ST_STITCH, (double)(own1 - y_done) * W2 * (mask_dev ? 3.0 : 2.0));
+      launch_stitch_finalise_seg(ri, c->logit_ring.as<float4>(), (int)std::max<int64_t>(ring_cap, 1), 0, 0, y_done, own1, fa, s, &c->lc);
+      download_rows(y_done, own1);
+    }
+  } else {
+    {
+      StageScope scope(c, s, ST_STITCH, (double)T * 16.0 + (double)plane * (mask_dev ? 3.0 : 2.0));
       launch_stitch_finalise_cls(ri, c->tile_logits.as<float4>(), (int)T, fa, s, &c->lc);
     }
-    if (counts_out) launch_counts(ri, (int)T, W2, own0, own1, counts_out, s, &c->lc);
+    download_rows(own0, own1);
   }
+  if (counts_out) launch_counts(ri, (int)T, W2, own0, own1, counts_out, s, &c->lc);
+  if (last_d2h) CUDA_CHECK(cudaStreamWaitEvent(s, last_d2h, 0));     // the call's outputs are ordered on the caller's stream
+  up_r.need(s, rows_r);                                               // ... and so is the last read of the caller's raster
 
   if (host_out) {
-    StageScope scope(c, s, ST_D2H, (double)plane * 2.0);
-    CUDA_CHECK(cudaMemcpyAsync(out->classes, cls_dev, (size_t)plane, cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaMemcpyAsync(out->heatmap, heat_dev, (size_t)plane, cudaMemcpyDeviceToHost, s));
+    StageScope scope(c, s, ST_D2H, (double)plane * 4.0 * ((out->canvas ? 4 : 0) + (out->probs ? 4 : 0) + (out->counts ? 1 : 0)));
     if (out->canvas) CUDA_CHECK(cudaMemcpyAsync(out->canvas, canvas_out, (size_t)plane * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (out->probs) CUDA_CHECK(cudaMemcpyAsync(out->probs, probs_out, (size_t)plane * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (out->counts) CUDA_CHECK(cudaMemcpyAsync(out->counts, counts_out, (size_t)plane * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -743,6 +891,8 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
     for (int64_t i = 0; i < T; ++i) memcpy(&orig[(size_t)order[i] * 4], &sorted[(size_t)i * 4], 4 * sizeof(float));
     CUDA_CHECK(cudaMemcpy(out->tile_logits, orig.data(), (size_t)T * 4 * sizeof(float), host_out ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice));
   }
+  // Host outputs: the call returns when they are complete (and reports a conv pipeline failure).  Device outputs:
+  // fully asynchronous; the sticky error flag is reported by the next synchronising call or by wsi_check.
   if (host_out || c->stage_timing) {
     check_device_flag(c, s);
     resolve_spans(c);
@@ -751,6 +901,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
 
 // one batch through the network: x f32 NCHW (normalised) or tiles cut from a raster
 static void forward_common(wsi_ctx* c, NetPlan* plan, int n, int head, float* out, int mem, cudaStream_t s) {
+  if (plan->head_op) plan->head_op->set_head_out(plan->logits.as<float>());   // wsi_run_slide points it into its logit ring
   plan->run(c, s);
   const int ph = plan->ph, pw = plan->pw;
   const size_t out_elems = (head == WSI_HEAD_SEG) ? (size_t)n * 4 * ph * pw : (size_t)n * plan->out_dim;
@@ -816,6 +967,9 @@ int wsi_ctx_create(int device, wsi_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->err_flag.alloc(sizeof(int));
   CUDA_CHECK(cudaMemset(ctx->err_flag.p, 0, sizeof(int)));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ctx->idx_event, cudaEventDisableTiming));
   init_tensor_map_api();
   *out = ctx.release();
   WSI_API_END(c)
@@ -827,6 +981,10 @@ int wsi_ctx_destroy(wsi_ctx* ctx) {
   cudaDeviceSynchronize();
   for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  for (auto e : ctx->order_events) cudaEventDestroy(e);
+  if (ctx->idx_event) cudaEventDestroy(ctx->idx_event);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   delete ctx;
   return WSI_OK;
 }
@@ -839,6 +997,10 @@ int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value) {
   const std::string k(key);
   if (k == "batch_tiles") { WSI_REQUIRE(value >= 0 && value <= 4096, WSI_ERR_INVALID, "batch_tiles out of range"); ctx->batch_tiles = value; }
   else if (k == "stage_timing") ctx->stage_timing = value ? 1 : 0;
+  else if (k == "precision") {
+    WSI_REQUIRE(value == WSI_PRECISION_BF16 || value == WSI_PRECISION_FP32, WSI_ERR_INVALID, "precision must be WSI_PRECISION_BF16 (0) or WSI_PRECISION_FP32 (1)");
+    ctx->precision = (int)value;
+  }
   else WSI_THROW(WSI_ERR_INVALID, "unknown option '%s'", key);
   WSI_API_END(ctx)
 }
@@ -892,7 +1054,6 @@ int wsi_forward_batch(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_
   CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
   NetPlan* plan = get_plan(ctx, head, (int)n, h, w);
-  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
   const float* xd = x;
   const size_t in_bytes = (size_t)n * 3 * h * w * sizeof(float);
   DevBuf tmp;
@@ -903,7 +1064,7 @@ int wsi_forward_batch(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, int32_
   }
   {
     StageScope scope(ctx, s, ST_GATHER, (double)n * h * w * 18.0);
-    launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc);
+    launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc, 0, plan->in_planes(), plan->in_plane_stride());
   }
   forward_common(ctx, plan, (int)n, head, out, mem, s);
   WSI_API_END(ctx)
@@ -917,7 +1078,6 @@ int wsi_forward_batch_tta(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, in
   CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
   NetPlan* plan = get_plan(ctx, head, (int)n, h, w);
-  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
   const float* xd = x;
   const size_t in_bytes = (size_t)n * 3 * h * w * sizeof(float);
   DevBuf tmp, acc;
@@ -935,7 +1095,7 @@ int wsi_forward_batch_tta(wsi_ctx* ctx, const float* x, int64_t n, int32_t h, in
   for (int view = 0; view < 4; ++view) {                                 // utils/eval.py:305-318 / :386-399
     {
       StageScope scope(ctx, s, ST_GATHER, (double)n * h * w * 18.0);
-      launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc, view);
+      launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc, view, plan->in_planes(), plan->in_plane_stride());
     }
     plan->run(ctx, s);
     launch_tta_accumulate(dst, plan->logits.as<float>(), out_elems, view == 0, view == 3 ? 4.f : 0.f, s, &ctx->lc);
@@ -961,7 +1121,6 @@ int wsi_forward_patches(wsi_ctx* ctx, const float* xs, int64_t B, int32_t P, int
               WSI_ERR_NOMODEL, "fc.0 / fc.2 do not match %d patches x 512 features", P);
   const int n_hid = (int)w1.shape[0], n_out = (int)w2.shape[0];
   NetPlan* plan = get_plan(ctx, WSI_HEAD_CLS, (int)n, h, w);
-  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
   DevBuf tmp, hid, ens_d;
   const float* xd = xs;
   const size_t in_bytes = (size_t)n * 3 * h * w * sizeof(float);
@@ -972,7 +1131,7 @@ int wsi_forward_patches(wsi_ctx* ctx, const float* xs, int64_t B, int32_t P, int
   }
   {
     StageScope scope(ctx, s, ST_GATHER, (double)n * h * w * 18.0);
-    launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc);
+    launch_pack_nchw(xd, (int)n, h, w, plan->in_pad.as<bf16>(), s, &ctx->lc, 0, plan->in_planes(), plan->in_plane_stride());
   }
   forward_common(ctx, plan, (int)n, WSI_HEAD_CLS, y, mem, s);            // trunk + avgpool + fc0 for all P*B patches
   if (!ctx->ens_ready) {
@@ -1006,16 +1165,15 @@ int wsi_forward_tiles(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* 
   check_tiles(slide, tiles_xy, n_tiles, rows_r);
   ensure_lut(ctx);
   NetPlan* plan = get_plan(ctx, head, (int)n_tiles, slide->ph, slide->pw);
-  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
   int64_t rstride = 0;
-  const uint8_t* rgb = stage_raster(ctx, slide, rows_r, &rstride, s);
+  const uint8_t* rgb = stage_raster_all(ctx, slide, rows_r, &rstride, s);
   std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * n_tiles);
   upload(ctx->tiles_dev, xy, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
   {
     StageScope scope(ctx, s, ST_GATHER, 9.0 * n_tiles * slide->ph * slide->pw);
     launch_gather(rgb, rstride, slide->row0, ctx->tiles_dev.as<int32_t>(), (int)n_tiles, slide->ph, slide->pw, ctx->lut.as<float>(),
-                  plan->in_pad.as<bf16>(), nullptr, s, &ctx->lc);
+                  plan->in_pad.as<bf16>(), nullptr, s, &ctx->lc, plan->in_planes(), plan->in_plane_stride());
   }
   forward_common(ctx, plan, (int)n_tiles, head, out, mem, s);
   WSI_API_END(ctx)
@@ -1170,7 +1328,6 @@ int wsi_debug_conv(wsi_ctx* ctx, const void* x, int n, int h, int w, int cin, co
   WSI_REQUIRE(ctx && x && wt && y, WSI_ERR_INVALID, "NULL argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
   std::vector<ConvInputPart> parts;
   parts.push_back(ConvInputPart{TensorView{x, n, h, w, cin}, up2 != 0});
   if (skip) parts.push_back(ConvInputPart{TensorView{skip, n, up2 ? 2 * h : h, up2 ? 2 * w : w, cskip}, false});
@@ -1196,6 +1353,50 @@ int wsi_debug_conv(wsi_ctx* ctx, const void* x, int n, int h, int w, int cin, co
   WSI_API_END(ctx)
 }
 
+int wsi_debug_conv_f32(wsi_ctx* ctx, const float* x, int n, int h, int w, int cin, const float* wt, int cout, int ksize, int stride, int pad,
+                       const float* scale, const float* bias, const float* res, int relu, int up2, const float* skip, int cskip, float* y,
+                       void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && x && wt && y, WSI_ERR_INVALID, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int hin = up2 ? 2 * h : h, win = up2 ? 2 * w : w;
+  const int oh = (hin + 2 * pad - ksize) / stride + 1, ow = (win + 2 * pad - ksize) / stride + 1;
+  DevBuf xs, ss, rs, ys;
+  xs.alloc((size_t)n * h * w * cin * 3 * 2);
+  launch_split_planes(x, (int64_t)n * h * w, cin, xs.as<bf16>(), s, &ctx->lc);
+  std::vector<ConvInputPart> parts;
+  parts.push_back(ConvInputPart{TensorView{xs.p, n, h, w, cin}, up2 != 0});
+  if (skip) {
+    ss.alloc((size_t)n * hin * win * cskip * 3 * 2);
+    launch_split_planes(skip, (int64_t)n * hin * win, cskip, ss.as<bf16>(), s, &ctx->lc);
+    parts.push_back(ConvInputPart{TensorView{ss.p, n, hin, win, cskip}, false});
+  }
+  if (res) {
+    rs.alloc((size_t)n * oh * ow * cout * 3 * 2);
+    launch_split_planes(res, (int64_t)n * oh * ow, cout, rs.as<bf16>(), s, &ctx->lc);
+  }
+  ys.alloc((size_t)n * oh * ow * cout * 3 * 2);
+  ConvSpec sp;
+  sp.ksize = ksize; sp.stride = stride; sp.pad = pad; sp.cout = cout; sp.relu = relu != 0;
+  ConvOp op;
+  op.build(parts, sp, wt, scale, bias, res ? rs.p : nullptr, ys.p, nullptr, nullptr, nullptr, ctx->err_flag.as<int>(), ctx->num_sms, LAYOUT_NHWC,
+           LAYOUT_NHWC, 1);
+  op.launch(s, &ctx->lc);
+  launch_merge_planes(ys.as<bf16>(), (int64_t)n * oh * ow, cout, y, s, &ctx->lc);
+  check_device_flag(ctx, s);
+  WSI_API_END(ctx)
+}
+
+int wsi_check(wsi_ctx* ctx, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx, WSI_ERR_INVALID, "ctx is NULL");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  check_device_flag(ctx, (cudaStream_t)stream);
+  resolve_spans(ctx);
+  WSI_API_END(ctx)
+}
+
 int wsi_debug_gather(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int n, float* norm_out, void* padded_out,
                      void* stream) {
   WSI_API_BEGIN
@@ -1207,7 +1408,7 @@ int wsi_debug_gather(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* t
   check_tiles(slide, tiles_xy, n, rows_r);
   ensure_lut(ctx);
   int64_t rstride = 0;
-  const uint8_t* rgb = stage_raster(ctx, slide, rows_r, &rstride, s);
+  const uint8_t* rgb = stage_raster_all(ctx, slide, rows_r, &rstride, s);
   std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * (size_t)n);
   upload(ctx->tiles_dev, xy, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1228,9 +1429,8 @@ int wsi_debug_stem(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* til
   const int64_t rows_r = (slide->rows == 0 && slide->row0 == 0) ? slide->ih : slide->rows;
   check_tiles(slide, tiles_xy, n, rows_r);
   ensure_lut(ctx);
-  CUDA_CHECK(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), s));
   int64_t rstride = 0;
-  const uint8_t* rgb = stage_raster(ctx, slide, rows_r, &rstride, s);
+  const uint8_t* rgb = stage_raster_all(ctx, slide, rows_r, &rstride, s);
   std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * (size_t)n);
   upload(ctx->tiles_dev, xy, s);
   CUDA_CHECK(cudaStreamSynchronize(s));

@@ -16,14 +16,21 @@ namespace wsi {
 __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t row0,
                                                       const int32_t* __restrict__ tiles_xy, int n_tiles, int ph, int pw,
                                                       const float* __restrict__ lut, bf16* __restrict__ padded,
-                                                      float* __restrict__ norm_out) {
-  // s_lut: the 3x256 possible outputs of Normalize(ToTensor(u8)) in fp32 (host-built, reference op order)
+                                                      float* __restrict__ norm_out, int planes, int64_t plane_stride) {
+  // s_lut: the 3x256 possible outputs of Normalize(ToTensor(u8)) in fp32 (host-built, reference op order), rounded to
+  // bf16 — and, for the fp32-emulated precision (planes == 3), the bf16 remainders b = rn(v - a), c = rn(v - a - b)
   __shared__ float s_f32[768];
-  __shared__ uint16_t s_lut[768];
+  __shared__ uint16_t s_lut[3][768];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
     const float v = lut[i];
     s_f32[i] = v;
-    s_lut[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    float r = v;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const bf16 h = __float2bfloat16_rn(r);
+      s_lut[j][i] = __bfloat16_as_ushort(h);
+      r -= __bfloat162float(h);
+    }
   }
   __syncthreads();
   // persistent blocks over (tile, row) pairs: the table is built once per block, not once per 512 pixels
@@ -35,12 +42,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
     bf16* dst = padded + ((int64_t)t * (ph + 6) + (r + 3)) * pitch + 3 * 4;
     for (int x = threadIdx.x; x < pw; x += blockDim.x) {
       const uint8_t c0 = __ldg(src + 3 * x), c1 = __ldg(src + 3 * x + 1), c2 = __ldg(src + 3 * x + 2);
-      const uint16_t v0 = s_lut[c0], v1 = s_lut[256 + c1], v2 = s_lut[512 + c2];
       if (padded) {
-        uint2 o;
-        o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
-        o.y = (uint32_t)v2;
-        *reinterpret_cast<uint2*>(dst + 4 * x) = o;
+        for (int j = 0; j < planes; ++j) {
+          const uint16_t v0 = s_lut[j][c0], v1 = s_lut[j][256 + c1], v2 = s_lut[j][512 + c2];
+          uint2 o;
+          o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
+          o.y = (uint32_t)v2;
+          *reinterpret_cast<uint2*>(dst + (int64_t)j * plane_stride + 4 * x) = o;
+        }
       }
       if (norm_out) {
         const int64_t plane = (int64_t)ph * pw;
@@ -54,17 +63,19 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
 }
 
 void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n, int ph,
-                   int pw, const float* lut_dev, bf16* padded, float* norm_out, cudaStream_t s, LaunchCounter* lc) {
+                   int pw, const float* lut_dev, bf16* padded, float* norm_out, cudaStream_t s, LaunchCounter* lc, int planes,
+                   int64_t plane_stride) {
   if (n <= 0) return;
   const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n * ph, 148 * 8);
-  gather_kernel<<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out);
+  gather_kernel<<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, planes, plane_stride);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
 
 // view: the test-time-augmentation views of predict_reg / predict_breastpathq (utils/eval.py:305-310, square tiles):
 //   0 image, 1 image.transpose(2, 3), 2 image.flip(2), 3 image.transpose(2, 3).flip(3) — folded into the read address
-__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ x, int h, int w, int view, bf16* __restrict__ padded) {
+__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ x, int h, int w, int view, bf16* __restrict__ padded, int planes,
+                                                        int64_t plane_stride) {
   const int t = blockIdx.x / h, r = blockIdx.x % h;
   const int64_t plane = (int64_t)h * w;
   const float* img = x + (int64_t)t * 3 * plane;
@@ -77,19 +88,24 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict_
     else if (view == 2) { sy = h - 1 - r; }
     else if (view == 3) { sy = w - 1 - c; sx = r; }
     const float* src = img + (int64_t)sy * w + sx;
-    __nv_bfloat162 a = __floats2bfloat162_rn(src[0], src[plane]);
-    __nv_bfloat162 b = __floats2bfloat162_rn(src[2 * plane], 0.f);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&a);
-    o.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(dst + 4 * c) = o;
+    float v0 = src[0], v1 = src[plane], v2 = src[2 * plane];
+    for (int j = 0; j < planes; ++j) {          // planes == 3: bf16 expansion a + b + c of the fp32 value
+      __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v2, 0.f);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(dst + (int64_t)j * plane_stride + 4 * c) = o;
+      v0 -= __low2float(a); v1 -= __high2float(a); v2 -= __low2float(b);
+    }
   }
 }
 
-void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc, int view) {
+void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc, int view, int planes,
+                      int64_t plane_stride) {
   if (n <= 0) return;
   WSI_REQUIRE(view == 0 || h == w, WSI_ERR_UNSUPPORTED, "TTA views need square tiles (%dx%d)", h, w);
-  pack_nchw_kernel<<<(unsigned)((int64_t)n * h), 256, 0, s>>>(x, h, w, view, padded);
+  pack_nchw_kernel<<<(unsigned)((int64_t)n * h), 256, 0, s>>>(x, h, w, view, padded, planes, plane_stride);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
@@ -157,6 +173,65 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const bf16* __restrict__ x
   }
 }
 
+// fp32-emulated precision: x is [n, h, w, 3c] = three bf16 planes [a | b | c] whose sum is the fp32 activation; the
+// maximum is taken over the sums (exact in fp32) and its three planes are copied through
+__global__ void __launch_bounds__(256) maxpool_split_kernel(const bf16* __restrict__ x, int n, int h, int w, int c, bf16* __restrict__ y) {
+  const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1, cg = c / 8;
+  const int64_t total = (int64_t)n * oh * ow * cg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    int64_t r = i / cg;
+    const int ox = (int)(r % ow); r /= ow;
+    const int oy = (int)(r % oh);
+    const int b = (int)(r / oh);
+    float m[8];
+    uint16_t best[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; best[0][j] = 0xff80; best[1][j] = 0; best[2][j] = 0; }
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int iy = 2 * oy + dy;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ix = 2 * ox + dx;
+        if (ix < 0 || ix >= w) continue;
+        const bf16* px = x + (((int64_t)b * h + iy) * w + ix) * (3 * c) + g * 8;
+        uint4 v[3];
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) v[pl] = __ldg(reinterpret_cast<const uint4*>(px + pl * c));
+        const uint16_t* e0 = reinterpret_cast<const uint16_t*>(&v[0]);
+        const uint16_t* e1 = reinterpret_cast<const uint16_t*>(&v[1]);
+        const uint16_t* e2 = reinterpret_cast<const uint16_t*>(&v[2]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f = (__uint_as_float((uint32_t)e0[j] << 16) + __uint_as_float((uint32_t)e1[j] << 16)) + __uint_as_float((uint32_t)e2[j] << 16);
+          if (f > m[j]) { m[j] = f; best[0][j] = e0[j]; best[1][j] = e1[j]; best[2][j] = e2[j]; }
+        }
+      }
+    }
+    bf16* o = y + (((int64_t)b * oh + oy) * ow + ox) * (3 * c) + g * 8;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      uint4 q;
+      q.x = (uint32_t)best[pl][0] | ((uint32_t)best[pl][1] << 16);
+      q.y = (uint32_t)best[pl][2] | ((uint32_t)best[pl][3] << 16);
+      q.z = (uint32_t)best[pl][4] | ((uint32_t)best[pl][5] << 16);
+      q.w = (uint32_t)best[pl][6] | ((uint32_t)best[pl][7] << 16);
+      *reinterpret_cast<uint4*>(o + pl * c) = q;
+    }
+  }
+}
+
+void launch_maxpool_split(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc) {
+  const int64_t total = (int64_t)n * ((h - 1) / 2 + 1) * ((w - 1) / 2 + 1) * (c / 8);
+  if (total <= 0) return;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+  maxpool_split_kernel<<<grid, 256, 0, s>>>(x, n, h, w, c, y);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
 void launch_maxpool(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc) {
   const int64_t total = (int64_t)n * ((h - 1) / 2 + 1) * ((w - 1) / 2 + 1) * (c / 8);
   if (total <= 0) return;
@@ -173,14 +248,19 @@ void launch_maxpool(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStre
 __global__ void __launch_bounds__(512) pool_head_kernel(const bf16* __restrict__ x4, int hw, int c,
                                                          const float* __restrict__ w1, const float* __restrict__ b1, int n1,
                                                          const float* __restrict__ w2, const float* __restrict__ b2, int n2,
-                                                         float* __restrict__ feat_out, float* __restrict__ out) {
+                                                         float* __restrict__ feat_out, float* __restrict__ out, int planes) {
   __shared__ float s_feat[512];
   __shared__ float s_hid[512];
   const int t = blockIdx.x;
-  const bf16* src = x4 + (int64_t)t * hw * c;
+  const int cs = c * planes;                       // planes == 3: pixel = [a | b | c] bf16 planes of the fp32 activation
+  const bf16* src = x4 + (int64_t)t * hw * cs;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float s = 0.f;
-    for (int i = 0; i < hw; ++i) s += __bfloat162float(src[(int64_t)i * c + ch]);
+    for (int i = 0; i < hw; ++i) {
+      float v = __bfloat162float(src[(int64_t)i * cs + ch]);
+      if (planes == 3) v = (v + __bfloat162float(src[(int64_t)i * cs + c + ch])) + __bfloat162float(src[(int64_t)i * cs + 2 * c + ch]);
+      s += v;
+    }
     s = s / (float)hw;
     s_feat[ch] = s;
     if (feat_out) feat_out[(int64_t)t * c + ch] = s;
@@ -211,10 +291,47 @@ __global__ void __launch_bounds__(512) pool_head_kernel(const bf16* __restrict__
 }
 
 void launch_pool_head(const bf16* x4, int n, int hw, int c, const float* w1, const float* b1, int n1, const float* w2,
-                      const float* b2, int n2, float* feat_out, float* out, cudaStream_t s, LaunchCounter* lc) {
+                      const float* b2, int n2, float* feat_out, float* out, cudaStream_t s, LaunchCounter* lc, int planes) {
   WSI_REQUIRE(c <= 512 && n1 <= 512, WSI_ERR_UNSUPPORTED, "pool_head: c=%d n1=%d", c, n1);
   if (n <= 0) return;
-  pool_head_kernel<<<n, 512, 0, s>>>(x4, hw, c, w1, b1, n1, w2, b2, n2, feat_out, out);
+  pool_head_kernel<<<n, 512, 0, s>>>(x4, hw, c, w1, b1, n1, w2, b2, n2, feat_out, out, planes);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+
+// fp32 NHWC [px][c] <-> three bf16 planes [px][a(c) | b(c) | c(c)] (per-layer tests of the fp32-emulated convs)
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t px, int c, bf16* __restrict__ y) {
+  const int64_t total = px * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / c;
+    const int ch = (int)(i - p * c);
+    float r = x[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const bf16 h = __float2bfloat16_rn(r);
+      y[p * 3 * c + (int64_t)j * c + ch] = h;
+      r -= __bfloat162float(h);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) merge_planes_kernel(const bf16* __restrict__ x, int64_t px, int c, float* __restrict__ y) {
+  const int64_t total = px * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / c;
+    const int ch = (int)(i - p * c);
+    const bf16* q = x + p * 3 * c + ch;
+    y[i] = (__bfloat162float(q[0]) + __bfloat162float(q[c])) + __bfloat162float(q[2 * c]);
+  }
+}
+void launch_split_planes(const float* x, int64_t px, int c, bf16* y, cudaStream_t s, LaunchCounter* lc) {
+  if (px * c <= 0) return;
+  split_planes_kernel<<<(int)std::min<int64_t>(ceil_div(px * c, 256), 148 * 16), 256, 0, s>>>(x, px, c, y);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n++;
+}
+void launch_merge_planes(const bf16* x, int64_t px, int c, float* y, cudaStream_t s, LaunchCounter* lc) {
+  if (px * c <= 0) return;
+  merge_planes_kernel<<<(int)std::min<int64_t>(ceil_div(px * c, 256), 148 * 16), 256, 0, s>>>(x, px, c, y);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
@@ -266,144 +383,141 @@ __device__ __forceinline__ void for_each_cover(const RectIndex& ri, int t0, int 
 }
 
 // =============================================================================================
-// K6 (seg): overlap-accumulate, reference pred[:, ty:ty+dy, tx:tx+dx] += pred_src[bj]
-// (utils/eval.py:213-215), gather formulation.
+// K6 + K7 fused, canvas-free (north_star (4)).
+//   reference: pred[:, ty:ty+dy, tx:tx+dx] += pred_src[bj] into a float64 canvas (utils/eval.py:183,213-215), then
+//   threshold_probs (utils/preprocessing.py:156-172: torch.softmax of the SUMMED logits in float64, per-class floor,
+//   np.argmax = first maximum) and the heatmap (utils/eval.py:220-228: p[2]+p[3] | p[1], x mask, np.uint8(255 * h)
+//   = truncation).
+//   Gather formulation: one owner thread per canvas pixel sums the logits of every tile covering it, in the fixed
+//   sorted (ty, tx) order, starting from zero, in DOUBLE like the reference's canvas (a sum of <= 64 fp32 values is
+//   exact in double unless their magnitudes differ by > 2^25, so the result does not depend on the order the
+//   reference's shuffling DataLoader presents the tiles in), then softmax / floor / argmax / heat in double, and writes
+//   the u8 mask + u8 heatmap (+ optional fp32 summed logits and probabilities).  No canvas, no atomics: every logit is
+//   read exactly once (T*P*16 B) and every output pixel written once (2 B) — SURVEY §8d's fused figure.
+//   A CTA owns 256 consecutive pixels of one canvas row: the covering tile rows and the candidate tiles of each are
+//   found ONCE per CTA (uniform binary searches on the sorted index), not once per pixel.
 // =============================================================================================
-__global__ void __launch_bounds__(256) stitch_seg_kernel(float4* __restrict__ canvas, RectIndex ri, const float4* __restrict__ logits,
-                                                          int t0, int t1, int logit_base, int64_t W2, int64_t own0, int y_lo, int x_lo, int x_hi) {
-  const int Y = y_lo + blockIdx.y;
-  const int X = x_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (X >= x_hi) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  bool any = false;
-  const int64_t plane = (int64_t)ri.dx * ri.dy;
-  for_each_cover(ri, t0, t1, X, Y, [&](int i, int ox, int oy) {
-    const float4 v = __ldg(logits + (int64_t)(i - logit_base) * plane + (int64_t)oy * ri.dx + ox);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    any = true;
-  });
-  if (any) {
-    float4* c = canvas + (int64_t)(Y - own0) * W2 + X;
-    float4 o = *c;
-    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-    *c = o;
-  }
-}
+struct PixelOut { uint8_t cls, heat; double p[4]; };
 
-void launch_stitch_seg_box(float4* canvas, const RectIndex& ri, const float4* logits, int t0, int t1, int logit_base,
-                           int64_t W2, int64_t own0, int64_t own1, int y_lo, int y_hi, int x_lo, int x_hi,
-                           cudaStream_t s, LaunchCounter* lc) {
-  y_lo = (int)std::max<int64_t>(y_lo, own0);
-  y_hi = (int)std::min<int64_t>(y_hi, own1);
-  x_lo = std::max(x_lo, 0);
-  x_hi = (int)std::min<int64_t>(x_hi, W2);
-  if (y_hi <= y_lo || x_hi <= x_lo) return;
-  dim3 grid((unsigned)ceil_div(x_hi - x_lo, 256), (unsigned)(y_hi - y_lo));
-  stitch_seg_kernel<<<grid, 256, 0, s>>>(canvas, ri, logits, t0, t1, logit_base, W2, own0, y_lo, x_lo, x_hi);
-  CUDA_CHECK(cudaGetLastError());
-  if (lc) lc->n++;
-}
-
-// =============================================================================================
-// K7: threshold_probs (utils/preprocessing.py:156-172) + heatmap (utils/eval.py:220-228)
-//   softmax over the SUMMED logits, per-class floor, first-max argmax, heat = p[2]+p[3] | p[1],
-//   x mask, uint8(255*h) truncation.
-// =============================================================================================
-struct PixelOut { uint8_t cls, heat; float p[4]; };
-
-__device__ __forceinline__ PixelOut finalise_pixel(const float4 l, float maskv, const float* cp, int heat_mode) {
+__device__ __forceinline__ PixelOut finalise_pixel(double l0, double l1, double l2, double l3, double maskv, const double* cp, int heat_mode) {
   PixelOut o;
-  const float mx = fmaxf(fmaxf(l.x, l.y), fmaxf(l.z, l.w));
-  float e0 = expf(l.x - mx), e1 = expf(l.y - mx), e2 = expf(l.z - mx), e3 = expf(l.w - mx);
-  const float inv = 1.f / (e0 + e1 + e2 + e3);
-  float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv, p3 = e3 * inv;
-  if (p0 < cp[0]) p0 = 0.f;
-  if (p1 < cp[1]) p1 = 0.f;
-  if (p2 < cp[2]) p2 = 0.f;
-  if (p3 < cp[3]) p3 = 0.f;
-  int am = 0; float best = p0;
+  const double mx = fmax(fmax(l0, l1), fmax(l2, l3));
+  const double e0 = exp(l0 - mx), e1 = exp(l1 - mx), e2 = exp(l2 - mx), e3 = exp(l3 - mx);
+  const double sum = ((e0 + e1) + e2) + e3;                 // torch's vec_softmax: sequential over the class dim
+  double p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
+  if (p0 < cp[0]) p0 = 0.0;
+  if (p1 < cp[1]) p1 = 0.0;
+  if (p2 < cp[2]) p2 = 0.0;
+  if (p3 < cp[3]) p3 = 0.0;
+  int am = 0; double best = p0;
   if (p1 > best) { best = p1; am = 1; }
   if (p2 > best) { best = p2; am = 2; }
   if (p3 > best) { best = p3; am = 3; }
-  const float h = (heat_mode == 1) ? p1 : (p2 + p3);
-  const float hv = 255.f * (maskv * h);
+  const double h = (heat_mode == 1) ? p1 : (p2 + p3);
+  const double hv = 255.0 * (maskv * h);
   o.cls = (uint8_t)am;
-  o.heat = (uint8_t)(int)fminf(hv, 255.f);
+  o.heat = (uint8_t)(int)fmin(hv, 255.0);
   o.p[0] = p0; o.p[1] = p1; o.p[2] = p2; o.p[3] = p3;
   return o;
 }
 
-__device__ __forceinline__ void write_pixel(const FinaliseArgs& a, int64_t idx, int64_t plane, const float4 l, const PixelOut& o) {
+__device__ __forceinline__ void write_pixel(const FinaliseArgs& a, int64_t idx, int64_t plane, double l0, double l1, double l2, double l3,
+                                            const PixelOut& o) {
   a.classes[idx] = o.cls;
   a.heatmap[idx] = o.heat;
   if (a.canvas_out) {
-    a.canvas_out[idx] = l.x; a.canvas_out[plane + idx] = l.y; a.canvas_out[2 * plane + idx] = l.z; a.canvas_out[3 * plane + idx] = l.w;
+    a.canvas_out[idx] = (float)l0; a.canvas_out[plane + idx] = (float)l1; a.canvas_out[2 * plane + idx] = (float)l2; a.canvas_out[3 * plane + idx] = (float)l3;
   }
   if (a.probs_out) {
-    a.probs_out[idx] = o.p[0]; a.probs_out[plane + idx] = o.p[1]; a.probs_out[2 * plane + idx] = o.p[2]; a.probs_out[3 * plane + idx] = o.p[3];
+    a.probs_out[idx] = (float)o.p[0]; a.probs_out[plane + idx] = (float)o.p[1]; a.probs_out[2 * plane + idx] = (float)o.p[2];
+    a.probs_out[3 * plane + idx] = (float)o.p[3];
   }
 }
 
-// 4 pixels per thread: 64 B canvas read, 4 B + 4 B output
-__global__ void __launch_bounds__(256) finalise_seg_kernel(const float4* __restrict__ canvas, FinaliseArgs a) {
-  const int64_t rows = a.own1 - a.own0, plane = rows * a.W2;
-  const int64_t quads = (plane + 3) / 4;
-  for (int64_t qd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t base = qd * 4;
-    if (base + 3 < plane && !a.canvas_out && !a.probs_out) {
-      uint32_t cw = 0, hw = 0;
-      uint32_t mk = 0x01010101u;
-      if (a.mask) mk = *reinterpret_cast<const uint32_t*>(a.mask + base);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 l = __ldg(canvas + base + j);
-        const PixelOut o = finalise_pixel(l, (float)((mk >> (8 * j)) & 0xffu), a.class_probs, a.heat_mode);
-        cw |= (uint32_t)o.cls << (8 * j);
-        hw |= (uint32_t)o.heat << (8 * j);
-      }
-      *reinterpret_cast<uint32_t*>(a.classes + base) = cw;
-      *reinterpret_cast<uint32_t*>(a.heatmap + base) = hw;
-    } else {
-      for (int64_t idx = base; idx < base + 4 && idx < plane; ++idx) {
-        const float4 l = canvas[idx];
-        const float mv = a.mask ? (float)a.mask[idx] : 1.f;
-        const PixelOut o = finalise_pixel(l, mv, a.class_probs, a.heat_mode);
-        write_pixel(a, idx, plane, l, o);
-      }
+// visit, in sorted order, the tiles of [t_lo, t_hi) that cover row Y and may cover columns [X0, X0 + 256): f(i, tx, oy).
+// All control flow is uniform across the CTA.
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo, int t_hi, int X0, int Y, F&& f) {
+  int lo = 0, hi = ri.R;
+  while (lo < hi) {  // first row with row_y > Y - dy
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(ri.row_y + mid) > Y - ri.dy) hi = mid; else lo = mid + 1;
+  }
+  for (int r = lo; r < ri.R; ++r) {
+    const int ry = __ldg(ri.row_y + r);
+    if (ry > Y) break;
+    const int a = max(__ldg(ri.row_start + r), t_lo), b = min(__ldg(ri.row_start + r + 1), t_hi);
+    if (a >= b) continue;
+    int l2 = a, h2 = b;
+    while (l2 < h2) {  // first rect with tx > X0 - dx
+      const int mid = (l2 + h2) >> 1;
+      if (__ldg(ri.tx + mid) > X0 - ri.dx) h2 = mid; else l2 = mid + 1;
+    }
+    for (int i = l2; i < b; ++i) {
+      const int tx = __ldg(ri.tx + i);
+      if (tx > X0 + 255) break;
+      f(i, tx, Y - ry);
     }
   }
 }
 
-void launch_finalise_seg(const float4* canvas, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
-  const int64_t plane = (a.own1 - a.own0) * a.W2;
-  if (plane <= 0) return;
-  const int grid = (int)std::min<int64_t>(ceil_div(ceil_div(plane, 4), 256), 148 * 32);
-  finalise_seg_kernel<<<grid, 256, 0, s>>>(canvas, a);
+// seg: logits of sorted tile i live in slot i % ring_cap of `ring` (f32 [ring_cap][dy][dx][4]); rows [y0, y0 + gridDim.x)
+__global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, const float4* __restrict__ ring, int ring_cap, int t_lo, int t_hi,
+                                                                   int y0, FinaliseArgs a) {
+  const int Y = y0 + blockIdx.x;
+  const int X0 = blockIdx.y * 256;
+  const int X = X0 + threadIdx.x;
+  const bool live = X < a.W2;
+  const int64_t tile_px = (int64_t)ri.dx * ri.dy;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for_each_candidate(ri, t_lo, t_hi, X0, Y, [&](int i, int tx, int oy) {
+    const int ox = X - tx;
+    if (live && ox >= 0 && ox < ri.dx) {
+      const float4 v = __ldg(ring + (int64_t)(i % ring_cap) * tile_px + (int64_t)oy * ri.dx + ox);
+      s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+    }
+  });
+  if (!live) return;
+  const int64_t idx = (int64_t)(Y - a.own0) * a.W2 + X, plane = (a.own1 - a.own0) * a.W2;
+  const double mv = a.mask ? (double)a.mask[idx] : 1.0;
+  const PixelOut o = finalise_pixel(s0, s1, s2, s3, mv, a.class_probs, a.heat_mode);
+  write_pixel(a, idx, plane, s0, s1, s2, s3, o);
+}
+
+void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int64_t y0, int64_t y1,
+                                const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
+  if (y1 <= y0 || a.W2 <= 0) return;
+  dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256));
+  stitch_finalise_seg_kernel<<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, (int)y0, a);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
 
-// K6+K7 (cls): pred_src [C] broadcast over the rectangle (utils/eval.py:210-215), canvas never materialised
-__global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, const float4* __restrict__ tile_logits, int T, FinaliseArgs a) {
-  const int64_t rows = a.own1 - a.own0, plane = rows * a.W2;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int Y = (int)(a.own0 + idx / a.W2), X = (int)(idx % a.W2);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for_each_cover(ri, 0, T, X, Y, [&](int i, int, int) {
+// cls: pred_src [C] broadcast over the tile rectangle (utils/eval.py:210-215); tile_logits f32 [T][4] in sorted order
+__global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, const float4* __restrict__ tile_logits, int T, int y0, FinaliseArgs a) {
+  const int Y = y0 + blockIdx.x;
+  const int X0 = blockIdx.y * 256;
+  const int X = X0 + threadIdx.x;
+  const bool live = X < a.W2;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for_each_candidate(ri, 0, T, X0, Y, [&](int i, int tx, int) {
+    const int ox = X - tx;
+    if (live && ox >= 0 && ox < ri.dx) {
       const float4 v = __ldg(tile_logits + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    });
-    const float mv = a.mask ? (float)a.mask[idx] : 1.f;
-    const PixelOut o = finalise_pixel(acc, mv, a.class_probs, a.heat_mode);
-    write_pixel(a, idx, plane, acc, o);
-  }
+      s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+    }
+  });
+  if (!live) return;
+  const int64_t idx = (int64_t)(Y - a.own0) * a.W2 + X, plane = (a.own1 - a.own0) * a.W2;
+  const double mv = a.mask ? (double)a.mask[idx] : 1.0;
+  const PixelOut o = finalise_pixel(s0, s1, s2, s3, mv, a.class_probs, a.heat_mode);
+  write_pixel(a, idx, plane, s0, s1, s2, s3, o);
 }
 
 void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
-  const int64_t plane = (a.own1 - a.own0) * a.W2;
-  if (plane <= 0) return;
-  const int grid = (int)std::min<int64_t>(ceil_div(plane, 256), 148 * 32);
-  stitch_finalise_cls_kernel<<<grid, 256, 0, s>>>(ri, tile_logits, T, a);
+  if (a.own1 <= a.own0 || a.W2 <= 0) return;
+  dim3 grid((unsigned)(a.own1 - a.own0), (unsigned)ceil_div(a.W2, 256));
+  stitch_finalise_cls_kernel<<<grid, 256, 0, s>>>(ri, tile_logits, T, (int)a.own0, a);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }

@@ -20,7 +20,7 @@ struct FinaliseArgs {
   int64_t W2;               // canvas width
   int64_t own0, own1;       // canvas rows handled
   const uint8_t* mask;      // [own1-own0, W2] or nullptr (= ones)
-  float class_probs[4];
+  double class_probs[4];    // per-class floor of threshold_probs (compared in double, as the reference does)
   int heat_mode;            // 0: p[2]+p[3] (seg), 1: p[1] (cls)
   uint8_t* classes;         // [rows, W2]
   uint8_t* heatmap;         // [rows, W2]
@@ -31,28 +31,33 @@ struct FinaliseArgs {
 // K0: raster u8 [rows, iw, 3] -> zero-padded normalised bf16 tiles [n][ph+6][pw+8][4] (interior only)
 void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n,
                    int ph, int pw, const float* lut_dev /*f32 [3][256]*/, bf16* padded_or_null, float* norm_out_or_null,
-                   cudaStream_t s, LaunchCounter* lc);
+                   cudaStream_t s, LaunchCounter* lc, int planes = 1, int64_t plane_stride = 0);
+// (planes == 3, fp32-emulated precision: three padded buffers plane_stride elements apart hold the bf16 expansion a + b + c)
 // normalised f32 NCHW -> padded bf16 tiles (nn.Module shim forward)
-void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc, int view = 0);
+void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc, int view = 0, int planes = 1,
+                      int64_t plane_stride = 0);
 // TTA mean over views in the reference's fp32 order (utils/eval.py:311-334)
 void launch_tta_accumulate(float* acc, const float* v, int64_t n, bool first, float final_div, cudaStream_t s, LaunchCounter* lc);
 // 3x3/s2/p1 max pool, NHWC bf16, C multiple of 8
 void launch_maxpool(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc);
+// same on the three-plane tensors of the fp32-emulated precision: x [n,h,w,3c] -> y [n,oh,ow,3c]
+void launch_maxpool_split(const bf16* x, int n, int h, int w, int c, bf16* y, cudaStream_t s, LaunchCounter* lc);
+// fp32 NHWC <-> three bf16 planes per pixel [a | b | c]
+void launch_split_planes(const float* x, int64_t px, int c, bf16* y, cudaStream_t s, LaunchCounter* lc);
+void launch_merge_planes(const bf16* x, int64_t px, int c, float* y, cudaStream_t s, LaunchCounter* lc);
 // global average pool + up to two Linear layers: feat[512] -> (W1,b1)[n1] (-> ReLU -> (W2,b2)[n2])
 void launch_pool_head(const bf16* x4, int n, int hw, int c, const float* w1, const float* b1, int n1,
                       const float* w2, const float* b2, int n2, float* feat_out_or_null, float* out,
-                      cudaStream_t s, LaunchCounter* lc);
+                      cudaStream_t s, LaunchCounter* lc, int planes = 1);
 // logits f32 NHWC4 [n,h,w,4] -> NCHW [n,4,h,w]
 void launch_nhwc4_to_nchw(const float* x, int n, int h, int w, float* y, cudaStream_t s, LaunchCounter* lc);
 
-// K6 (seg): canvas[own rows][W2] (float4) += sum over the sorted tiles [t0, t1) covering each pixel
-// of the box [y_lo, y_hi) x [x_lo, x_hi) (clipped to the owned rows and the canvas width).
-// logits: f32 [..][ph][pw][4], tile i at index (i - logit_base).  One owner thread per pixel.
-void launch_stitch_seg_box(float4* canvas, const RectIndex& ri, const float4* logits, int t0, int t1, int logit_base,
-                           int64_t W2, int64_t own0, int64_t own1, int y_lo, int y_hi, int x_lo, int x_hi,
-                           cudaStream_t s, LaunchCounter* lc);
-// K7 (seg): canvas -> classes/heatmap (+ optional planar canvas / probs)
-void launch_finalise_seg(const float4* canvas, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc);
+// K6 + K7 fused (seg): rows [y0, y1) of the canvas are final (every tile that touches them is among the sorted tiles
+// [t_lo, t_hi), whose fp32 logits [dy][dx][4] sit in slot (i % ring_cap) of `ring`): sum the covering tiles per pixel in
+// double in sorted order, softmax / floor / argmax / heat, write classes + heatmap (+ optional fp32 canvas / probs).
+// One owner thread per pixel; no canvas in memory, no atomics.
+void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int64_t y0, int64_t y1,
+                                const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc);
 // K6+K7 (cls): per-tile logits [T][4] (sorted order) broadcast over rectangles, summed per pixel and finalised
 void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const FinaliseArgs& a,
                                 cudaStream_t s, LaunchCounter* lc);
