@@ -72,6 +72,26 @@ def plan_tiles(ih, iw, ph, pw, sh, sw, mask=None, m=1.0):
     return out
 
 
+def find_nuclei_hsv(rgb: np.ndarray, mu_percent: float = 0.1) -> np.ndarray:
+    """utils/preprocessing.py:74-110 with the defaults mode='hsv', fill_mask=False:
+    ``color.rgb2hsv(np.asarray(wsi))[..., 1] > mu_percent`` as uint8.
+
+    scikit-image is NOT installed in this image and the reference pins no version: **parity unpinned** against
+    skimage itself.  Restated from skimage's published source (identical in 0.14 ... 0.25): ``rgb2hsv`` first converts
+    the uint8 image with ``img_as_float`` = ``np.multiply(image, 1. / 255, dtype=float64)`` (util/dtype.py ``_convert``:
+    a multiplication by the reciprocal, not a division), then ``out_v = arr.max(-1)``, ``delta = arr.ptp(-1)``,
+    ``out_s = delta / out_v`` with ``out_s[delta == 0.] = 0.``.  The formula is pinned against two independent
+    witnesses in tests/test_oracle_golden.py: stdlib ``colorsys.rgb_to_hsv`` (same (max - min) / max in float64, all
+    256 x 256 (max, min) pairs) and ``cv2.cvtColor(..., COLOR_RGB2HSV)`` on float32 input (away from the threshold)."""
+    arr = np.multiply(np.asarray(rgb)[..., :3], 1.0 / 255, dtype=np.float64)
+    out_v = arr.max(-1)
+    delta = arr.max(-1) - arr.min(-1)          # np.ptp
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out_s = delta / out_v
+    out_s[delta == 0.0] = 0.0
+    return (out_s > mu_percent).astype(np.uint8)
+
+
 # --------------------------------------------------------------------------------------------
 # A2/A3: tile gather + normalise  (utils/dataset.py:171-185, utils/preprocessing.py:206-212)
 # --------------------------------------------------------------------------------------------

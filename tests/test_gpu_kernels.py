@@ -265,9 +265,10 @@ def test_resize_argmax(ctx, shape):
 
 
 def test_find_nuclei_bit_exact(ctx):
-    """A12: find_nuclei(mode='hsv') — the device mask equals the float64 skimage formula (dataset.find_nuclei_hsv restates
-    it) on a synthetic H&E raster, on every (max, min) pair, and for other thresholds."""
-    from wsi_segmentation_pipeline_b200 import dataset as ds
+    """A12: find_nuclei(mode='hsv') — the device mask equals the oracle's float64 restatement of skimage's rgb2hsv
+    saturation rule (oracle.find_nuclei_hsv, pinned in tests/test_oracle_golden.py) on a synthetic H&E raster, on every
+    (max, min) pair, and for other thresholds."""
+    ds = O
     raster = synth.synth_slide(300, 417, 11)
     np.testing.assert_array_equal(ctx.find_nuclei(raster), ds.find_nuclei_hsv(raster))
     dev = ctx.find_nuclei(torch.from_numpy(raster).cuda(), device_out=True)

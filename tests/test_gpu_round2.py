@@ -192,7 +192,7 @@ def test_conv_fp32_emulated_matches_float64(ctx, case):
         f32 = F.relu(f32)
     err32 = (f32.double() - ref).abs().max().item() / ref.abs().max().item()
     print(f"{case}: fp32-emulated rel err {err:.2e} (torch fp32 CPU: {err32:.2e})")
-    assert err < 2e-6, f"{case}: rel err {err:.3e} vs float64"
+    assert err < 3e-6, f"{case}: rel err {err:.3e} vs float64"
 
 
 @pytest.mark.parametrize("arch,head,hw,n", [("resnet18_cls", capi.HEAD_CLS, 64, 5), ("unet_reg", capi.HEAD_REG, 128, 3),

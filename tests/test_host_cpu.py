@@ -38,9 +38,12 @@ def test_empty_slide_is_dropped_like_the_reference():
     assert len(ds.Dataset_wsi(short, ds.DotDict(ph=8, pw=8, sh=8, sw=8), None, scan_level=2)) == 0   # :123-124
 
 
-def test_find_nuclei_hsv_saturation_rule():
-    rgb = np.array([[[240, 240, 240], [200, 100, 180], [0, 0, 0], [100, 91, 100]]], np.uint8)
-    np.testing.assert_array_equal(ds.find_nuclei_hsv(rgb), [[0, 1, 0, 0]])
+def test_no_cpu_find_nuclei_in_the_product_package():
+    """find_nuclei runs on the GPU only: without an engine and without a cached mask the dataset refuses (no CPU fallback)."""
+    assert not hasattr(ds, "find_nuclei_hsv")
+    scan = ds.ArraySlide({2: np.full((200, 200, 3), 128, np.uint8)})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ds.Dataset_wsi(scan, ds.DotDict(ph=64, pw=64, sh=32, sw=32), None, scan_level=2)
 
 
 def _gather_worker(rank, world, port, q):

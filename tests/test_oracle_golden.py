@@ -108,3 +108,27 @@ def test_synth_checksum_is_stable():
     full = synth.synth_slide(256, 2048, 1234)
     np.testing.assert_array_equal(full[100:164], s)
     assert synth.checksum(synth.synth_slide(128, 160, 7)) == synth.checksum(synth.synth_slide(128, 160, 7))
+
+
+def test_find_nuclei_hsv_pinned_by_colorsys_and_cv2():
+    """A12: skimage is absent, so the restated saturation rule is pinned against two independent
+    witnesses.  (1) stdlib colorsys.rgb_to_hsv — s = (maxc - minc) / maxc in float64 — on ALL 256 x 256 (max, min)
+    pairs, fed the same float64 image skimage's img_as_float produces (u8 * (1/255)): identical masks for three
+    thresholds.  (2) cv2.cvtColor(COLOR_RGB2HSV) on the float32 image: identical wherever S is further than 1e-5 from
+    the threshold (cv2 computes in float32)."""
+    import colorsys
+    import cv2
+    mx, mn = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    lo = np.minimum(mx, mn)
+    pairs = np.stack([mx, lo, (mx.astype(int) + lo) // 2], -1).astype(np.uint8)      # max = R, min = G, B in between
+    arr = np.multiply(pairs, 1.0 / 255, dtype=np.float64)
+    sat = np.array([[colorsys.rgb_to_hsv(*arr[i, j])[1] for j in range(256)] for i in range(256)])
+    for mu in (0.1, 0.05, 0.5):
+        np.testing.assert_array_equal(O.find_nuclei_hsv(pairs, mu), (sat > mu).astype(np.uint8))
+        np.testing.assert_array_equal(O.find_nuclei_hsv(np.ascontiguousarray(pairs[..., [2, 0, 1]]), mu), (sat > mu).astype(np.uint8))
+    hsv = cv2.cvtColor(arr.astype(np.float32), cv2.COLOR_RGB2HSV)
+    clear = np.abs(hsv[..., 1].astype(np.float64) - 0.1) > 1e-5
+    np.testing.assert_array_equal(O.find_nuclei_hsv(pairs)[clear], (hsv[..., 1] > 0.1).astype(np.uint8)[clear])
+    # hand-checked pixels: background grey, eosin pink, black (max == 0 -> S = 0), barely-saturated
+    rgb = np.array([[[240, 240, 240], [200, 100, 180], [0, 0, 0], [100, 91, 100]]], np.uint8)
+    np.testing.assert_array_equal(O.find_nuclei_hsv(rgb), [[0, 1, 0, 0]])

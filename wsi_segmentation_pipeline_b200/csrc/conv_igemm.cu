@@ -103,7 +103,7 @@ static inline void split3(float v, uint16_t out[3]) {
     r -= bf16_bits_to_f32(out[j]);
   }
 }
-static const int kSplitBHost[6] = {0, 1, 0, 1, 2, 0};   // weight plane of product pr (kSplitB in conv_igemm.cuh)
+static const int kSplitBHost[6] = {2, 0, 1, 1, 0, 0};   // weight plane of product pr (kSplitB in conv_igemm.cuh)
 
 static inline int floor_div2(int t) { return (t >= 0) ? t / 2 : -((-t + 1) / 2); }
 

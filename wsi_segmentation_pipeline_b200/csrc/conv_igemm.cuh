@@ -79,9 +79,16 @@ struct ConvParams {
   int dbg;                    // -DWSI_DEBUG_SWITCHES builds only (pair kernel timing experiments)
 };
 
-// plane pairs of the fp32 emulation, smallest weights last
-__device__ __constant__ const int8_t kSplitA[6] = {0, 0, 1, 1, 0, 2};
-__device__ __constant__ const int8_t kSplitB[6] = {0, 1, 0, 1, 2, 0};
+// Plane pairs (activation plane, weight plane) of the fp32 emulation, SMALLEST products first.  The tensor core adds
+// into its fp32 accumulator with truncation (measured here: ~2e-8 x |acc| per 128xNx16 MMA, biased — a 4608-long K
+// loop of six products loses 2.6e-5), so the order and length of the accumulation chains matter:
+//   * the five correction products (weights 2^-16, 2^-16, 2^-16, 2^-8, 2^-8) are accumulated first, all K blocks, into
+//     one TMEM accumulator: their chain stays ~2^-8 of the result, its truncation ~1e-10;
+//   * the main product (a, a) is accumulated in short chains of kSplitChunkSteps MMAs, each drained by the epilogue
+//     warps into fp32 REGISTERS (round-to-nearest adds), double-buffered against the next chain.
+__device__ __constant__ const int8_t kSplitA[6] = {0, 2, 1, 0, 1, 0};
+__device__ __constant__ const int8_t kSplitB[6] = {2, 0, 1, 1, 0, 0};
+constexpr int kSplitChunkSteps = 8;     // MMAs (K = 16 each) per main-product chain
 
 struct AMaps {
   CUtensorMap m[kMaxAMaps];
@@ -316,10 +323,12 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
         const int tn = r;
         const int n0 = tn * p.bn, a0 = th * p.bh, b0 = tw * p.bw, co0 = ct * BLOCK_N;
         const KBlock* kb_tbl = tbl + par * num_kb;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const KBlock e = kb_tbl[kb];      // read BEFORE the wait (asm volatile + memory clobber would pin it after)
+        // fp32 emulation: product-major (all K blocks of product 0, then of product 1, ... the main product last)
 #pragma unroll 1
-          for (int pr = 0; pr < NPROD; ++pr) {
+        for (int pr = 0; pr < NPROD; ++pr) {
+#pragma unroll 1
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const KBlock e = kb_tbl[kb];      // read BEFORE the wait (asm volatile + memory clobber would pin it after)
             int mi = e.map, c0 = e.c0;
             if (NSPLIT == 3) { mi += kSplitA[pr] * p.split_map_step; c0 += kSplitA[pr] * p.a_plane[e.map]; }
             ptx::mbar_wait(&empty[stage], phase ^ 1u, p.error_flag, 1);
@@ -354,8 +363,20 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 2);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        constexpr int kChunkKb = (kSplitChunkSteps * 16 >= BLOCK_K) ? kSplitChunkSteps * 16 / BLOCK_K : 1;   // K blocks per main chain
+        int chain0 = 0;                       // first K-block index (product-major order) of the current accumulation chain
         for (int kb = 0; kb < num_kb * NPROD; ++kb) {
+          if (NSPLIT == 3 && kb >= num_kb * (NPROD - 1) && kb > chain0 && (kb - num_kb * (NPROD - 1)) % kChunkKb == 0) {
+            // close the chain (corrections, or kChunkKb main K blocks): hand it to the epilogue, continue in the other buffer
+            ptx::umma_commit(&tmem_full[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+            ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, p.error_flag, 2);
+            ptx::tc_fence_after();
+            d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            chain0 = kb;
+          }
           ptx::mbar_wait(&full[stage], phase, p.error_flag, 3);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * S::kStageBytes);
@@ -365,7 +386,7 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advancing 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
-            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - chain0) | k) != 0));
           }
           ptx::umma_commit(&empty[stage]);      // frees the smem stage when these MMAs retire
           if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
@@ -416,17 +437,53 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
         for (int j = 0; j < STEP / 8; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0) + j);
       }
 
-      ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 4);
-      ptx::tc_fence_after();
+      // fp32 emulation: the accumulation chains of this tile (corrections, then the main product in short chains) arrive
+      // one by one in alternating TMEM buffers and are summed here in fp32 registers (round-to-nearest)
+      float racc[NSPLIT == 3 ? CH : 1];
+      if (NSPLIT == 3) {
+        constexpr int kChunkKb = (kSplitChunkSteps * 16 >= BLOCK_K) ? kSplitChunkSteps * 16 / BLOCK_K : 1;
+        const int n_chains = 1 + (num_kb + kChunkKb - 1) / kChunkKb;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) racc[j] = 0.f;
+#pragma unroll 1
+        for (int chn = 0; chn < n_chains; ++chn) {
+          ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 4);
+          ptx::tc_fence_after();
+          if (!idle) {
+            const uint32_t t_chain = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c_lo);
+#pragma unroll
+            for (int c = 0; c < CH; c += STEP) {
+              uint32_t v[STEP];
+#pragma unroll
+              for (int j = 0; j < STEP; j += 16) ptx::tmem_ld16(t_chain + (uint32_t)(c + j), *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < STEP; ++j) racc[c + j] += __uint_as_float(v[j]);
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tmem_empty[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      } else {
+        ptx::mbar_wait(&tmem_full[acc], acc_phase, p.error_flag, 4);
+        ptx::tc_fence_after();
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c_lo);
 
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (!idle) {
-#pragma unroll 1
+#pragma unroll (NSPLIT == 3 ? 8 : 1)
         for (int c = 0; c < CH; c += STEP) {
           uint32_t v[STEP];
+          if (NSPLIT == 3) {
 #pragma unroll
-          for (int j = 0; j < STEP; j += 16) ptx::tmem_ld16(t_row + (uint32_t)(c + j), *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
+            for (int j = 0; j < STEP; ++j) v[j] = __float_as_uint(racc[c + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < STEP; j += 16) ptx::tmem_ld16(t_row + (uint32_t)(c + j), *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
+          }
           if (has_res && NSPLIT == 1 && c + STEP < CH) {
 #pragma unroll
             for (int j = 0; j < STEP / 8; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(p.res + off0 + c + STEP) + j);
@@ -555,10 +612,12 @@ conv_igemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ C
           reinterpret_cast<float4*>(p.head_out)[pix] = o;
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (NSPLIT == 1) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
     }
   }
 

@@ -1208,11 +1208,13 @@ int wsi_find_nuclei(wsi_ctx* ctx, const uint8_t* rgb, int64_t row_stride, int rg
   WSI_REQUIRE(ctx && rgb && mask && H > 0 && W > 0 && row_stride >= 3 * W, WSI_ERR_INVALID, "bad argument");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
-  // skimage.color.rgb2hsv on the float64 image u8/255: S = (max - min) / max, 0 where max == min; S > mu_percent
+  // skimage.color.rgb2hsv: the u8 image becomes float64 by MULTIPLICATION with 1/255 (skimage.util.dtype._convert:
+  // np.multiply(image, 1. / imax_in)), then S = ptp / max with S = 0 where ptp == 0; mask = S > mu_percent
   std::vector<uint32_t> bits(2048, 0);
+  const double inv255 = 1.0 / 255.0;
   for (int mx = 0; mx < 256; ++mx)
     for (int mn = 0; mn <= mx; ++mn) {
-      const double a = mx / 255.0, b = mn / 255.0, delta = a - b;
+      const double a = mx * inv255, b = mn * inv255, delta = a - b;
       const double sat = (delta == 0.0) ? 0.0 : delta / a;
       if (sat > mu_percent) bits[(mx * 256 + mn) >> 5] |= 1u << ((mx * 256 + mn) & 31);
     }

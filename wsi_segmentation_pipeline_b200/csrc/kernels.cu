@@ -13,20 +13,21 @@ namespace wsi {
 //   reference's exact fp32 op order and rounds it to bf16 once, so the kernel is a byte gather.
 //   Output is the stem's operand layout: [n][ph+6][pw+8][4] bf16, zero border (3 top/left), ch 3 = 0.
 // =============================================================================================
+template <int PLANES>
 __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t row0,
                                                       const int32_t* __restrict__ tiles_xy, int n_tiles, int ph, int pw,
                                                       const float* __restrict__ lut, bf16* __restrict__ padded,
-                                                      float* __restrict__ norm_out, int planes, int64_t plane_stride) {
+                                                      float* __restrict__ norm_out, int64_t plane_stride) {
   // s_lut: the 3x256 possible outputs of Normalize(ToTensor(u8)) in fp32 (host-built, reference op order), rounded to
   // bf16 — and, for the fp32-emulated precision (planes == 3), the bf16 remainders b = rn(v - a), c = rn(v - a - b)
   __shared__ float s_f32[768];
-  __shared__ uint16_t s_lut[3][768];
+  __shared__ uint16_t s_lut[PLANES][768];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
     const float v = lut[i];
     s_f32[i] = v;
     float r = v;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
+    for (int j = 0; j < PLANES; ++j) {
       const bf16 h = __float2bfloat16_rn(r);
       s_lut[j][i] = __bfloat16_as_ushort(h);
       r -= __bfloat162float(h);
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
     for (int x = threadIdx.x; x < pw; x += blockDim.x) {
       const uint8_t c0 = __ldg(src + 3 * x), c1 = __ldg(src + 3 * x + 1), c2 = __ldg(src + 3 * x + 2);
       if (padded) {
-        for (int j = 0; j < planes; ++j) {
+#pragma unroll
+        for (int j = 0; j < PLANES; ++j) {
           const uint16_t v0 = s_lut[j][c0], v1 = s_lut[j][256 + c1], v2 = s_lut[j][512 + c2];
           uint2 o;
           o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
@@ -67,7 +69,8 @@ void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const i
                    int64_t plane_stride) {
   if (n <= 0) return;
   const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n * ph, 148 * 8);
-  gather_kernel<<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, planes, plane_stride);
+  if (planes == 3) gather_kernel<3><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride);
+  else gather_kernel<1><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }

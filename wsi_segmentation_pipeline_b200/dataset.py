@@ -71,23 +71,15 @@ def _level_raster(scan, level: int) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(img), dtype=np.uint8)
 
 
-def find_nuclei_hsv(rgb: np.ndarray, mu_percent: float = 0.1) -> np.ndarray:
-    """utils/preprocessing.py:74-110 with mode='hsv', fill_mask=False: HSV saturation > 0.1,
-    evaluated in float64 as skimage.color.rgb2hsv does (S = (max-min)/max, 0 where max == 0)."""
-    a = rgb.astype(np.float64) / 255.0
-    mx, mn = a.max(-1), a.min(-1)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        s = np.where(mx > 0, (mx - mn) / mx, 0.0)
-    return (s > mu_percent).astype(np.uint8)
-
-
 class Dataset_wsi:
     """One slide: the tile plan (``datalist``: list of (x, y) in scan-level pixels, reference
     order) and lazy access to the scan-level raster."""
 
     def __init__(self, scan, params, mask: Optional[np.ndarray], scan_level: int = 2, engine=None):
-        """engine: a capi.Context — the foreground mask (find_nuclei) and the foreground test of the tile plan then run
-        on the GPU (wsi_find_nuclei / wsi_plan_tiles_gpu, same results); None: host numpy / host C++ planner."""
+        """engine: a capi.Context — the foreground mask (find_nuclei, utils/preprocessing.py:74-110) and the foreground
+        test of the tile plan run on the GPU (wsi_find_nuclei / wsi_plan_tiles_gpu).  With engine None a mask must be
+        given (the reference's cached mask PNG, utils/dataset.py:131-134) and the host C++ planner enumerates the tiles;
+        there is no CPU implementation of find_nuclei in this package."""
         self.scan, self.params, self.scan_level = scan, params, scan_level
         self.datalist, self.tiles = [], np.zeros((0, 2), np.int32)
         self.mask = mask
@@ -96,7 +88,10 @@ class Dataset_wsi:
         self.params.iw, self.params.ih = scan.level_dimensions[scan_level]
         if self.mask is None:                                # :131-134
             thumb = _level_raster(scan, 2)
-            self.mask = engine.find_nuclei(thumb) if engine is not None else find_nuclei_hsv(thumb)
+            if engine is None:
+                raise RuntimeError("no foreground mask for this slide and no engine: find_nuclei runs on the GPU only "
+                                   "(pass engine=capi.Context(...) or a cached mask) — no CPU fallback")
+            self.mask = engine.find_nuclei(thumb)
         self.m = scan.level_downsamples[scan_level] / scan.level_downsamples[2]
         plan = engine.plan_tiles if engine is not None else capi.plan_tiles
         self.tiles = plan(self.params.ih, self.params.iw, self.params.ph, self.params.pw, self.params.sh, self.params.sw, self.mask, self.m)
