@@ -105,7 +105,8 @@ WSI_API int wsi_ctx_create(int device, wsi_ctx** out);
 WSI_API int wsi_ctx_destroy(wsi_ctx* ctx);
 WSI_API const char* wsi_last_error(wsi_ctx* ctx);           /* ctx may be NULL: last global error       */
 WSI_API const char* wsi_version(void);
-/* knobs: "batch_tiles" (tiles per forward batch, 0 = auto), "stage_timing" (0/1), "precision" (wsi_precision) */
+/* knobs: "batch_tiles" (tiles per forward batch, 0 = auto), "stage_timing" (0/1), "precision" (wsi_precision),
+ * "op_trace" (0/1, see wsi_op_stats) */
 WSI_API int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value);
 WSI_API int wsi_set_class_probs(wsi_ctx* ctx, const float* p, int n);   /* myargs.py:15 class_probs     */
 WSI_API int64_t wsi_kernel_launches(wsi_ctx* ctx);          /* kernels launched by this ctx so far      */
@@ -224,6 +225,13 @@ WSI_API int wsi_debug_maxpool(wsi_ctx* ctx, const void* x, int n, int h, int w, 
  * (FLOPs for stem/conv, bytes otherwise).  Reset with wsi_stage_reset.            */
 WSI_API int wsi_stage_stats(wsi_ctx* ctx, const char* stage, double* ms_out, int64_t* launches_out, double* work_out);
 WSI_API int wsi_stage_reset(wsi_ctx* ctx);
+/* Per-kernel evidence (bench.py roofline table): with option "op_trace" = 1 (set before the first run) every conv launch
+ * is bracketed by CUDA events on the launching stream.  idx walks the convs of the current network plan in execution
+ * order (stem first); returns WSI_ERR_INVALID past the end.  flops / bytes = ALGORITHMIC work of one launch (2*MAC;
+ * every operand read once + output written once), ms_per_launch = mean device time.  Adds ~2 events per kernel: not for
+ * the timed region of a benchmark. */
+WSI_API int wsi_op_stats(wsi_ctx* ctx, int idx, char* desc, int desc_cap, char* kernel, int kernel_cap, double* ms_per_launch,
+                 double* flops, double* bytes, int64_t* count);
 
 #ifdef __cplusplus
 }

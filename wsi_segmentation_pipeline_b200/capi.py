@@ -31,7 +31,7 @@ SYMBOLS = (
     "wsi_synth_slide", "wsi_debug_conv", "wsi_debug_gather", "wsi_debug_stem", "wsi_debug_maxpool",
     "wsi_stage_stats", "wsi_stage_reset", "wsi_resize_argmax",
     "wsi_find_nuclei", "wsi_plan_tiles_gpu", "wsi_forward_patches",
-    "wsi_forward_batch_tta", "wsi_debug_umma_shift", "wsi_check", "wsi_debug_conv_f32",
+    "wsi_forward_batch_tta", "wsi_debug_umma_shift", "wsi_check", "wsi_debug_conv_f32", "wsi_op_stats",
 )
 
 
@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
         "wsi_debug_conv_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
         "wsi_check": (C.c_int, [vp, vp]),
+        "wsi_op_stats": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl),
+                                   C.POINTER(i64)]),
         "wsi_debug_gather": (C.c_int, [vp, C.POINTER(SlideDesc), vp, C.c_int, vp, vp, vp]),
         "wsi_debug_stem": (C.c_int, [vp, C.POINTER(SlideDesc), vp, C.c_int, vp, vp, vp, vp, vp]),
         "wsi_debug_maxpool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
@@ -237,6 +239,18 @@ class Context:
             ms, n, w = C.c_double(0), C.c_int64(0), C.c_double(0)
             _check(self._lib.wsi_stage_stats(self._h, s.encode(), C.byref(ms), C.byref(n), C.byref(w)), self._h)
             out[s] = {"ms": ms.value, "launches": n.value, "work": w.value}
+        return out
+
+    def op_stats(self) -> list:
+        """Per-conv evidence of the current plan (option op_trace = 1): [{desc, kernel, ms, flops, bytes, count}]."""
+        out, i = [], 0
+        while True:
+            d, k = C.create_string_buffer(200), C.create_string_buffer(100)
+            ms, fl, by, n = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int64(0)
+            if self._lib.wsi_op_stats(self._h, i, d, 200, k, 100, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)) != WSI_OK:
+                break
+            out.append({"desc": d.value.decode(), "kernel": k.value.decode(), "ms": ms.value, "flops": fl.value, "bytes": by.value, "count": n.value})
+            i += 1
         return out
 
     def stage_reset(self):

@@ -350,6 +350,18 @@ void ConvOp::set_head_out(float* ptr) {
   p_.head_out = ptr;
 }
 
+std::string ConvOp::kernel_name() const {
+  char b[96];
+  if (stream_) return stream_->kernel_name();
+  if (upstream_) { snprintf(b, sizeof(b), "conv_upstream_kernel<%d>", block_n_); return b; }
+  if (row_) { snprintf(b, sizeof(b), "conv_rowtile_kernel<%d>", block_n_); return b; }
+  if (stem_) return "stem_rowtile_kernel";
+  if (halo_) { snprintf(b, sizeof(b), "conv_halo_pair_kernel<%d,%s>", block_n_, (p_.halo_plain && !p_.out_planar) ? "plain" : "table"); return b; }
+  if (pair_) { snprintf(b, sizeof(b), "conv_igemm_pair_kernel<%d>", block_n_); return b; }
+  snprintf(b, sizeof(b), "conv_igemm_kernel<%d,%d%s%s>", block_n_, block_k_, resb_ ? ",RESB" : "", split_ ? ",NSPLIT=3" : "");
+  return b;
+}
+
 bool ConvOp::stem_routes_to_rowtile() { return getenv("WSI_NO_ROWTILE") == nullptr; }
 
 void ConvOp::build_stem(const void* padded_tiles, int n, int ph, int pw, const float* w_oihw, const float* scale,

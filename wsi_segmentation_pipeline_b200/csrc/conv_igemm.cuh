@@ -695,6 +695,7 @@ class ConvOp {
   int block_k() const { return block_k_; }
   bool is_pair() const { return pair_ || halo_; }
   bool is_halo() const { return halo_; }
+  std::string kernel_name() const;   // the __global__ function this op launches (evidence tables)
 
  private:
   void finish(const std::vector<KBlock>& table, int num_parity, const std::vector<uint16_t>& wpacked, int K,

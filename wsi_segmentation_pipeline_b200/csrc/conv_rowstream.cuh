@@ -63,6 +63,11 @@ class RowStreamOp {
   void launch(cudaStream_t stream, LaunchCounter* lc) const;
   double flops() const { return flops_; }
   void set_head_out(float* p) { p_.head_out = p; }
+  std::string kernel_name() const {
+    char b[96];
+    snprintf(b, sizeof(b), "%s<%d%s>", p_.lanes == 2 ? "conv_rowstream2_kernel" : "conv_rowstream_kernel", p_.Cout, p_.head_out ? ",HEAD" : "");
+    return b;
+  }
 
  private:
   StreamParams p_{};

@@ -90,6 +90,7 @@ struct wsi_ctx {
   float class_probs[4] = {0.f, 0.f, 0.f, 0.f};
   int64_t batch_tiles = 0;
   int stage_timing = 0;
+  int op_trace = 0;                // per-conv CUDA events (wsi_op_stats); set before the plan is built
   int precision = WSI_PRECISION_BF16;
   DevBuf lut;        // f32 [3][256] normalise table
   DevBuf err_flag;   // int, set by a timed-out barrier wait inside the conv kernel
@@ -226,14 +227,14 @@ struct NetPlan {
   double conv_flops = 0, stem_flops = 0;   // per batch of `cap` tiles (algorithmic: 2*MAC, no padding)
   std::vector<Act*> feats;                 // [x4, x3, x2, x1, x0]
   // WSI_CONV_TRACE=1: per-op device time (dev tool; events around every conv launch)
-  struct OpStat { std::string desc; double ms = 0, flops = 0; int64_t count = 0; };
+  struct OpStat { std::string desc; double ms = 0, flops = 0; int64_t count = 0; double bytes = 0; std::string kernel; };
   std::vector<OpStat> op_stats;
   struct OpSpan { cudaEvent_t a, b; int idx; };
   std::vector<OpSpan> op_spans;
   bool trace = false;
   void resolve_trace();
   void print_trace();
-  ~NetPlan() { if (trace) { resolve_trace(); print_trace(); } }
+  ~NetPlan() { if (trace) { resolve_trace(); if (getenv("WSI_CONV_TRACE")) print_trace(); } }
 
   Act* new_act(int N, int H, int W, int C, int layout = LAYOUT_NHWC) {
     acts.emplace_back(new Act());
@@ -281,8 +282,10 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
     op->build_stem(in_pad.p, cap, ph, pw, w.data.data(), f.scale.data(), f.bias.data(), x0->buf.p, ef, sms, x0_layout, precise);
     steps.push_back(Step{0, ST_STEM, op, nullptr, x0});
     stem_flops = op->flops();
-    op_stats.push_back(OpStat{"stem 7x7/s2 3->64", 0, op->flops(), 0});
-    trace = getenv("WSI_CONV_TRACE") != nullptr;
+    // algorithmic bytes: the padded bf16 operand read once + x0 written once
+    op_stats.push_back(OpStat{"stem 7x7/s2 3->64", 0, op->flops(), 0, (double)cap * ph * pw * 8.0 + (double)cap * (ph / 2) * (pw / 2) * 64 * 2.0 * (precise ? 3 : 1),
+                              op->kernel_name()});
+    trace = getenv("WSI_CONV_TRACE") != nullptr || c->op_trace;
   }
   // ---- maxpool 3x3/s2/p1 (:199) ----
   // layer1's four 64->64 convs run on the row-tile kernel: the pooled tensor, the block-internal tensors and
@@ -310,7 +313,14 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
     snprintf(d, sizeof(d), "conv%dx%d/s%d %4d->%-4d @%dx%d%s%s BN%d BK%d%s", spec.ksize, spec.ksize, spec.stride, cin_t, spec.cout,
              parts[0].up2 ? 2 * parts[0].t.H : parts[0].t.H, parts[0].up2 ? 2 * parts[0].t.W : parts[0].t.W, parts[0].up2 ? " up2" : "",
              res ? " +res" : "", op->block_n(), op->block_k(), op->is_halo() ? " x2 halo" : (op->is_pair() ? " x2" : ""));
-    op_stats.push_back(OpStat{d, 0, op->flops(), 0});
+    // algorithmic bytes: every operand read once, the output (bf16 tensor or fp32 logits) written once
+    double by = 0;
+    for (auto& q : parts) by += (double)q.t.N * q.t.H * q.t.W * q.t.C * 2.0;
+    if (res) by += (double)res->N * res->H * res->W * res->C * 2.0;
+    if (out) by += (double)out->N * out->H * out->W * out->C * 2.0;
+    if (precise) by *= 3.0;
+    if (hout) by += (double)parts[0].t.N * parts[0].t.H * parts[0].t.W * 16.0;
+    op_stats.push_back(OpStat{d, 0, op->flops(), 0, by, op->kernel_name()});
   };
 
   // ---- layer1..layer4, BasicBlock (resnets_shift.py:49-65) ----
@@ -997,6 +1007,7 @@ int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value) {
   const std::string k(key);
   if (k == "batch_tiles") { WSI_REQUIRE(value >= 0 && value <= 4096, WSI_ERR_INVALID, "batch_tiles out of range"); ctx->batch_tiles = value; }
   else if (k == "stage_timing") ctx->stage_timing = value ? 1 : 0;
+  else if (k == "op_trace") { ctx->op_trace = value ? 1 : 0; ctx->plan.reset(); }
   else if (k == "precision") {
     WSI_REQUIRE(value == WSI_PRECISION_BF16 || value == WSI_PRECISION_FP32, WSI_ERR_INVALID, "precision must be WSI_PRECISION_BF16 (0) or WSI_PRECISION_FP32 (1)");
     ctx->precision = (int)value;
@@ -1468,6 +1479,26 @@ int wsi_stage_stats(wsi_ctx* ctx, const char* stage, double* ms_out, int64_t* la
       return WSI_OK;
     }
   WSI_THROW(WSI_ERR_INVALID, "unknown stage '%s'", stage);
+  WSI_API_END(ctx)
+}
+
+int wsi_op_stats(wsi_ctx* ctx, int idx, char* desc, int desc_cap, char* kernel, int kernel_cap, double* ms_per_launch, double* flops,
+                 double* bytes, int64_t* count) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx, WSI_ERR_INVALID, "ctx is NULL");
+  NetPlan* p = ctx->plan.get();
+  WSI_REQUIRE(p && p->trace, WSI_ERR_INVALID, "no traced plan: set option op_trace = 1 before running");
+  if (idx < 0 || idx >= (int)p->op_stats.size()) return WSI_ERR_INVALID;      // end of the list: not an error worth a message
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  p->resolve_trace();
+  const NetPlan::OpStat& o = p->op_stats[idx];
+  if (desc && desc_cap > 0) snprintf(desc, (size_t)desc_cap, "%s", o.desc.c_str());
+  if (kernel && kernel_cap > 0) snprintf(kernel, (size_t)kernel_cap, "%s", o.kernel.c_str());
+  if (ms_per_launch) *ms_per_launch = o.count ? o.ms / (double)o.count : 0.0;
+  if (flops) *flops = o.flops;
+  if (bytes) *bytes = o.bytes;
+  if (count) *count = o.count;
   WSI_API_END(ctx)
 }
 

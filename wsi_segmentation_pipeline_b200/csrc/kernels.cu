@@ -437,10 +437,10 @@ __device__ __forceinline__ void write_pixel(const FinaliseArgs& a, int64_t idx, 
   }
 }
 
-// visit, in sorted order, the tiles of [t_lo, t_hi) that cover row Y and may cover columns [X0, X0 + 256): f(i, tx, oy).
+// visit, in sorted order, the tiles of [t_lo, t_hi) that cover row Y and may cover columns [X0, X0 + span): f(i, tx, oy).
 // All control flow is uniform across the CTA.
 template <class F>
-__device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo, int t_hi, int X0, int Y, F&& f) {
+__device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo, int t_hi, int X0, int span, int Y, F&& f) {
   int lo = 0, hi = ri.R;
   while (lo < hi) {  // first row with row_y > Y - dy
     const int mid = (lo + hi) >> 1;
@@ -458,39 +458,57 @@ __device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo
     }
     for (int i = l2; i < b; ++i) {
       const int tx = __ldg(ri.tx + i);
-      if (tx > X0 + 255) break;
+      if (tx >= X0 + span) break;
       f(i, tx, Y - ry);
     }
   }
 }
 
-// seg: logits of sorted tile i live in slot i % ring_cap of `ring` (f32 [ring_cap][dy][dx][4]); rows [y0, y0 + gridDim.x)
+// seg: logits of sorted tile i live in slot i % ring_cap of `ring` (f32 [ring_cap][dy][dx][4]); rows [y0, y0 + gridDim.x).
+// A CTA owns kStitchPx * 256 consecutive pixels of one canvas row, a thread kStitchPx of them 256 apart (coalesced per
+// access): kStitchPx independent 16-byte loads per candidate tile keep enough bytes in flight to cover the DRAM latency
+// (one pixel per thread measured 2.3 TB/s: 16 dependent round trips per thread).
+constexpr int kStitchPx = 4;
+
 __global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, const float4* __restrict__ ring, int ring_cap, int t_lo, int t_hi,
                                                                    int y0, FinaliseArgs a) {
   const int Y = y0 + blockIdx.x;
-  const int X0 = blockIdx.y * 256;
-  const int X = X0 + threadIdx.x;
-  const bool live = X < a.W2;
+  const int X0 = blockIdx.y * (256 * kStitchPx);
+  const int Xt = X0 + threadIdx.x;
   const int64_t tile_px = (int64_t)ri.dx * ri.dy;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for_each_candidate(ri, t_lo, t_hi, X0, Y, [&](int i, int tx, int oy) {
-    const int ox = X - tx;
-    if (live && ox >= 0 && ox < ri.dx) {
-      const float4 v = __ldg(ring + (int64_t)(i % ring_cap) * tile_px + (int64_t)oy * ri.dx + ox);
-      s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+  double s[kStitchPx][4];
+#pragma unroll
+  for (int k = 0; k < kStitchPx; ++k) s[k][0] = s[k][1] = s[k][2] = s[k][3] = 0.0;
+  for_each_candidate(ri, t_lo, t_hi, X0, 256 * kStitchPx, Y, [&](int i, int tx, int oy) {
+    const float4* src = ring + (int64_t)(i % ring_cap) * tile_px + (int64_t)oy * ri.dx;
+    float4 v[kStitchPx];
+    bool hit[kStitchPx];
+#pragma unroll
+    for (int k = 0; k < kStitchPx; ++k) {
+      const int ox = Xt + 256 * k - tx;
+      hit[k] = (ox >= 0) && (ox < ri.dx) && (Xt + 256 * k < a.W2);
+      if (hit[k]) v[k] = __ldg(src + ox);
     }
+#pragma unroll
+    for (int k = 0; k < kStitchPx; ++k)
+      if (hit[k]) { s[k][0] += (double)v[k].x; s[k][1] += (double)v[k].y; s[k][2] += (double)v[k].z; s[k][3] += (double)v[k].w; }
   });
-  if (!live) return;
-  const int64_t idx = (int64_t)(Y - a.own0) * a.W2 + X, plane = (a.own1 - a.own0) * a.W2;
-  const double mv = a.mask ? (double)a.mask[idx] : 1.0;
-  const PixelOut o = finalise_pixel(s0, s1, s2, s3, mv, a.class_probs, a.heat_mode);
-  write_pixel(a, idx, plane, s0, s1, s2, s3, o);
+  const int64_t plane = (a.own1 - a.own0) * a.W2;
+#pragma unroll
+  for (int k = 0; k < kStitchPx; ++k) {
+    const int X = Xt + 256 * k;
+    if (X >= a.W2) break;
+    const int64_t idx = (int64_t)(Y - a.own0) * a.W2 + X;
+    const double mv = a.mask ? (double)a.mask[idx] : 1.0;
+    const PixelOut o = finalise_pixel(s[k][0], s[k][1], s[k][2], s[k][3], mv, a.class_probs, a.heat_mode);
+    write_pixel(a, idx, plane, s[k][0], s[k][1], s[k][2], s[k][3], o);
+  }
 }
 
 void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int64_t y0, int64_t y1,
                                 const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
   if (y1 <= y0 || a.W2 <= 0) return;
-  dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256));
+  dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256 * kStitchPx));
   stitch_finalise_seg_kernel<<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, (int)y0, a);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
@@ -503,7 +521,7 @@ __global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, 
   const int X = X0 + threadIdx.x;
   const bool live = X < a.W2;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for_each_candidate(ri, 0, T, X0, Y, [&](int i, int tx, int) {
+  for_each_candidate(ri, 0, T, X0, 256, Y, [&](int i, int tx, int) {
     const int ox = X - tx;
     if (live && ox >= 0 && ox < ri.dx) {
       const float4 v = __ldg(tile_logits + i);
