@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from oracle import wsi_oracle as O                      # noqa: E402  (weights only)
+from wsi_segmentation_pipeline_b200 import weights as O   # noqa: E402  (synthetic checkpoint)
 from wsi_segmentation_pipeline_b200 import capi        # noqa: E402
 
 

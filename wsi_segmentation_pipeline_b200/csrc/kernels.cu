@@ -465,37 +465,37 @@ __device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo
 }
 
 // seg: logits of sorted tile i live in slot i % ring_cap of `ring` (f32 [ring_cap][dy][dx][4]); rows [y0, y0 + gridDim.x).
-// A CTA owns kStitchPx * 256 consecutive pixels of one canvas row, a thread kStitchPx of them 256 apart (coalesced per
-// access): kStitchPx independent 16-byte loads per candidate tile keep enough bytes in flight to cover the DRAM latency
-// (one pixel per thread measured 2.3 TB/s: 16 dependent round trips per thread).
-constexpr int kStitchPx = 4;
-
+// A CTA owns PX * 256 consecutive pixels of one canvas row, a thread PX of them 256 apart (coalesced per access).
+// Measured (12k x 12k slide, same box): PX = 1 / 2 / 4 -> 2.20 / 2.35 / 1.55 TB/s; an L1-prefetch pass ahead of the
+// accumulate pass made every variant slower.  ncu: the 64 F2F.F64.F32 per pixel keep the XU pipe 36 % busy and the
+// double-precision finalise costs registers (occupancy), the kernel is issue/latency-bound, not DRAM-bound (21 %).
+template <int PX>
 __global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, const float4* __restrict__ ring, int ring_cap, int t_lo, int t_hi,
                                                                    int y0, FinaliseArgs a) {
   const int Y = y0 + blockIdx.x;
-  const int X0 = blockIdx.y * (256 * kStitchPx);
+  const int X0 = blockIdx.y * (256 * PX);
   const int Xt = X0 + threadIdx.x;
   const int64_t tile_px = (int64_t)ri.dx * ri.dy;
-  double s[kStitchPx][4];
+  double s[PX][4];
 #pragma unroll
-  for (int k = 0; k < kStitchPx; ++k) s[k][0] = s[k][1] = s[k][2] = s[k][3] = 0.0;
-  for_each_candidate(ri, t_lo, t_hi, X0, 256 * kStitchPx, Y, [&](int i, int tx, int oy) {
+  for (int k = 0; k < PX; ++k) s[k][0] = s[k][1] = s[k][2] = s[k][3] = 0.0;
+  for_each_candidate(ri, t_lo, t_hi, X0, 256 * PX, Y, [&](int i, int tx, int oy) {
     const float4* src = ring + (int64_t)(i % ring_cap) * tile_px + (int64_t)oy * ri.dx;
-    float4 v[kStitchPx];
-    bool hit[kStitchPx];
+    float4 v[PX];
+    bool hit[PX];
 #pragma unroll
-    for (int k = 0; k < kStitchPx; ++k) {
+    for (int k = 0; k < PX; ++k) {
       const int ox = Xt + 256 * k - tx;
       hit[k] = (ox >= 0) && (ox < ri.dx) && (Xt + 256 * k < a.W2);
       if (hit[k]) v[k] = __ldg(src + ox);
     }
 #pragma unroll
-    for (int k = 0; k < kStitchPx; ++k)
+    for (int k = 0; k < PX; ++k)
       if (hit[k]) { s[k][0] += (double)v[k].x; s[k][1] += (double)v[k].y; s[k][2] += (double)v[k].z; s[k][3] += (double)v[k].w; }
   });
   const int64_t plane = (a.own1 - a.own0) * a.W2;
 #pragma unroll
-  for (int k = 0; k < kStitchPx; ++k) {
+  for (int k = 0; k < PX; ++k) {
     const int X = Xt + 256 * k;
     if (X >= a.W2) break;
     const int64_t idx = (int64_t)(Y - a.own0) * a.W2 + X;
@@ -508,8 +508,9 @@ __global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, 
 void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int64_t y0, int64_t y1,
                                 const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
   if (y1 <= y0 || a.W2 <= 0) return;
-  dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256 * kStitchPx));
-  stitch_finalise_seg_kernel<<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, (int)y0, a);
+  constexpr int px = 2;
+  dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256 * px));
+  stitch_finalise_seg_kernel<px><<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, (int)y0, a);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
