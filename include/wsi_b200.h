@@ -133,6 +133,18 @@ WSI_API int wsi_band_partition(int64_t ih, int32_t ph, int32_t sh, int32_t nrank
 WSI_API int wsi_band_tiles(const int32_t* xy, int64_t n, int32_t ph, double m, int64_t own0, int64_t own1,
                    int64_t** idx_out, int64_t* n_out);
 
+/* ---- peer-mapped result (multi-GPU, one process per GPU of one node; no reference counterpart) -----
+ * The band outputs of every rank are the u8 rows [own0, own1) of ONE result [2][H2][W2] (classes, heatmap) that lives
+ * in rank 0's HBM.  Rank 0 allocates it (wsi_ipc_alloc -> device pointer + a 64-byte CUDA IPC handle to send to the
+ * other processes), every other rank maps it (wsi_ipc_open) and passes pointers INTO the mapping as the device outputs
+ * of wsi_run_slide: the fused stitch + finalise kernel then stores its u8 rows straight into rank 0's memory over
+ * NVLink / NVSwitch — compute and "gather" are one kernel, no staging, no collective besides a closing barrier.
+ * The caller synchronises its stream and runs a barrier across ranks before rank 0 reads the result.             */
+WSI_API int wsi_ipc_alloc(wsi_ctx* ctx, int64_t bytes, void** dev_ptr, uint8_t* handle /*[64]*/);
+WSI_API int wsi_ipc_open(wsi_ctx* ctx, const uint8_t* handle /*[64]*/, void** dev_ptr);
+WSI_API int wsi_ipc_close(wsi_ctx* ctx, void* dev_ptr);      /* on the ranks that opened it */
+WSI_API int wsi_ipc_free(wsi_ctx* ctx, void* dev_ptr);       /* on the rank that allocated it, after the others closed */
+
 /* ---- the hot path (replaces the loop of predict_tumorbed, utils/eval.py:190-228) ------------- */
 WSI_API int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,
                   int head, const wsi_out_desc* out, void* stream);

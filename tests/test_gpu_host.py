@@ -166,3 +166,52 @@ def test_predict_reg_tta_mirror(golden_dir):
     ref_mean = (((single[0] + single[1]) + single[2]) + single[3]) / 4
     np.testing.assert_array_equal(got, ref_mean.cpu().numpy())
     assert np.abs(got - single[0].cpu().numpy()).max() > 0
+
+
+# ------------------------------------------------------------------------------------------
+# multi-process: the peer-mapped result (every rank's stitch + finalise kernel stores into rank 0's memory)
+# ------------------------------------------------------------------------------------------
+def _peer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # both processes share cuda:0 on the 1-GPU test box
+    try:
+        ih, iw, p, s = 700, 300, 64, 32
+        raster = synth.synth_slide(ih, iw, 1234)
+        mask = np.ascontiguousarray(synth.synth_mask(ih * 8, iw * 8, 3)[::8, ::8])
+        ctx = capi.Context(0)
+        ctx.load_state_dict(capi.ARCH_UNET_R18, O.random_state_dict("unet", 4))
+        params = ds.DotDict(ph=p, pw=p, sh=s, sw=s)
+        out = ev.predict_tumorbed_banded(ctx, lambda r0, r1: np.ascontiguousarray(raster[r0:r1]), ih, iw, params, mask, rank, world,
+                                         mode="seg", peer=True)
+        if rank == 0:
+            tiles = capi.plan_tiles(ih, iw, p, p, s, s, mask, 1.0)
+            ref = ctx.run_slide(ctx.slide_desc(raster, ih, iw, p, p, mask=mask), tiles, capi.HEAD_SEG)
+            ok = torch.equal(out[0].cpu(), ref["classes"]) and torch.equal(out[1].cpu(), ref["heatmap"])
+            q.put("ok" if ok else "mismatch")
+        else:
+            assert out is None
+        ctx.close()
+    except Exception as e:           # noqa: BLE001 — report instead of hanging the peer in a collective
+        q.put(f"rank {rank}: {e!r}")
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_mapped_result_across_processes(world):
+    """row bands in separate processes, each writing its rows of the ONE result that lives in rank 0's memory
+    (CUDA IPC mapping; on the GPU box: NVLink peer stores) — byte-identical with the single-process result."""
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29900 + (os.getpid() % 300) + world
+    procs = [mpc.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(300)
+    status = q.get(timeout=10)
+    assert status == "ok", status
+    assert all(pr.exitcode == 0 for pr in procs)

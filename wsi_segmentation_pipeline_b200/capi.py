@@ -32,6 +32,7 @@ SYMBOLS = (
     "wsi_stage_stats", "wsi_stage_reset", "wsi_resize_argmax",
     "wsi_find_nuclei", "wsi_plan_tiles_gpu", "wsi_forward_patches",
     "wsi_forward_batch_tta", "wsi_debug_umma_shift", "wsi_check", "wsi_debug_conv_f32", "wsi_op_stats",
+    "wsi_ipc_alloc", "wsi_ipc_open", "wsi_ipc_close", "wsi_ipc_free",
 )
 
 
@@ -94,6 +95,10 @@ def lib() -> C.CDLL:
         "wsi_debug_conv_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
         "wsi_check": (C.c_int, [vp, vp]),
+        "wsi_ipc_alloc": (C.c_int, [vp, i64, C.POINTER(vp), C.c_char_p]),
+        "wsi_ipc_open": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+        "wsi_ipc_close": (C.c_int, [vp, vp]),
+        "wsi_ipc_free": (C.c_int, [vp, vp]),
         "wsi_op_stats": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl),
                                    C.POINTER(i64)]),
         "wsi_debug_gather": (C.c_int, [vp, C.POINTER(SlideDesc), vp, C.c_int, vp, vp, vp]),
@@ -224,6 +229,24 @@ class Context:
     def check(self, stream=None):
         """Synchronise and raise if an earlier asynchronous (device-output) call failed on the device."""
         _check(self._lib.wsi_check(self._h, _stream_ptr(stream)), self._h)
+
+    # ---- peer-mapped result buffer (multi-GPU) ---------------------------------------------
+    def ipc_alloc(self, nbytes: int):
+        """Device buffer on this GPU + the 64-byte CUDA IPC handle other processes open it with."""
+        ptr, h = C.c_void_p(), C.create_string_buffer(64)
+        _check(self._lib.wsi_ipc_alloc(self._h, int(nbytes), C.byref(ptr), h), self._h)
+        return int(ptr.value), bytes(h.raw)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        _check(self._lib.wsi_ipc_open(self._h, C.create_string_buffer(handle, 64), C.byref(ptr)), self._h)
+        return int(ptr.value)
+
+    def ipc_close(self, ptr: int):
+        _check(self._lib.wsi_ipc_close(self._h, C.c_void_p(ptr)), self._h)
+
+    def ipc_free(self, ptr: int):
+        _check(self._lib.wsi_ipc_free(self._h, C.c_void_p(ptr)), self._h)
 
     def set_class_probs(self, probs):
         arr = (C.c_float * 4)(*[float(p) for p in probs])
@@ -521,3 +544,16 @@ class Context:
         _check(self._lib.wsi_debug_maxpool(self._h, C.c_void_p(x_nhwc.data_ptr()), n, h, w, c, C.c_void_p(y.data_ptr()),
                                            _stream_ptr(None)), self._h)
         return y
+
+
+class _DevPtr:
+    """Raw device memory as a __cuda_array_interface__ object (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_u8_tensor(ptr: int, shape, device: int):
+    """A torch u8 view of device memory the library (or a peer process) owns."""
+    import torch
+    return torch.as_tensor(_DevPtr(ptr, shape), device=torch.device("cuda", device))

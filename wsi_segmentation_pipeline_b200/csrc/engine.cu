@@ -1401,6 +1401,60 @@ int wsi_debug_conv_f32(wsi_ctx* ctx, const float* x, int n, int h, int w, int ci
   WSI_API_END(ctx)
 }
 
+// ---- peer-mapped result buffer (multi-GPU, one process per GPU on one node) ---------------------------------------
+int wsi_ipc_alloc(wsi_ctx* ctx, int64_t bytes, void** dev_ptr, uint8_t* handle /*[64]*/) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && dev_ptr && handle && bytes > 0, WSI_ERR_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  WSI_REQUIRE(e == cudaSuccess, WSI_ERR_NOMEM, "cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    WSI_THROW(WSI_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle, &h, 64);
+  *dev_ptr = p;
+  WSI_API_END(ctx)
+}
+
+int wsi_ipc_open(wsi_ctx* ctx, const uint8_t* handle, void** dev_ptr) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && handle && dev_ptr, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    WSI_THROW(WSI_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s (peer access over NVLink / PCIe unavailable between these processes)", cudaGetErrorString(e));
+  }
+  *dev_ptr = p;
+  WSI_API_END(ctx)
+}
+
+int wsi_ipc_close(wsi_ctx* ctx, void* dev_ptr) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && dev_ptr, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+  WSI_API_END(ctx)
+}
+
+int wsi_ipc_free(wsi_ctx* ctx, void* dev_ptr) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && dev_ptr, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(cudaFree(dev_ptr));
+  WSI_API_END(ctx)
+}
+
 int wsi_check(wsi_ctx* ctx, void* stream) {
   WSI_API_BEGIN
   WSI_REQUIRE(ctx, WSI_ERR_INVALID, "ctx is NULL");

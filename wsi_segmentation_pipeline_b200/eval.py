@@ -174,11 +174,71 @@ def gather_bands(parts, rows_per_rank, W2: int, rank: int, world: int, device=No
     return classes, heatmap
 
 
+class PeerResult:
+    """The slide's u8 result [2, H2, W2] (classes, heatmap) in rank 0's HBM, mapped into every rank's address space
+    through CUDA IPC (wsi_ipc_alloc / wsi_ipc_open).  Each rank hands ``band(own0, own1)`` to ``run_slide`` as its device
+    outputs: the fused stitch + finalise kernel stores its rows straight into rank 0's memory over NVLink, so the final
+    "gather" of SURVEY 8e costs no extra pass — only ``finish()``, a stream sync + barrier.  Needs ``torch.distributed``
+    initialised with one process per GPU on one node; raises ``capi.WsiError`` when peer mapping is unavailable (callers
+    fall back to ``gather_bands``)."""
+
+    def __init__(self, ctx: capi.Context, H2: int, W2: int, rank: int, world: int):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.H2, self.W2 = ctx, rank, world, int(H2), int(W2)
+        self._ptr, self._owner = None, rank == 0
+        handle, err = [None], None
+        if rank == 0:
+            self._ptr, handle[0] = ctx.ipc_alloc(2 * self.H2 * self.W2)
+        if world > 1:
+            dist.broadcast_object_list(handle, src=0)
+            if rank != 0:
+                try:
+                    self._ptr = ctx.ipc_open(handle[0])
+                except capi.WsiError as e:
+                    err = e
+            ok = torch.tensor([0 if err else 1], device=torch.device("cuda", ctx.device))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:                       # every rank takes the same decision
+                self.close()
+                raise err or capi.WsiError(-2, "a peer rank could not map the result buffer")
+        self.full = capi.device_u8_tensor(self._ptr, (2, self.H2, self.W2), ctx.device)
+
+    def band(self, own0: int, own1: int) -> dict:
+        return {"classes": self.full[0, own0:own1], "heatmap": self.full[1, own0:own1]}
+
+    def finish(self):
+        """All ranks: wait for the local kernels, then a barrier; rank 0 gets (classes, heatmap)."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.ctx.device)
+        if self.world > 1:
+            dist.barrier()
+        return (self.full[0], self.full[1]) if self.rank == 0 else None
+
+    def close(self):
+        """Collective: every rank calls it (also after a failed mapping)."""
+        import torch.distributed as dist
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        self.full = None
+        if self._ptr is not None and not self._owner:
+            self.ctx.ipc_close(self._ptr)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier()
+        if self._ptr is not None and self._owner:
+            self.ctx.ipc_free(self._ptr)
+        self._ptr = None
+
+
 def predict_tumorbed_banded(model, raster_rows_fn, ih: int, iw: int, params, mask: Optional[np.ndarray], rank: int, world: int,
-                            mode: str = "seg"):
+                            mode: str = "seg", peer: Optional[bool] = None):
     """Row-band sharded slide (m == 1).  ``raster_rows_fn(row0, row1)`` returns the u8 [row1-row0, iw, 3]
     raster rows this rank needs (numpy or torch, host or device).  Returns (classes, heatmap) on
-    rank 0, None elsewhere."""
+    rank 0, None elsewhere.  peer (default: on for world > 1): every rank's finalise kernel writes its rows straight
+    into rank 0's result over NVLink (``PeerResult``); otherwise, or when peer mapping is unavailable, one NCCL
+    gather of the band outputs (``gather_bands``)."""
     ctx = _engine_of(model)
     tiles = capi.plan_tiles(ih, iw, params.ph, params.pw, params.sh, params.sw, mask, 1.0)
     plan = band_plan(ih, params.ph, params.sh, tiles, 1.0, world)
@@ -186,6 +246,21 @@ def predict_tumorbed_banded(model, raster_rows_fn, ih: int, iw: int, params, mas
     band = raster_rows_fn(row0, row1)
     bmask = None if mask is None else np.ascontiguousarray(mask[own0:own1])
     sl = ctx.slide_desc(band, ih, iw, params.ph, params.pw, mask=bmask, row0=row0, rows=row1 - row0, own0=own0, own1=own1)
-    r = ctx.run_slide(sl, tiles[idx], capi.HEAD_SEG if mode == "seg" else capi.HEAD_CLS, device_out=True)
+    head = capi.HEAD_SEG if mode == "seg" else capi.HEAD_CLS
+    import torch
+    if peer is None:
+        peer = world > 1 and torch.cuda.is_available()
+    if peer:
+        try:
+            pr = PeerResult(ctx, ih, iw, rank, world)
+        except capi.WsiError:
+            pr = None                                  # no peer mapping between these processes: NCCL gather below
+        if pr is not None:
+            ctx.run_slide(sl, tiles[idx], head, device_out=True, out=pr.band(own0, own1))
+            res = pr.finish()
+            out = None if res is None else (res[0].clone(), res[1].clone())
+            pr.close()
+            return out
+    r = ctx.run_slide(sl, tiles[idx], head, device_out=True)
     rows = [p[1] - p[0] for p in plan]
     return gather_bands((r["classes"], r["heatmap"]), rows, iw, rank, world)
