@@ -185,6 +185,31 @@ WSI_API int wsi_plan_tiles_gpu(wsi_ctx* ctx, int64_t ih, int64_t iw, int32_t ph,
 WSI_API int wsi_resize_argmax(wsi_ctx* ctx, const float* canvas, int64_t H, int64_t W, int64_t H2, int64_t W2,
                       uint8_t* classes, float* pred_or_null, int mem, void* stream);
 
+/* ---- tumour-bed post-processing of the outputs -------------------------------------------------
+ * cv2.morphologyEx / cv2.erode / cv2.dilate with an np.ones((k, k)) kernel, default anchor and border (utils/eval.py:93,96;
+ * paper_tools/overlay_tb_wsi.py:50-54,63-67; paper_tools/check_for_false_positives.py:66-70): bit-exact with OpenCV.
+ * src / dst: u8 [H][W] in `mem` memory (dst may alias src). */
+typedef enum { WSI_MORPH_ERODE = 0, WSI_MORPH_DILATE = 1, WSI_MORPH_OPEN = 2, WSI_MORPH_CLOSE = 3 } wsi_morph_op;
+WSI_API int wsi_morph(wsi_ctx* ctx, const uint8_t* src, int64_t H, int64_t W, int op, int k, uint8_t* dst, int mem, void* stream);
+/* The tumour-bed chain of utils/eval.py:90-96 (and of the two paper_tools scripts):
+ *   tb = rule(src)                      rule_lut: host u8 [256], the reference's threshold evaluated for every u8 level,
+ *                                       e.g. classes >= 2 (:91), heatmap >= 0.99 * 255, heatmap / 255 >= 0.9
+ *   tb = MORPH_OPEN(tb, ones(open_k))                    -> opened_out (u8 {0,1}), *n_open_out = count_nonzero
+ *   tb_pred = convex_hull_image(tb)                      -> hull_out   (skimage, restated: boundary-inclusive, exact integer test)
+ *   outline = dilate(bwperim(tb_pred), ones(dilate_k))   -> outline_out (mahotas.bwperim n=4 restated; dilate_k <= 1: no dilation)
+ * Any output pointer may be NULL; all buffers in `mem` memory. */
+WSI_API int wsi_tumor_bed(wsi_ctx* ctx, const uint8_t* src, int64_t H, int64_t W, const uint8_t* rule_lut, int open_k, int dilate_k,
+                  uint8_t* opened_out, uint8_t* hull_out, uint8_t* outline_out, int64_t* n_open_out, int mem, void* stream);
+/* host-only part of convex_hull_image (no ctx, no GPU): per-row first / last set column (-1 / -1 for an empty row) ->
+ * per-row inclusive pixel range [xl, xr] of the hull image (xl > xr: empty row).  Exposed for CPU tests. */
+WSI_API int wsi_hull_rows(const int32_t* xmin, const int32_t* xmax, int64_t H, int32_t* xl, int32_t* xr);
+/* Overlays.  WSI_OVERLAY_HEAT: np.uint8(img * 0.75 + 255 * rule(heat) * 0.25) (utils/eval.py:262-267; on_lut = host u8 [256],
+ * heat > 255 * 0.99 per level).  WSI_OVERLAY_BED: np.uint8(0.65 * img + 0.35 * (heat * im)) with outline pixels set to 0
+ * (paper_tools/overlay_tb_wsi.py:56-72; im / perim may be NULL).  rgb / out: u8 [H][W][3]; heat / im / perim: u8 [H][W]. */
+typedef enum { WSI_OVERLAY_HEAT = 0, WSI_OVERLAY_BED = 1 } wsi_overlay_mode;
+WSI_API int wsi_overlay(wsi_ctx* ctx, const uint8_t* rgb, const uint8_t* heat, int64_t H, int64_t W, int mode, const uint8_t* on_lut,
+                const uint8_t* im, const uint8_t* perim, uint8_t* out, int mem, void* stream);
+
 /* ---- one batch through the network (nn.Module shim forward; utils/eval.py:196-200) ----------- */
 /* x: f32 [n, 3, h, w] already normalised (standard_augmentor output); out: SEG f32 [n,C,h,w],
  * CLS [n,C], REG [n,1], FEATURES [n,512].  Both in `mem` memory.                                 */

@@ -377,6 +377,69 @@ def predict_reg_tta(sd, x: "torch.Tensor", arch: str = "unet_reg") -> np.ndarray
 
 
 # --------------------------------------------------------------------------------------------
+# tumour-bed post-processing (utils/eval.py:90-96,262-267; paper_tools/overlay_tb_wsi.py; check_for_false_positives.py)
+#
+# cv2 IS installed: the morphology oracle is cv2 itself (tests call cv2.morphologyEx / cv2.dilate directly).
+# scikit-image and mahotas are NOT: convex_hull_image and bwperim are restated from their published sources —
+# **parity unpinned** against the packages themselves.
+# --------------------------------------------------------------------------------------------
+def convex_hull_image(image: np.ndarray) -> np.ndarray:
+    """skimage.morphology.convex_hull_image(image) with its defaults (offset_coordinates=True, tolerance=1e-10,
+    include_borders=True), restated: candidate points = first / last set pixel of every row and column
+    (``possible_hull``), each replaced by the midpoints of its four pixel edges (``_offsets_diamond``), duplicates
+    removed, ``scipy.spatial.ConvexHull`` (qhull — the same library skimage calls), then every pixel centre inside or on
+    the hull polygon (``grid_points_in_poly(..., binarize=False) >= 1``).  Coordinates are multiples of 0.5, so the
+    half-plane tests below are exact in float64."""
+    from scipy.spatial import ConvexHull
+    img = np.asarray(image) != 0
+    out = np.zeros(img.shape, bool)
+    if not img.any():
+        return out
+    pts = set()
+    for r in np.nonzero(img.any(1))[0]:
+        c = np.nonzero(img[r])[0]
+        pts.add((int(r), int(c[0]))); pts.add((int(r), int(c[-1])))
+    for c in np.nonzero(img.any(0))[0]:
+        r = np.nonzero(img[:, c])[0]
+        pts.add((int(r[0]), int(c))); pts.add((int(r[-1]), int(c)))
+    coords = np.array(sorted(pts), np.float64)
+    offsets = np.array([[-0.5, 0.0], [0.5, 0.0], [0.0, -0.5], [0.0, 0.5]])
+    coords = np.unique((coords[:, None, :] + offsets).reshape(-1, 2), axis=0)
+    hull = ConvexHull(coords)
+    v = hull.points[hull.vertices]                   # polygon vertices in (row, col); orientation taken from the signed area
+    rr, cc = np.mgrid[0:img.shape[0], 0:img.shape[1]]
+    inside = np.ones(img.shape, bool)
+    n = len(v)
+    area2 = sum(v[i, 0] * v[(i + 1) % n, 1] - v[(i + 1) % n, 0] * v[i, 1] for i in range(n))
+    orient = 1.0 if area2 > 0 else -1.0
+    for i in range(n):
+        a, b = v[i], v[(i + 1) % n]
+        cross = (b[0] - a[0]) * (cc - a[1]) - (b[1] - a[1]) * (rr - a[0])
+        inside &= (orient * cross >= 0)
+    return inside
+
+
+def bwperim(bw: np.ndarray) -> np.ndarray:
+    """mahotas.bwperim(bw, n=4) restated: a set pixel belongs to the perimeter iff at least one of its 4 neighbours is
+    unset; pixels outside the image count as unset."""
+    b = np.asarray(bw) != 0
+    p = np.pad(b, 1, constant_values=False)
+    full = p[:-2, 1:-1] & p[2:, 1:-1] & p[1:-1, :-2] & p[1:-1, 2:]
+    return b & ~full
+
+
+def tumor_bed(src: np.ndarray, rule, open_k: int = 20, dilate_k: int = 20) -> dict:
+    """utils/eval.py:90-96 with cv2 for the morphology (the reference's own calls) and the restatements above."""
+    import cv2
+    tb = np.asarray(rule(src)).astype(np.uint8)
+    tb = cv2.morphologyEx(tb, cv2.MORPH_OPEN, np.ones((open_k, open_k), dtype=np.uint8))
+    hull = convex_hull_image(tb)
+    per = bwperim(hull).astype(np.uint8)
+    outline = cv2.dilate(per, np.ones((dilate_k, dilate_k), dtype=np.uint8), iterations=1) if dilate_k > 1 else per
+    return {"opened": tb, "hull": hull.astype(np.uint8), "outline": outline, "n_open": int(np.count_nonzero(tb))}
+
+
+# --------------------------------------------------------------------------------------------
 # random-init weights with the reference's state_dict keys (SURVEY §8d): the synthetic-checkpoint generator lives in the
 # package (wsi_segmentation_pipeline_b200/weights.py — test / bench DATA, shared by bench.py's GPU arm, which must not
 # import anything under oracle/); re-exported here for the tests.

@@ -113,3 +113,36 @@ def test_models_refuse_cpu_forward():
     sd = O.random_state_dict("resnet18", 0, with_fc=True)
     missing, unexpected = r.load_state_dict(sd, strict=False)
     assert not unexpected and all(k.startswith(("fc1.", "fc2.")) for k in missing), (missing, unexpected)
+
+
+def test_hull_rows_matches_restated_convex_hull_image():
+    """the host half of wsi_tumor_bed's convex_hull_image (exact integer monotone chain + per-row
+    ranges) against the oracle's restatement of skimage.morphology.convex_hull_image (qhull + inclusive point-in-polygon)."""
+    from oracle import wsi_oracle as O
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        H, W = int(rng.integers(3, 90)), int(rng.integers(3, 100))
+        img = np.zeros((H, W), np.uint8)
+        if trial % 4 == 0:
+            img = (rng.random((H, W)) < 0.03).astype(np.uint8)
+        elif trial % 4 == 1:
+            yy, xx = np.mgrid[0:H, 0:W]
+            img = (((yy - H / 2) ** 2 + (xx - W / 3) ** 2) < (min(H, W) / 3) ** 2).astype(np.uint8)
+        else:
+            for _ in range(int(rng.integers(1, 5))):
+                y, x, h, w = int(rng.integers(0, H)), int(rng.integers(0, W)), int(rng.integers(1, 20)), int(rng.integers(1, 20))
+                img[y:y + h, x:x + w] = 1
+        if not img.any():
+            img[H // 2, W // 2] = 1
+        xmin, xmax = np.full(H, -1, np.int32), np.full(H, -1, np.int32)
+        for y in range(H):
+            c = np.nonzero(img[y])[0]
+            if len(c):
+                xmin[y], xmax[y] = c[0], c[-1]
+        xl, xr = capi.hull_rows(xmin, xmax)
+        got = np.zeros((H, W), bool)
+        for y in range(H):
+            if xl[y] <= xr[y]:
+                got[y, max(int(xl[y]), 0):min(int(xr[y]), W - 1) + 1] = True
+        np.testing.assert_array_equal(got, O.convex_hull_image(img), err_msg=f"trial {trial} ({H}x{W})")
+        assert (got | ~(img != 0)).all()                      # the hull contains the set

@@ -33,6 +33,7 @@ SYMBOLS = (
     "wsi_find_nuclei", "wsi_plan_tiles_gpu", "wsi_forward_patches",
     "wsi_forward_batch_tta", "wsi_debug_umma_shift", "wsi_check", "wsi_debug_conv_f32", "wsi_op_stats",
     "wsi_ipc_alloc", "wsi_ipc_open", "wsi_ipc_close", "wsi_ipc_free",
+    "wsi_morph", "wsi_tumor_bed", "wsi_overlay", "wsi_hull_rows",
 )
 
 
@@ -95,6 +96,10 @@ def lib() -> C.CDLL:
         "wsi_debug_conv_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
         "wsi_check": (C.c_int, [vp, vp]),
+        "wsi_morph": (C.c_int, [vp, vp, i64, i64, C.c_int, C.c_int, vp, C.c_int, vp]),
+        "wsi_tumor_bed": (C.c_int, [vp, vp, i64, i64, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(i64), C.c_int, vp]),
+        "wsi_overlay": (C.c_int, [vp, vp, vp, i64, i64, C.c_int, vp, vp, vp, vp, C.c_int, vp]),
+        "wsi_hull_rows": (C.c_int, [vp, vp, i64, vp, vp]),
         "wsi_ipc_alloc": (C.c_int, [vp, i64, C.POINTER(vp), C.c_char_p]),
         "wsi_ipc_open": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
         "wsi_ipc_close": (C.c_int, [vp, vp]),
@@ -171,6 +176,26 @@ def band_tiles(xy: np.ndarray, ph, m, own0, own1) -> np.ndarray:
     finally:
         L.wsi_free(idx)
     return out
+
+
+def hull_rows(xmin: np.ndarray, xmax: np.ndarray):
+    """Host part of convex_hull_image: per-row first / last set column (-1 for empty rows) -> inclusive hull range per row."""
+    xmin = np.ascontiguousarray(xmin, dtype=np.int32)
+    xmax = np.ascontiguousarray(xmax, dtype=np.int32)
+    H = xmin.shape[0]
+    xl, xr = np.empty(H, np.int32), np.empty(H, np.int32)
+    _check(lib().wsi_hull_rows(_np_ptr(xmin), _np_ptr(xmax), H, _np_ptr(xl), _np_ptr(xr)))
+    return xl, xr
+
+
+MORPH_ERODE, MORPH_DILATE, MORPH_OPEN, MORPH_CLOSE = 0, 1, 2, 3
+OVERLAY_HEAT, OVERLAY_BED = 0, 1
+
+
+def rule_lut(rule) -> np.ndarray:
+    """A per-level threshold rule of the reference, evaluated by numpy for the 256 u8 levels exactly as the reference
+    evaluates it per pixel (e.g. ``lambda v: v >= 0.99 * 255``) -> u8 [256] of {0, 1}."""
+    return np.ascontiguousarray(np.asarray(rule(np.arange(256, dtype=np.uint8))).astype(np.uint8))
 
 
 # ------------------------------------------------------------------------------------------
@@ -413,6 +438,57 @@ class Context:
             return np.ctypeslib.as_array(xy, shape=(max(n.value, 1), 2))[:n.value].copy() if n.value else np.zeros((0, 2), np.int32)
         finally:
             self._lib.wsi_free(xy)
+
+    # ---- tumour-bed post-processing ------------------------------------------
+    def _u8_like(self, ref, shape):
+        import torch
+        if isinstance(ref, np.ndarray):
+            return np.empty(shape, np.uint8)
+        return torch.empty(shape, dtype=torch.uint8, device=ref.device)
+
+    def morph(self, src, op: int, k: int, stream=None):
+        """cv2.erode / dilate / morphologyEx(OPEN | CLOSE) with np.ones((k, k)) — bit-exact.  src: u8 [H,W] numpy or CUDA tensor."""
+        p, mem, _ = _ptr_and_mem(src)
+        H, W = int(src.shape[0]), int(src.shape[1])
+        dst = self._u8_like(src, (H, W))
+        q, _, _ = _ptr_and_mem(dst)
+        _check(self._lib.wsi_morph(self._h, p, H, W, int(op), int(k), q, mem, _stream_ptr(stream)), self._h)
+        return dst
+
+    def tumor_bed(self, src, rule, open_k: int = 20, dilate_k: int = 20, want=("opened", "hull", "outline"), stream=None) -> dict:
+        """utils/eval.py:90-96: tb = rule(src); MORPH_OPEN(open_k); convex_hull_image; dilate(bwperim(.), dilate_k).
+        src: u8 [H,W] (class mask or heatmap; numpy or CUDA tensor); rule: callable on the u8 levels (see rule_lut).
+        Returns {'opened', 'hull', 'outline' (each u8 {0,1} [H,W], as requested), 'n_open': count_nonzero(opened)}."""
+        p, mem, _ = _ptr_and_mem(src)
+        H, W = int(src.shape[0]), int(src.shape[1])
+        lut = rule_lut(rule)
+        outs = {k: self._u8_like(src, (H, W)) for k in ("opened", "hull", "outline") if k in want}
+        ptr = lambda k: _ptr_and_mem(outs[k])[0] if k in outs else None
+        n_open = C.c_int64(0)
+        _check(self._lib.wsi_tumor_bed(self._h, p, H, W, _np_ptr(lut), int(open_k), int(dilate_k), ptr("opened"), ptr("hull"), ptr("outline"),
+                                       C.byref(n_open), mem, _stream_ptr(stream)), self._h)
+        outs["n_open"] = int(n_open.value)
+        return outs
+
+    def overlay_heat(self, rgb, heat, rule=lambda v: v > 255 * 0.99, stream=None):
+        """utils/eval.py:262-267: np.uint8(img * 0.75 + 255 * (heat > 255 * 0.99) * 0.25).  rgb u8 [H,W,3], heat u8 [H,W]."""
+        p, mem, _ = _ptr_and_mem(rgb)
+        q, mem2, _ = _ptr_and_mem(heat)
+        assert mem == mem2
+        H, W = int(heat.shape[0]), int(heat.shape[1])
+        out = self._u8_like(rgb, (H, W, 3))
+        lut = rule_lut(rule)
+        _check(self._lib.wsi_overlay(self._h, p, q, H, W, OVERLAY_HEAT, _np_ptr(lut), None, None, _ptr_and_mem(out)[0], mem, _stream_ptr(stream)), self._h)
+        return out
+
+    def overlay_bed(self, rgb, heat, im=None, perim=None, stream=None):
+        """paper_tools/overlay_tb_wsi.py:56-72: np.uint8(0.65 * img + 0.35 * (heat * im)), outline pixels 0."""
+        p, mem, _ = _ptr_and_mem(rgb)
+        H, W = int(heat.shape[0]), int(heat.shape[1])
+        out = self._u8_like(rgb, (H, W, 3))
+        _check(self._lib.wsi_overlay(self._h, p, _ptr_and_mem(heat)[0], H, W, OVERLAY_BED, None, _ptr_and_mem(im)[0], _ptr_and_mem(perim)[0],
+                                     _ptr_and_mem(out)[0], mem, _stream_ptr(stream)), self._h)
+        return out
 
     def resize_argmax(self, canvas, H2: int, W2: int, want_pred: bool = True, stream=None):
         """predict_wsis tail (utils/eval.py:66-81): canvas f32 [4,H,W] (torch CPU or CUDA) -> classes u8 [H2,W2]

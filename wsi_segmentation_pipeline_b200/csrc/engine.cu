@@ -1565,3 +1565,194 @@ int wsi_stage_reset(wsi_ctx* ctx) {
 }
 
 }  // extern "C"
+
+// ---- tumour-bed post-processing ---------------------------------------------------------------
+namespace wsi {
+
+struct P2 { int64_t x, y; };
+static inline __int128 cross3(const P2& o, const P2& a, const P2& b) { return (__int128)(a.x - o.x) * (b.y - o.y) - (__int128)(a.y - o.y) * (b.x - o.x); }
+static inline int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q; }
+static inline int64_t ceil_div_s(int64_t a, int64_t b) { return -floor_div(-a, b); }
+
+// skimage.morphology.convex_hull_image (offset_coordinates=True, include_borders=True) restated with exact integer
+// arithmetic in doubled coordinates: candidate points = the first / last set pixel of every row (the hull of the set
+// pixels is the hull of those), each replaced by the four midpoints of its pixel edges (x +- 1/2, y), (x, y +- 1/2);
+// hull by Andrew's monotone chain; a pixel centre belongs to the image iff it lies inside or ON the hull polygon.
+// Returns per row the inclusive pixel range [xl, xr] (xl > xr: empty).
+static void hull_row_ranges(const std::vector<int32_t>& xmin, const std::vector<int32_t>& xmax, int64_t H, std::vector<int32_t>& xl, std::vector<int32_t>& xr) {
+  std::vector<P2> pts;
+  for (int64_t y = 0; y < H; ++y) {
+    if (xmax[(size_t)y] < 0) continue;
+    const int32_t ends[2] = {xmin[(size_t)y], xmax[(size_t)y]};
+    for (int e = 0; e < (ends[0] == ends[1] ? 1 : 2); ++e) {
+      const int64_t X = 2 * (int64_t)ends[e], Y = 2 * y;
+      pts.push_back({X - 1, Y}); pts.push_back({X + 1, Y}); pts.push_back({X, Y - 1}); pts.push_back({X, Y + 1});
+    }
+  }
+  xl.assign((size_t)H, 1);
+  xr.assign((size_t)H, 0);
+  if (pts.empty()) return;
+  std::sort(pts.begin(), pts.end(), [](const P2& a, const P2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+  pts.erase(std::unique(pts.begin(), pts.end(), [](const P2& a, const P2& b) { return a.x == b.x && a.y == b.y; }), pts.end());
+  std::vector<P2> hull(2 * pts.size());
+  size_t k = 0;
+  for (size_t i = 0; i < pts.size(); ++i) {
+    while (k >= 2 && cross3(hull[k - 2], hull[k - 1], pts[i]) <= 0) --k;
+    hull[k++] = pts[i];
+  }
+  for (size_t i = pts.size() - 1, t = k + 1; i-- > 0;) {
+    while (k >= t && cross3(hull[k - 2], hull[k - 1], pts[i]) <= 0) --k;
+    hull[k++] = pts[i];
+  }
+  hull.resize(k > 1 ? k - 1 : k);
+  const size_t V = hull.size();
+  for (int64_t y = 0; y < H; ++y) {
+    const int64_t Y = 2 * y;
+    // exact min / max of X over the intersection of the line Y with the polygon: rationals num / den (den > 0)
+    bool any = false;
+    int64_t lo_n = 0, lo_d = 1, hi_n = 0, hi_d = 1;
+    auto upd = [&](int64_t n, int64_t d) {
+      if (!any) { lo_n = hi_n = n; lo_d = hi_d = d; any = true; return; }
+      if ((__int128)n * lo_d < (__int128)lo_n * d) { lo_n = n; lo_d = d; }
+      if ((__int128)n * hi_d > (__int128)hi_n * d) { hi_n = n; hi_d = d; }
+    };
+    for (size_t i = 0; i < V; ++i) {
+      const P2 &p = hull[i], &q = hull[(i + 1) % V];
+      if ((p.y < Y && q.y < Y) || (p.y > Y && q.y > Y)) continue;
+      if (p.y == q.y) { upd(p.x, 1); upd(q.x, 1); continue; }
+      int64_t d = q.y - p.y, n = p.x * d + (q.x - p.x) * (Y - p.y);
+      if (d < 0) { d = -d; n = -n; }
+      upd(n, d);
+    }
+    if (!any) continue;
+    // pixel x is inside iff lo <= 2x <= hi
+    xl[(size_t)y] = (int32_t)ceil_div_s(lo_n, 2 * lo_d);
+    xr[(size_t)y] = (int32_t)floor_div(hi_n, 2 * hi_d);
+  }
+}
+
+}  // namespace wsi
+
+extern "C" {
+
+int wsi_hull_rows(const int32_t* xmin, const int32_t* xmax, int64_t H, int32_t* xl, int32_t* xr) {
+  wsi_ctx* none = nullptr;
+  WSI_API_BEGIN
+  WSI_REQUIRE(xmin && xmax && xl && xr && H > 0, WSI_ERR_INVALID, "bad argument");
+  std::vector<int32_t> a(xmin, xmin + H), b(xmax, xmax + H), l, r;
+  hull_row_ranges(a, b, H, l, r);
+  memcpy(xl, l.data(), (size_t)H * sizeof(int32_t));
+  memcpy(xr, r.data(), (size_t)H * sizeof(int32_t));
+  WSI_API_END(none)
+}
+
+int wsi_morph(wsi_ctx* ctx, const uint8_t* src, int64_t H, int64_t W, int op, int k, uint8_t* dst, int mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && src && dst && H > 0 && W > 0 && op >= 0 && op <= 3, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)H * W;
+  DevBuf in, tmp, out;
+  tmp.alloc(n);
+  const uint8_t* sd = src;
+  uint8_t* dd = dst;
+  if (mem == WSI_MEM_HOST) {
+    in.alloc(n); out.alloc(n);
+    CUDA_CHECK(cudaMemcpyAsync(in.p, src, n, cudaMemcpyHostToDevice, s));
+    sd = in.as<uint8_t>(); dd = out.as<uint8_t>();
+  }
+  // cv2.morphologyEx: OPEN = dilate(erode(src)), CLOSE = erode(dilate(src)), same kernel and anchor for both passes
+  const bool first_max = (op == WSI_MORPH_DILATE || op == WSI_MORPH_CLOSE);
+  launch_morph(sd, H, W, k, first_max, tmp.as<uint8_t>(), dd, nullptr, s, &ctx->lc);
+  if (op == WSI_MORPH_OPEN || op == WSI_MORPH_CLOSE) launch_morph(dd, H, W, k, !first_max, tmp.as<uint8_t>(), dd, nullptr, s, &ctx->lc);
+  if (mem == WSI_MEM_HOST) CUDA_CHECK(cudaMemcpyAsync(dst, dd, n, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  WSI_API_END(ctx)
+}
+
+int wsi_tumor_bed(wsi_ctx* ctx, const uint8_t* src, int64_t H, int64_t W, const uint8_t* rule_lut, int open_k, int dilate_k, uint8_t* opened_out,
+                  uint8_t* hull_out, uint8_t* outline_out, int64_t* n_open_out, int mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && src && rule_lut && H > 0 && W > 0 && W < (1LL << 30) && open_k >= 1, WSI_ERR_INVALID, "bad argument");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)H * W;
+  const bool host = (mem == WSI_MEM_HOST);
+  DevBuf in, lut, bin, tmp, hull, perim, outline, cnt, ext;
+  const uint8_t* sd = src;
+  if (host) { in.alloc(n); CUDA_CHECK(cudaMemcpyAsync(in.p, src, n, cudaMemcpyHostToDevice, s)); sd = in.as<uint8_t>(); }
+  lut.alloc(256);
+  CUDA_CHECK(cudaMemcpyAsync(lut.p, rule_lut, 256, cudaMemcpyHostToDevice, s));
+  cnt.alloc(sizeof(unsigned long long));
+  CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), s));
+  tmp.alloc(n);
+  uint8_t* opened = (!host && opened_out) ? opened_out : (bin.alloc(n), bin.as<uint8_t>());
+  launch_lut(sd, (int64_t)n, lut.as<uint8_t>(), opened, nullptr, s, &ctx->lc);                                   // tb = rule(src)
+  launch_morph(opened, H, W, open_k, false, tmp.as<uint8_t>(), opened, nullptr, s, &ctx->lc);                    // cv2.MORPH_OPEN: erode ...
+  launch_morph(opened, H, W, open_k, true, tmp.as<uint8_t>(), opened, cnt.as<unsigned long long>(), s, &ctx->lc);   // ... then dilate
+  unsigned long long n_open = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&n_open, cnt.p, sizeof(n_open), cudaMemcpyDeviceToHost, s));
+  std::vector<int32_t> xmin, xmax, xl, xr;
+  if (hull_out || outline_out) {
+    ext.alloc((size_t)H * 4 * sizeof(int32_t));
+    int32_t* e = ext.as<int32_t>();
+    launch_row_extent(opened, H, W, e, e + H, s, &ctx->lc);
+    xmin.resize((size_t)H); xmax.resize((size_t)H);
+    CUDA_CHECK(cudaMemcpyAsync(xmin.data(), e, (size_t)H * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(xmax.data(), e + H, (size_t)H * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (n_open_out) *n_open_out = (int64_t)n_open;
+  if (host && opened_out) CUDA_CHECK(cudaMemcpyAsync(opened_out, opened, n, cudaMemcpyDeviceToHost, s));
+  if (hull_out || outline_out) {
+    hull_row_ranges(xmin, xmax, H, xl, xr);                   // O(H x hull vertices) on the host: 2H points in, a few hundred vertices out
+    int32_t* e = ext.as<int32_t>();
+    CUDA_CHECK(cudaMemcpyAsync(e + 2 * H, xl.data(), (size_t)H * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(e + 3 * H, xr.data(), (size_t)H * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    uint8_t* hd = (!host && hull_out) ? hull_out : (hull.alloc(n), hull.as<uint8_t>());
+    launch_fill_rows(e + 2 * H, e + 3 * H, H, W, hd, s, &ctx->lc);                                               // chull(tb)
+    if (host && hull_out) CUDA_CHECK(cudaMemcpyAsync(hull_out, hd, n, cudaMemcpyDeviceToHost, s));
+    if (outline_out) {
+      perim.alloc(n);
+      launch_bwperim(hd, H, W, perim.as<uint8_t>(), s, &ctx->lc);                                                // bwperim(tb_pred)
+      uint8_t* od = (!host) ? outline_out : (outline.alloc(n), outline.as<uint8_t>());
+      if (dilate_k > 1) launch_morph(perim.as<uint8_t>(), H, W, dilate_k, true, tmp.as<uint8_t>(), od, nullptr, s, &ctx->lc);   // cv2.dilate
+      else CUDA_CHECK(cudaMemcpyAsync(od, perim.p, n, cudaMemcpyDeviceToDevice, s));
+      if (host) CUDA_CHECK(cudaMemcpyAsync(outline_out, od, n, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  WSI_API_END(ctx)
+}
+
+int wsi_overlay(wsi_ctx* ctx, const uint8_t* rgb, const uint8_t* heat, int64_t H, int64_t W, int mode, const uint8_t* on_lut, const uint8_t* im,
+                const uint8_t* perim, uint8_t* out, int mem, void* stream) {
+  WSI_API_BEGIN
+  WSI_REQUIRE(ctx && rgb && heat && out && H > 0 && W > 0 && (mode == WSI_OVERLAY_HEAT || mode == WSI_OVERLAY_BED), WSI_ERR_INVALID, "bad argument");
+  WSI_REQUIRE(mode != WSI_OVERLAY_HEAT || on_lut, WSI_ERR_INVALID, "WSI_OVERLAY_HEAT needs the 256-level rule table");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)H * W;
+  const bool host = (mem == WSI_MEM_HOST);
+  DevBuf b_rgb, b_heat, b_im, b_perim, b_out, lut;
+  auto dev_in = [&](DevBuf& b, const uint8_t* p, size_t bytes) -> const uint8_t* {
+    if (!p || !host) return p;
+    b.alloc(bytes);
+    CUDA_CHECK(cudaMemcpyAsync(b.p, p, bytes, cudaMemcpyHostToDevice, s));
+    return b.as<uint8_t>();
+  };
+  const uint8_t *d_rgb = dev_in(b_rgb, rgb, 3 * n), *d_heat = dev_in(b_heat, heat, n), *d_im = dev_in(b_im, im, n), *d_perim = dev_in(b_perim, perim, n);
+  uint8_t* d_out = host ? (b_out.alloc(3 * n), b_out.as<uint8_t>()) : out;
+  if (mode == WSI_OVERLAY_HEAT) {
+    lut.alloc(256);
+    CUDA_CHECK(cudaMemcpyAsync(lut.p, on_lut, 256, cudaMemcpyHostToDevice, s));
+    launch_overlay_heat(d_rgb, d_heat, (int64_t)n, lut.as<uint8_t>(), d_out, s, &ctx->lc);
+  } else {
+    launch_overlay_bed(d_rgb, d_heat, d_im, d_perim, (int64_t)n, d_out, s, &ctx->lc);
+  }
+  if (host) CUDA_CHECK(cudaMemcpyAsync(out, d_out, 3 * n, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  WSI_API_END(ctx)
+}
+
+}  // extern "C"

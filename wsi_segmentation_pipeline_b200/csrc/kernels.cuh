@@ -84,4 +84,16 @@ void launch_window_count(const uint8_t* mask, int64_t mh, int64_t mw, const int6
 void launch_ensemble_head(const float* feats, int B, int P, const float* w1, const float* b1, int n_hid, const float* w2, const float* b2,
                           int n_out, float* hid, float* out, cudaStream_t s, LaunchCounter* lc);
 
+// ---- tumour-bed post-processing (postproc.cu) ----------------------------------------------------
+void launch_lut(const uint8_t* src, int64_t n, const uint8_t* lut_dev, uint8_t* dst, unsigned long long* nonzero_or_null, cudaStream_t s, LaunchCounter* lc);
+// one k x k erosion (is_max = false) / dilation (true) with cv2's window and border rule; tmp: H*W scratch; src may equal dst
+void launch_morph(const uint8_t* src, int64_t H, int64_t W, int k, bool is_max, uint8_t* tmp, uint8_t* dst, unsigned long long* nonzero_or_null,
+                  cudaStream_t s, LaunchCounter* lc);
+void launch_row_extent(const uint8_t* mask, int64_t H, int64_t W, int32_t* xmin, int32_t* xmax, cudaStream_t s, LaunchCounter* lc);
+void launch_fill_rows(const int32_t* xl, const int32_t* xr, int64_t H, int64_t W, uint8_t* out, cudaStream_t s, LaunchCounter* lc);
+void launch_bwperim(const uint8_t* bw, int64_t H, int64_t W, uint8_t* out, cudaStream_t s, LaunchCounter* lc);
+void launch_overlay_heat(const uint8_t* rgb, const uint8_t* heat, int64_t n_px, const uint8_t* on_lut_dev, uint8_t* out, cudaStream_t s, LaunchCounter* lc);
+void launch_overlay_bed(const uint8_t* rgb, const uint8_t* heat, const uint8_t* im_or_null, const uint8_t* perim_or_null, int64_t n_px, uint8_t* out,
+                        cudaStream_t s, LaunchCounter* lc);
+
 }  // namespace wsi

@@ -80,15 +80,35 @@ def predict_tumorbed(model, dataset, ep, mode: str = "seg", args=None, return_ou
             Image.fromarray(heat).save(f"{a.val_save_pth}/{ep}/{key}_{a.tile_stride_w}_heatmap.png")     # :229
             if a.save_overlay:                                                                            # :262-267
                 scan = entry["scan"]
-                img = np.asarray(scan.read_region((0, 0), 2, scan.level_dimensions[2]).convert("RGB")).astype(np.uint8)
-                img = img * 0.75 + 255 * np.repeat(np.expand_dims(heat > 255 * 0.99, -1), repeats=3, axis=-1) * 0.25
-                Image.fromarray(np.uint8(img)).save(f"{a.val_save_pth}/{ep}/{key}_{a.tile_stride_w}_overlay.png")
+                img = np.ascontiguousarray(np.asarray(scan.read_region((0, 0), 2, scan.level_dimensions[2]).convert("RGB")), dtype=np.uint8)
+                over = ctx.overlay_heat(img, np.ascontiguousarray(heat))            # img * 0.75 + 255 * (heat > 255 * 0.99) * 0.25, on the device
+                Image.fromarray(over).save(f"{a.val_save_pth}/{ep}/{key}_{a.tile_stride_w}_overlay.png")
         if return_outputs:
             outputs[key] = {"classes": classes, "heatmap": heat}
         dataset.wsis[key] = None                                                                          # :282
     if hasattr(model, "train"):
         model.train()                                                                                     # :286
     return outputs
+
+
+# the reference's three tumour-bed rules (evaluated per u8 level by numpy, exactly as the reference evaluates them per pixel)
+RULE_CLASSES_GE2 = lambda v: v >= 2                                                     # utils/eval.py:91  (p >= 2)
+RULE_HEAT_099 = lambda v: v >= 0.99 * 255                                               # paper_tools/check_for_false_positives.py:64
+RULE_HEAT_090 = lambda v: v / 255 >= 0.9                                                # paper_tools/overlay_tb_wsi.py:48
+
+
+def tumor_bed(model, src, rule=RULE_CLASSES_GE2, open_k: int = 20, dilate_k: int = 20, **kw) -> dict:
+    """The tumour-bed chain that follows the argmax in predict_wsis (utils/eval.py:90-96) and the heatmap in
+    paper_tools/: threshold rule -> cv2 MORPH_OPEN -> convex hull image -> perimeter -> dilate, on the device
+    (``wsi_tumor_bed``).  ``src``: u8 class mask or heatmap (numpy or CUDA tensor)."""
+    return _engine_of(model).tumor_bed(src, rule, open_k, dilate_k, **kw)
+
+
+def slide_has_tumor(model, heatmap, open_k: int = 50, cancer_thresh: float = 0.0) -> bool:
+    """paper_tools/check_for_false_positives.py:62-72: heatmap >= 0.99 * 255, MORPH_OPEN 50 x 50,
+    count_nonzero / size > cancer_thresh."""
+    r = _engine_of(model).tumor_bed(heatmap, RULE_HEAT_099, open_k, 0, want=())
+    return r["n_open"] / float(heatmap.shape[0] * heatmap.shape[1]) > cancer_thresh
 
 
 def predict_wsis(model, dataset, ep, args=None):
