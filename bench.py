@@ -337,6 +337,7 @@ class Runner:
         else:
             self.dev_out = {k: torch.empty((self.rows, iw), dtype=torch.uint8, device="cuda") for k in ("classes", "heatmap")}
         self.host_raster = None
+        self.shared_host = False
 
     def slide(self, raster):
         return self.ctx.slide_desc(raster, self.ih, self.iw, self.tile, self.tile, row0=self.row0, rows=self.row1 - self.row0,
@@ -375,22 +376,42 @@ class Runner:
         if self.world == 1:
             self.host_out = {k: torch.empty((self.rows, self.iw), dtype=torch.uint8, pin_memory=True) for k in ("classes", "heatmap")}
             return
-        # one host result shared by all ranks: POSIX shared memory, page-locked in every process
+        # one host result shared by all ranks: POSIX shared memory, page-locked in every process.  When /dev/shm cannot
+        # hold it (container limit) or cannot be page-locked, every rank keeps its rows in its own pinned buffer instead.
+        import shutil
         import torch.distributed as dist
-        name = [f"/dev/shm/wsi_b200_bench_{os.getpid()}"] if self.rank == 0 else [None]
-        dist.broadcast_object_list(name, src=0)
-        self._shm_path = name[0]
         nbytes = 2 * self.ih * self.iw
+        name = [None]
         if self.rank == 0:
-            with open(self._shm_path, "wb") as f:
-                f.truncate(nbytes)
+            try:
+                if shutil.disk_usage("/dev/shm").free > nbytes + (1 << 30):
+                    name = [f"/dev/shm/wsi_b200_bench_{os.getpid()}"]
+                    with open(name[0], "wb") as f:
+                        f.truncate(nbytes)
+            except OSError:
+                name = [None]
+        dist.broadcast_object_list(name, src=0)
+        self._shm_path, self._shm, ok = name[0], None, 0
+        if self._shm_path is not None:
+            try:
+                self._shm = torch.from_file(self._shm_path, shared=True, size=nbytes, dtype=torch.uint8)
+                ok = 1 if int(torch.cuda.cudart().cudaHostRegister(self._shm.data_ptr(), nbytes, 0)) == 0 else 0
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.shared_host = bool(int(flag.item()))
+        if self.shared_host:
+            full = self._shm.view(2, self.ih, self.iw)
+            self.host_out = {"classes": full[0, self.own0:self.own1], "heatmap": full[1, self.own0:self.own1]}
+            return
+        if self._shm is not None and ok:
+            torch.cuda.cudart().cudaHostUnregister(self._shm.data_ptr())
+        self._shm = None
         dist.barrier()
-        self._shm = torch.from_file(self._shm_path, shared=True, size=nbytes, dtype=torch.uint8)
-        rc = torch.cuda.cudart().cudaHostRegister(self._shm.data_ptr(), nbytes, 0)
-        if int(rc) != 0:
-            raise RuntimeError(f"cudaHostRegister failed: {rc}")
-        full = self._shm.view(2, self.ih, self.iw)
-        self.host_out = {"classes": full[0, self.own0:self.own1], "heatmap": full[1, self.own0:self.own1]}
+        if self.rank == 0 and self._shm_path and os.path.exists(self._shm_path):
+            os.unlink(self._shm_path)
+        self.host_out = {k: torch.empty((self.rows, self.iw), dtype=torch.uint8, pin_memory=True) for k in ("classes", "heatmap")}
 
     def step_host(self):
         self.ctx.run_slide(self.slide(self.host_raster), self.my_tiles, self.head, device_out=False, out=self.host_out)
@@ -545,6 +566,13 @@ def main():
     # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region ----------------
     e2e = None
     if not args.no_e2e:
+        # pinned band raster + (N > 1) the shared pinned result: skip e2e rather than exhaust the box's host memory
+        import psutil
+        need = (R.row1 - R.row0) * iw * 3 * n_gpus + 2 * ih * iw
+        if need > 0.4 * psutil.virtual_memory().available:
+            args.no_e2e = True
+            e2e = {"skipped": f"host buffers of {need / 1e9:.1f} GB exceed 40 % of the available host memory"}
+    if not args.no_e2e:
         ctx.set_option("stage_timing", 0)
         R.prepare_host()
         R.step_host()
@@ -555,7 +583,8 @@ def main():
         e2e = {"value": mpx / (e_ms * 1e-3), "unit": "Mpx/s", "ms_per_step": e_ms, "steps": args.steps,
                "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(2 * ih * iw),
                "how": "pinned band raster -> wsi_run_slide(WSI_MEM_HOST) -> u8 mask + heatmap in host memory"
-                      + ("" if n_gpus == 1 else "; every rank writes its rows into one POSIX-shared, page-locked host buffer over its own PCIe link")}
+                      + ("" if n_gpus == 1 else ("; every rank writes its rows into one POSIX-shared, page-locked host buffer over its own PCIe link"
+                                                 if R.shared_host else "; every rank keeps its rows in its own pinned host buffer (/dev/shm too small for one shared result)"))}
         R.release_host()
 
     if rank == 0:

@@ -100,7 +100,7 @@ struct wsi_ctx {
   std::vector<EventSpan> spans;
   std::vector<cudaEvent_t> event_pool;
   // scratch reused across slides
-  DevBuf raster, maskbuf, logit_ring, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, tile_logits, scratch_f32, counts;
+  DevBuf raster, maskbuf, logit_ring, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, rect_rows, tile_logits, scratch_f32, counts;
   // copy streams: chunked raster upload / strip-wise output download overlap the compute on the caller's stream
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // pinned staging for the per-slide index arrays (tile list, rect index): uploaded without a stream sync
@@ -729,10 +729,11 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   // index arrays -> pinned staging -> device, stream-ordered (no host sync)
   {
     if (c->idx_pending) { CUDA_CHECK(cudaEventSynchronize(c->idx_event)); c->idx_pending = false; }
-    const size_t n_xy = (size_t)2 * T, n_tx = (size_t)T, n_ry = rowy.size(), n_rs = rowstart.size();
-    c->idx_host.alloc((n_xy + n_tx + n_ry + n_rs) * sizeof(int32_t));
+    const size_t n_xy = (size_t)2 * T, n_tx = (size_t)T, n_ry = rowy.size(), n_rs = rowstart.size(), n_ri = rowy.size() * 8;
+    c->idx_host.alloc((n_xy + n_tx + n_ry + n_rs + n_ri + 8) * sizeof(int32_t));
     int32_t* h = static_cast<int32_t*>(c->idx_host.p);
-    int32_t *h_xy = h, *h_tx = h + n_xy, *h_ry = h_tx + n_tx, *h_rs = h_ry + n_ry;
+    int32_t *h_xy = h, *h_tx = h + n_xy, *h_ry = h_tx + n_tx, *h_rs = h_ry + n_ry, *h_ri = h_rs + n_rs;
+    h_ri += (4 - ((h_ri - h) & 3)) & 3;                       // RowInfo entries are read with 16-byte loads
     for (int64_t i = 0; i < T; ++i) {
       const int32_t o = order[i];
       h_xy[2 * i] = tiles_xy[2 * o];
@@ -741,6 +742,18 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
     }
     if (n_ry) memcpy(h_ry, rowy.data(), n_ry * sizeof(int32_t));
     memcpy(h_rs, rowstart.data(), n_rs * sizeof(int32_t));
+    static_assert(sizeof(RowInfo) == 32, "RowInfo is 8 ints");
+    for (size_t r = 0; r < n_ry; ++r) {                       // per tile row: its rects and the regular-grid prefix of their x origins
+      RowInfo q{};
+      q.ry = rowy[r]; q.a = rowstart[r]; q.b = rowstart[r + 1];
+      q.tx0 = h_tx[q.a]; q.step = 0; q.nreg = 1;
+      if (q.b - q.a >= 2 && h_tx[q.a + 1] > h_tx[q.a]) {
+        q.step = h_tx[q.a + 1] - h_tx[q.a];
+        q.nreg = 2;
+        while (q.a + q.nreg < q.b && h_tx[q.a + q.nreg] - h_tx[q.a + q.nreg - 1] == q.step) ++q.nreg;
+      }
+      memcpy(h_ri + 8 * r, &q, sizeof(q));
+    }
     auto up = [&](DevBuf& b, const int32_t* src, size_t n) {
       b.alloc(std::max<size_t>(n, 1) * sizeof(int32_t));
       if (n) CUDA_CHECK(cudaMemcpyAsync(b.p, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -749,6 +762,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
     up(c->rect_tx, h_tx, n_tx);
     up(c->rect_rowy, h_ry, n_ry);
     up(c->rect_rowstart, h_rs, n_rs);
+    up(c->rect_rows, h_ri, n_ri);
     CUDA_CHECK(cudaEventRecord(c->idx_event, s));
     c->idx_pending = true;
   }
@@ -756,6 +770,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   ri.tx = c->rect_tx.as<int32_t>();
   ri.row_y = c->rect_rowy.as<int32_t>();
   ri.row_start = c->rect_rowstart.as<int32_t>();
+  ri.rows = c->rect_rows.as<RowInfo>();
   ri.R = (int32_t)rowy.size();
   ri.dx = (int32_t)dx;
   ri.dy = (int32_t)dy;
@@ -804,6 +819,11 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   const double tile_px = (double)ph * pw;
   const int64_t tile_elems = (int64_t)ph * pw * 4;
 
+  // tile rows [r_lo, r_hi) that can touch canvas rows [ya, yb)
+  auto row_range = [&](int64_t ya, int64_t yb, int* r_lo, int* r_hi) {
+    *r_lo = (int)(std::upper_bound(rowy.begin(), rowy.end(), (int32_t)std::max<int64_t>(ya - dy, INT32_MIN)) - rowy.begin());
+    *r_hi = (int)(std::upper_bound(rowy.begin(), rowy.end(), (int32_t)std::min<int64_t>(yb - 1, INT32_MAX)) - rowy.begin());
+  };
   // first sorted tile that can still touch canvas row y: ty + dy > y
   auto first_needed = [&](int64_t y) { return (int64_t)(std::upper_bound(sty.begin(), sty.end(), (int32_t)std::max<int64_t>(y - dy, INT32_MIN)) - sty.begin()); };
   // rows below which no unprocessed tile starts once the first e sorted tiles are done
@@ -861,7 +881,9 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
         // algorithmic bytes (fused stitch + finalise): T*P*C*4 logits read once + S*2 written (+ S mask read)
         StageScope scope(c, s, ST_STITCH, pending_logit_bytes + (double)(y_ready - y_done) * W2 * (mask_dev ? 3.0 : 2.0));
         pending_logit_bytes = 0;
-        launch_stitch_finalise_seg(ri, c->logit_ring.as<float4>(), (int)ring_cap, (int)first_needed(y_done), (int)e, y_done, y_ready, fa, s, &c->lc);
+        int r_lo, r_hi;
+        row_range(y_done, y_ready, &r_lo, &r_hi);
+        launch_stitch_finalise_seg(ri, c->logit_ring.as<float4>(), (int)ring_cap, (int)first_needed(y_done), (int)e, r_lo, r_hi, y_done, y_ready, fa, s, &c->lc);
       }
       if (y_ready > y_done) { download_rows(y_done, y_ready); y_done = y_ready; }
     } else {
@@ -873,13 +895,15 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   if (head == WSI_HEAD_SEG) {
     if (y_done < own1) {                       // T == 0 (or nothing owned was reached): uncovered rows
       StageScope scope(c, s, ST_STITCH, (double)(own1 - y_done) * W2 * (mask_dev ? 3.0 : 2.0));
-      launch_stitch_finalise_seg(ri, c->logit_ring.as<float4>(), (int)std::max<int64_t>(ring_cap, 1), 0, 0, y_done, own1, fa, s, &c->lc);
+      launch_stitch_finalise_seg(ri, c->logit_ring.as<float4>(), (int)std::max<int64_t>(ring_cap, 1), 0, 0, 0, 0, y_done, own1, fa, s, &c->lc);
       download_rows(y_done, own1);
     }
   } else {
     {
       StageScope scope(c, s, ST_STITCH, (double)T * 16.0 + (double)plane * (mask_dev ? 3.0 : 2.0));
-      launch_stitch_finalise_cls(ri, c->tile_logits.as<float4>(), (int)T, fa, s, &c->lc);
+      int r_lo, r_hi;
+      row_range(own0, own1, &r_lo, &r_hi);
+      launch_stitch_finalise_cls(ri, c->tile_logits.as<float4>(), (int)T, own0, own1, r_lo, r_hi, fa, s, &c->lc);
     }
     download_rows(own0, own1);
   }

@@ -437,41 +437,65 @@ __device__ __forceinline__ void write_pixel(const FinaliseArgs& a, int64_t idx, 
   }
 }
 
-// visit, in sorted order, the tiles of [t_lo, t_hi) that cover row Y and may cover columns [X0, X0 + span): f(i, tx, oy).
-// All control flow is uniform across the CTA.
-template <class F>
-__device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo, int t_hi, int X0, int span, int Y, F&& f) {
-  int lo = 0, hi = ri.R;
-  while (lo < hi) {  // first row with row_y > Y - dy
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(ri.row_y + mid) > Y - ri.dy) hi = mid; else lo = mid + 1;
-  }
-  for (int r = lo; r < ri.R; ++r) {
-    const int ry = __ldg(ri.row_y + r);
-    if (ry > Y) break;
-    const int a = max(__ldg(ri.row_start + r), t_lo), b = min(__ldg(ri.row_start + r + 1), t_hi);
-    if (a >= b) continue;
-    int l2 = a, h2 = b;
-    while (l2 < h2) {  // first rect with tx > X0 - dx
-      const int mid = (l2 + h2) >> 1;
-      if (__ldg(ri.tx + mid) > X0 - ri.dx) h2 = mid; else l2 = mid + 1;
+// x origin of sorted rect i of row q
+__device__ __forceinline__ int rect_tx(const RectIndex& ri, const RowInfo& q, int i) {
+  return (i < q.a + q.nreg) ? q.tx0 + (i - q.a) * q.step : __ldg(ri.tx + i);
+}
+// first rect i in [a2, b2) of row q with tx(i) > lim: O(1) on the regular prefix, a short scan / bisection on the rest
+__device__ __forceinline__ int row_first_right_of(const RectIndex& ri, const RowInfo& q, int lim, int a2, int b2) {
+  int i = q.a;
+  if (lim >= q.tx0) i = q.a + ((q.step > 0) ? min((lim - q.tx0) / q.step + 1, q.nreg) : 1);
+  i = min(max(i, a2), b2);
+  if (i >= q.a + q.nreg) {                       // irregular tail
+    if (b2 - i > 8) {
+      int lo = i, hi = b2;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(ri.tx + mid) > lim) hi = mid; else lo = mid + 1;
+      }
+      i = lo;
+    } else {
+      while (i < b2 && __ldg(ri.tx + i) <= lim) ++i;
     }
-    for (int i = l2; i < b; ++i) {
-      const int tx = __ldg(ri.tx + i);
+  }
+  return i;
+}
+
+// visit, in sorted order, the tiles of [t_lo, t_hi) in tile rows [r_lo, r_hi) that cover row Y and may cover columns
+// [X0, X0 + span): f(i, tx, oy).  All control flow is uniform across the CTA; a regular tile grid needs one 32-byte
+// RowInfo load per tile row and no other index access (the first version bisected row_y and tx per CTA: ~70 dependent
+// L1 round trips, ~3 000 cycles of latency per 256 pixels).
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo, int t_hi, int r_lo, int r_hi, int X0, int span, int Y, F&& f) {
+  for (int r = r_lo; r < r_hi; ++r) {
+    const int4 w0 = __ldg(reinterpret_cast<const int4*>(ri.rows + r));
+    const int4 w1 = __ldg(reinterpret_cast<const int4*>(ri.rows + r) + 1);
+    RowInfo q;
+    q.ry = w0.x; q.a = w0.y; q.b = w0.z; q.tx0 = w0.w; q.step = w1.x; q.nreg = w1.y;
+    if (q.ry > Y) break;
+    if (q.ry + ri.dy <= Y) continue;
+    const int a2 = max(q.a, t_lo), b2 = min(q.b, t_hi);
+    if (a2 >= b2) continue;
+    for (int i = row_first_right_of(ri, q, X0 - ri.dx, a2, b2); i < b2; ++i) {
+      const int tx = rect_tx(ri, q, i);
       if (tx >= X0 + span) break;
-      f(i, tx, Y - ry);
+      f(i, tx, Y - q.ry);
     }
   }
 }
 
 // seg: logits of sorted tile i live in slot i % ring_cap of `ring` (f32 [ring_cap][dy][dx][4]); rows [y0, y0 + gridDim.x).
 // A CTA owns PX * 256 consecutive pixels of one canvas row, a thread PX of them 256 apart (coalesced per access).
-// Measured (12k x 12k slide, same box): PX = 1 / 2 / 4 -> 2.20 / 2.35 / 1.55 TB/s; an L1-prefetch pass ahead of the
-// accumulate pass made every variant slower.  ncu: the 64 F2F.F64.F32 per pixel keep the XU pipe 36 % busy and the
-// double-precision finalise costs registers (occupancy), the kernel is issue/latency-bound, not DRAM-bound (21 %).
+// Measured (12k x 12k slide, same box, T*P*16 + 2*S algorithmic bytes): PX = 1 / 2 / 4 -> 2.20 / 2.35 / 1.55 TB/s; an
+// L1-prefetch pass ahead of the accumulate pass made every variant slower; O(1) tile lookup (RowInfo) -> 2.62 TB/s; a
+// variant that staged every covering run in shared memory with cp.async.bulk (192 KB in flight per SM, no load
+// scoreboard) was SLOWER (2.27 TB/s: one thread walks the candidates per CTA) — the stage is not starved for bytes in
+// flight.  Cost split by elimination: float accumulation instead of double -0.9 ms of 13.3, float finalise -2.0 ms,
+// both -3.4 ms (3.55 TB/s): the float64 arithmetic that makes the stage bit-compatible with the reference's float64
+// canvas costs a quarter of it; the rest is the 16-way gather itself (28 address streams per CTA, 92 strip launches).
 template <int PX>
 __global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, const float4* __restrict__ ring, int ring_cap, int t_lo, int t_hi,
-                                                                   int y0, FinaliseArgs a) {
+                                                                   int r_lo, int r_hi, int y0, FinaliseArgs a) {
   const int Y = y0 + blockIdx.x;
   const int X0 = blockIdx.y * (256 * PX);
   const int Xt = X0 + threadIdx.x;
@@ -479,7 +503,7 @@ __global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, 
   double s[PX][4];
 #pragma unroll
   for (int k = 0; k < PX; ++k) s[k][0] = s[k][1] = s[k][2] = s[k][3] = 0.0;
-  for_each_candidate(ri, t_lo, t_hi, X0, 256 * PX, Y, [&](int i, int tx, int oy) {
+  for_each_candidate(ri, t_lo, t_hi, r_lo, r_hi, X0, 256 * PX, Y, [&](int i, int tx, int oy) {
     const float4* src = ring + (int64_t)(i % ring_cap) * tile_px + (int64_t)oy * ri.dx;
     float4 v[PX];
     bool hit[PX];
@@ -505,24 +529,25 @@ __global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, 
   }
 }
 
-void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int64_t y0, int64_t y1,
+void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int r_lo, int r_hi, int64_t y0, int64_t y1,
                                 const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
   if (y1 <= y0 || a.W2 <= 0) return;
   constexpr int px = 2;
   dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256 * px));
-  stitch_finalise_seg_kernel<px><<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, (int)y0, a);
+  stitch_finalise_seg_kernel<px><<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, r_lo, r_hi, (int)y0, a);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
 
 // cls: pred_src [C] broadcast over the tile rectangle (utils/eval.py:210-215); tile_logits f32 [T][4] in sorted order
-__global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, const float4* __restrict__ tile_logits, int T, int y0, FinaliseArgs a) {
+__global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, const float4* __restrict__ tile_logits, int T, int r_lo, int r_hi, int y0,
+                                                                   FinaliseArgs a) {
   const int Y = y0 + blockIdx.x;
   const int X0 = blockIdx.y * 256;
   const int X = X0 + threadIdx.x;
   const bool live = X < a.W2;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for_each_candidate(ri, 0, T, X0, 256, Y, [&](int i, int tx, int) {
+  for_each_candidate(ri, 0, T, r_lo, r_hi, X0, 256, Y, [&](int i, int tx, int) {
     const int ox = X - tx;
     if (live && ox >= 0 && ox < ri.dx) {
       const float4 v = __ldg(tile_logits + i);
@@ -536,10 +561,11 @@ __global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, 
   write_pixel(a, idx, plane, s0, s1, s2, s3, o);
 }
 
-void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
-  if (a.own1 <= a.own0 || a.W2 <= 0) return;
-  dim3 grid((unsigned)(a.own1 - a.own0), (unsigned)ceil_div(a.W2, 256));
-  stitch_finalise_cls_kernel<<<grid, 256, 0, s>>>(ri, tile_logits, T, (int)a.own0, a);
+void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, int64_t y0, int64_t y1, int r_lo, int r_hi, const FinaliseArgs& a,
+                                cudaStream_t s, LaunchCounter* lc) {
+  if (y1 <= y0 || a.W2 <= 0) return;
+  dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256));
+  stitch_finalise_cls_kernel<<<grid, 256, 0, s>>>(ri, tile_logits, T, r_lo, r_hi, (int)y0, a);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }

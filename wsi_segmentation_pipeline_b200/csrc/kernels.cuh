@@ -8,10 +8,21 @@ namespace wsi {
 
 // Rectangles (tiles mapped to canvas coordinates) sorted by (ty, tx) with a row index, the
 // lookup structure of the atomic-free gather-formulated stitch.
+struct RowInfo {            // one tile row (all sorted rects sharing a canvas y origin), 32 bytes
+  int32_t ry;               // canvas y origin
+  int32_t a, b;             // sorted rects [a, b)
+  int32_t tx0, step, nreg;  // the first nreg rects sit at tx0 + k * step (the regular grid of the tile planner; nreg >= 1,
+                            // step = 0 when nreg == 1): their x origin needs no memory access and the first rect right
+                            // of a given x is found in O(1); rects [a + nreg, b) (the reference's extra right-column
+                            // tile, or anything after a gap left by the foreground filter) are looked up in `tx`
+  int32_t pad0, pad1;
+};
+
 struct RectIndex {
   const int32_t* tx;        // [T] canvas x origin of sorted rect i
   const int32_t* row_y;     // [R] distinct canvas y origins, ascending
   const int32_t* row_start; // [R+1] first sorted rect of each row
+  const RowInfo* rows;      // [R]
   int32_t R;
   int32_t dx, dy;           // rectangle size on the canvas
 };
@@ -56,10 +67,11 @@ void launch_nhwc4_to_nchw(const float* x, int n, int h, int w, float* y, cudaStr
 // [t_lo, t_hi), whose fp32 logits [dy][dx][4] sit in slot (i % ring_cap) of `ring`): sum the covering tiles per pixel in
 // double in sorted order, softmax / floor / argmax / heat, write classes + heatmap (+ optional fp32 canvas / probs).
 // One owner thread per pixel; no canvas in memory, no atomics.
-void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int64_t y0, int64_t y1,
+void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int r_lo, int r_hi, int64_t y0, int64_t y1,
                                 const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc);
+// ([r_lo, r_hi): the tile rows that can touch canvas rows [y0, y1), found by the host)
 // K6+K7 (cls): per-tile logits [T][4] (sorted order) broadcast over rectangles, summed per pixel and finalised
-void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const FinaliseArgs& a,
+void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, int64_t y0, int64_t y1, int r_lo, int r_hi, const FinaliseArgs& a,
                                 cudaStream_t s, LaunchCounter* lc);
 // coverage counts from the rect index
 void launch_counts(const RectIndex& ri, int T, int64_t W2, int64_t own0, int64_t own1, int32_t* counts,
