@@ -395,7 +395,7 @@ class Runner:
         if self._shm_path is not None:
             try:
                 self._shm = torch.from_file(self._shm_path, shared=True, size=nbytes, dtype=torch.uint8)
-                ok = 1 if int(torch.cuda.cudart().cudaHostRegister(self._shm.data_ptr(), nbytes, 0)) == 0 else 0
+                ok = 1 if self.capi.host_register(self._shm.data_ptr(), nbytes) else 0
             except Exception:
                 ok = 0
         flag = torch.tensor([ok], device="cuda")
@@ -406,7 +406,7 @@ class Runner:
             self.host_out = {"classes": full[0, self.own0:self.own1], "heatmap": full[1, self.own0:self.own1]}
             return
         if self._shm is not None and ok:
-            torch.cuda.cudart().cudaHostUnregister(self._shm.data_ptr())
+            self.capi.host_unregister(self._shm.data_ptr(), nbytes)
         self._shm = None
         dist.barrier()
         if self.rank == 0 and self._shm_path and os.path.exists(self._shm_path):
@@ -419,7 +419,7 @@ class Runner:
     def release_host(self):
         if self.world > 1 and getattr(self, "_shm", None) is not None:
             import torch.distributed as dist
-            self.torch.cuda.cudart().cudaHostUnregister(self._shm.data_ptr())
+            self.capi.host_unregister(self._shm.data_ptr(), 2 * self.ih * self.iw)
             del self.host_out, self._shm
             dist.barrier()
             if self.rank == 0:

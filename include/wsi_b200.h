@@ -145,6 +145,11 @@ WSI_API int wsi_ipc_open(wsi_ctx* ctx, const uint8_t* handle /*[64]*/, void** de
 WSI_API int wsi_ipc_close(wsi_ctx* ctx, void* dev_ptr);      /* on the ranks that opened it */
 WSI_API int wsi_ipc_free(wsi_ctx* ctx, void* dev_ptr);       /* on the rank that allocated it, after the others closed */
 
+/* Page-lock / release caller-owned host memory (a result buffer shared between the ranks' processes): wsi_run_slide's
+ * strip-wise downloads into it are then asynchronous DMA.  WSI_ERR_NOMEM when the platform refuses (nothing stays locked). */
+WSI_API int wsi_host_register(void* ptr, int64_t bytes);
+WSI_API int wsi_host_unregister(void* ptr, int64_t bytes);
+
 /* ---- the hot path (replaces the loop of predict_tumorbed, utils/eval.py:190-228) ------------- */
 WSI_API int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,
                   int head, const wsi_out_desc* out, void* stream);

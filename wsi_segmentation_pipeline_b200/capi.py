@@ -33,7 +33,7 @@ SYMBOLS = (
     "wsi_find_nuclei", "wsi_plan_tiles_gpu", "wsi_forward_patches",
     "wsi_forward_batch_tta", "wsi_debug_umma_shift", "wsi_check", "wsi_debug_conv_f32", "wsi_op_stats",
     "wsi_ipc_alloc", "wsi_ipc_open", "wsi_ipc_close", "wsi_ipc_free",
-    "wsi_morph", "wsi_tumor_bed", "wsi_overlay", "wsi_hull_rows",
+    "wsi_morph", "wsi_tumor_bed", "wsi_overlay", "wsi_hull_rows", "wsi_host_register", "wsi_host_unregister",
 )
 
 
@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
         "wsi_debug_conv_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
         "wsi_check": (C.c_int, [vp, vp]),
+        "wsi_host_register": (C.c_int, [vp, i64]),
+        "wsi_host_unregister": (C.c_int, [vp, i64]),
         "wsi_morph": (C.c_int, [vp, vp, i64, i64, C.c_int, C.c_int, vp, C.c_int, vp]),
         "wsi_tumor_bed": (C.c_int, [vp, vp, i64, i64, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(i64), C.c_int, vp]),
         "wsi_overlay": (C.c_int, [vp, vp, vp, i64, i64, C.c_int, vp, vp, vp, vp, C.c_int, vp]),
@@ -176,6 +178,15 @@ def band_tiles(xy: np.ndarray, ph, m, own0, own1) -> np.ndarray:
     finally:
         L.wsi_free(idx)
     return out
+
+
+def host_register(ptr: int, nbytes: int) -> bool:
+    """Page-lock caller-owned host memory; False when the platform refuses (nothing stays locked)."""
+    return lib().wsi_host_register(C.c_void_p(ptr), int(nbytes)) == WSI_OK
+
+
+def host_unregister(ptr: int, nbytes: int):
+    lib().wsi_host_unregister(C.c_void_p(ptr), int(nbytes))
 
 
 def hull_rows(xmin: np.ndarray, xmax: np.ndarray):

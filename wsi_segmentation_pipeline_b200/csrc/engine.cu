@@ -1479,6 +1479,36 @@ int wsi_ipc_free(wsi_ctx* ctx, void* dev_ptr) {
   WSI_API_END(ctx)
 }
 
+// Page-lock caller-owned host memory (e.g. a POSIX-shared result buffer) so that copies to / from it are asynchronous DMA.
+// Registers in <= 1 GiB pieces; on failure everything registered so far is released, the CUDA error state is cleared and
+// WSI_ERR_NOMEM is returned (the caller falls back to pageable or private pinned memory).
+int wsi_host_register(void* ptr, int64_t bytes) {
+  wsi_ctx* none = nullptr;
+  WSI_API_BEGIN
+  WSI_REQUIRE(ptr && bytes > 0, WSI_ERR_INVALID, "bad argument");
+  const int64_t piece = 1LL << 30;
+  for (int64_t off = 0; off < bytes; off += piece) {
+    cudaError_t e = cudaHostRegister(static_cast<char*>(ptr) + off, (size_t)std::min(piece, bytes - off), cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int64_t o2 = 0; o2 < off; o2 += piece) cudaHostUnregister(static_cast<char*>(ptr) + o2);
+      cudaGetLastError();
+      WSI_THROW(WSI_ERR_NOMEM, "cudaHostRegister failed after %lld bytes: %s", (long long)off, cudaGetErrorString(e));
+    }
+  }
+  WSI_API_END(none)
+}
+
+int wsi_host_unregister(void* ptr, int64_t bytes) {
+  wsi_ctx* none = nullptr;
+  WSI_API_BEGIN
+  WSI_REQUIRE(ptr && bytes > 0, WSI_ERR_INVALID, "bad argument");
+  const int64_t piece = 1LL << 30;
+  for (int64_t off = 0; off < bytes; off += piece) cudaHostUnregister(static_cast<char*>(ptr) + off);
+  cudaGetLastError();
+  WSI_API_END(none)
+}
+
 int wsi_check(wsi_ctx* ctx, void* stream) {
   WSI_API_BEGIN
   WSI_REQUIRE(ctx, WSI_ERR_INVALID, "ctx is NULL");
