@@ -63,5 +63,69 @@ def full(path, note=""):
         print(",".join(('"' + r[c] + '"') if c == cols[0] else r[c] for c in cols))
 
 
+
+
+def batch(path, bench_json=None):
+    """profiles/rNN_kernels.csv: one row per kernel of a whole batch (ncu --metrics ... --csv log of tools/gpu_ncu_r2.sh),
+    joined with bench.py's live `kernels` table (CUDA-event time, algorithmic FLOPs / bytes) when given."""
+    import json
+    rows = [l for l in open(path) if not l.startswith("==")]
+    rd = csv.DictReader(io.StringIO("".join(rows)))
+    per = {}
+    order = []
+    for r in rd:
+        key = (r["ID"], short(r["Kernel Name"]))
+        if key not in per:
+            per[key] = {}
+            order.append(key)
+        per[key][r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) if r["Metric Value"] not in ("", "n/a") else 0.0
+        per[key]["unit:" + r["Metric Name"]] = r.get("Metric Unit", "")
+    agg = defaultdict(lambda: defaultdict(float))
+    for key in order:
+        m = per[key]
+        k = key[1]
+        t = m.get("gpu__time_duration.sum", 0.0)
+        u = m.get("unit:gpu__time_duration.sum", "ns")
+        us = t / 1e3 if u in ("ns", "nsecond") else (t if u in ("us", "usecond") else t * 1e3)
+
+        def byt(name):
+            v, un = m.get(name, 0.0), m.get("unit:" + name, "byte")
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(un, 1)
+        a = agg[k]
+        a["n"] += 1
+        a["us"] += us
+        a["tensor_x_us"] += m.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) * us
+        a["dram"] += byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum")
+        a["dram_pct_x_us"] += m.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 0.0) * us
+        a["regs"] = m.get("launch__registers_per_thread", 0.0)
+    total = sum(a["us"] for a in agg.values())
+    live = {}
+    if bench_json:
+        d = json.load(open(bench_json))
+        for row in (d.get("roofline", {}).get("kernels") or []):
+            live.setdefault(row["kernel"], []).append(row)
+    print(f"# one batch of 74 tiles of 512^2 (97 launches) inside: {CMD} --no-library --no-kernel-table ; ncu --metrics ... --clock-control none")
+    print("# ncu times are cold-cache and serialised (compare SHARES); live_* columns come from bench.py's traced step (CUDA events, warm)")
+    print("kernel,launches,ncu_us_total,share_pct,tensor_pipe_active_pct,dram_bytes_per_launch_MB,dram_throughput_pct,registers,live_ms_sum,live_alg_tflops,live_alg_gbs")
+    conv_t = conv_tx = 0.0
+    for k in sorted(agg, key=lambda k: -agg[k]["us"]):
+        a = agg[k]
+        tens = a["tensor_x_us"] / a["us"] if a["us"] else 0.0
+        if "conv_" in k or "stem" in k:
+            conv_t += a["us"]
+            conv_tx += a["tensor_x_us"]
+        lv = None
+        for name, rws in live.items():
+            base = name.split("<")[0]
+            if base in k and (("<" not in name) or all(tok in k.replace(" ", "") for tok in re.findall(r"\d+", name)[:1])):
+                lv = rws
+        lms = sum(r["ms"] for r in lv) if lv else ""
+        ltf = (sum(r["tflops"] * r["ms"] for r in lv) / max(sum(r["ms"] for r in lv), 1e-9)) if lv else ""
+        lgb = (sum(r["gbs"] * r["ms"] for r in lv) / max(sum(r["ms"] for r in lv), 1e-9)) if lv else ""
+        fmt = lambda v: f"{v:.1f}" if isinstance(v, float) else str(v)
+        print(f"\"{k}\",{int(a['n'])},{a['us']:.1f},{100 * a['us'] / total:.1f},{tens:.1f},{a['dram'] / a['n'] / 1e6:.1f},{a['dram_pct_x_us'] / a['us']:.1f},{int(a['regs'])},{fmt(lms)},{fmt(ltf)},{fmt(lgb)}")
+    print(f"# time-weighted tensor-pipe activity over the conv kernels (stem included): {conv_tx / max(conv_t, 1e-9):.1f} % of peak sustained active; conv kernels = {100 * conv_t / total:.1f} % of the batch")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "full": full, "batch": batch}[sys.argv[1]](*sys.argv[2:])

@@ -34,33 +34,53 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
     }
   }
   __syncthreads();
-  // persistent blocks over (tile, row) pairs: the table is built once per block, not once per 512 pixels
+  // Persistent blocks; ONE WARP per (tile, row) job.  (Round 1 gave a whole 256-thread block one row of 512 pixels: two
+  // pixels per thread per job, so the per-job index arithmetic — a 64-bit division, the tile lookup, 64-bit addressing —
+  // dominated: ncu counted ~93 instructions per pixel at 69 % issue utilisation.  A lane now carries pw / 32 pixels per
+  // job and walks jobs without dividing.)
   const int64_t pitch = (int64_t)(pw + 8) * 4;
-  for (int64_t job = blockIdx.x; job < (int64_t)n_tiles * ph; job += gridDim.x) {
-    const int t = (int)(job / ph), r = (int)(job - (int64_t)t * ph);
-    const int x0 = tiles_xy[2 * t], y0 = tiles_xy[2 * t + 1];
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int64_t n_jobs = (int64_t)n_tiles * ph;
+  int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int t = (int)(job / ph), r = (int)(job - (int64_t)t * ph);
+  const int dt = warps_total / ph, dr = warps_total - dt * ph;          // job += warps_total  ==  (t, r) += (dt, dr) with carry
+  for (; job < n_jobs; job += warps_total) {
+    const int x0 = __ldg(tiles_xy + 2 * t), y0 = __ldg(tiles_xy + 2 * t + 1);
     const uint8_t* src = rgb + (int64_t)(y0 + r - row0) * row_stride + (int64_t)x0 * 3;
-    bf16* dst = padded + ((int64_t)t * (ph + 6) + (r + 3)) * pitch + 3 * 4;
-    for (int x = threadIdx.x; x < pw; x += blockDim.x) {
-      const uint8_t c0 = __ldg(src + 3 * x), c1 = __ldg(src + 3 * x + 1), c2 = __ldg(src + 3 * x + 2);
-      if (padded) {
+    bf16* dst = padded ? padded + ((int64_t)t * (ph + 6) + (r + 3)) * pitch + 3 * 4 : nullptr;
+    float* q0 = norm_out ? norm_out + (int64_t)t * 3 * ph * pw + (int64_t)r * pw : nullptr;
+    for (int xb = 0; xb < pw; xb += 128) {                                 // 4 pixels per lane in flight
+      uint8_t c[4][3];
 #pragma unroll
-        for (int j = 0; j < PLANES; ++j) {
-          const uint16_t v0 = s_lut[j][c0], v1 = s_lut[j][256 + c1], v2 = s_lut[j][512 + c2];
-          uint2 o;
-          o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
-          o.y = (uint32_t)v2;
-          *reinterpret_cast<uint2*>(dst + (int64_t)j * plane_stride + 4 * x) = o;
+      for (int k = 0; k < 4; ++k) {
+        const int x = xb + 32 * k + lane;
+        if (x < pw) { c[k][0] = __ldg(src + 3 * x); c[k][1] = __ldg(src + 3 * x + 1); c[k][2] = __ldg(src + 3 * x + 2); }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = xb + 32 * k + lane;
+        if (x >= pw) continue;
+        if (dst) {
+#pragma unroll
+          for (int j = 0; j < PLANES; ++j) {
+            const uint16_t v0 = s_lut[j][c[k][0]], v1 = s_lut[j][256 + c[k][1]], v2 = s_lut[j][512 + c[k][2]];
+            uint2 o;
+            o.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
+            o.y = (uint32_t)v2;
+            *reinterpret_cast<uint2*>(dst + (int64_t)j * plane_stride + 4 * x) = o;
+          }
+        }
+        if (q0) {
+          const int64_t plane = (int64_t)ph * pw;
+          q0[x] = s_f32[c[k][0]];
+          q0[plane + x] = s_f32[256 + c[k][1]];
+          q0[2 * plane + x] = s_f32[512 + c[k][2]];
         }
       }
-      if (norm_out) {
-        const int64_t plane = (int64_t)ph * pw;
-        float* q = norm_out + (int64_t)t * 3 * plane + (int64_t)r * pw + x;
-        q[0] = s_f32[c0];
-        q[plane] = s_f32[256 + c1];
-        q[2 * plane] = s_f32[512 + c2];
-      }
     }
+    t += dt; r += dr;
+    if (r >= ph) { r -= ph; ++t; }
   }
 }
 
@@ -68,7 +88,8 @@ void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const i
                    int pw, const float* lut_dev, bf16* padded, float* norm_out, cudaStream_t s, LaunchCounter* lc, int planes,
                    int64_t plane_stride) {
   if (n <= 0) return;
-  const unsigned grid = (unsigned)std::min<int64_t>((int64_t)n * ph, 148 * 8);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div((int64_t)n * ph, 8), 148 * 8);
+  // (a per-lane, bank-conflict-free copy of the table — 96 KB, 2 blocks per SM — was slower: 7.5 vs 6.1 ms per 8 280 tiles)
   if (planes == 3) gather_kernel<3><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride);
   else gather_kernel<1><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride);
   CUDA_CHECK(cudaGetLastError());
