@@ -391,23 +391,30 @@ class Runner:
             except OSError:
                 name = [None]
         dist.broadcast_object_list(name, src=0)
-        self._shm_path, self._shm, ok = name[0], None, 0
+        self._shm_path, self._shm, ok, self._regs = name[0], None, 0, []
         if self._shm_path is not None:
             try:
                 self._shm = torch.from_file(self._shm_path, shared=True, size=nbytes, dtype=torch.uint8)
-                ok = 1 if self.capi.host_register(self._shm.data_ptr(), nbytes) else 0
+                full = self._shm.view(2, self.ih, self.iw)
+                views = {"classes": full[0, self.own0:self.own1], "heatmap": full[1, self.own0:self.own1]}
+                ok = 1
+                for v in views.values():           # every rank page-locks ITS rows of both planes (one registration each)
+                    if self.capi.host_register(v.data_ptr(), v.numel()):
+                        self._regs.append(v.data_ptr())
+                    else:
+                        ok = 0
+                        break
             except Exception:
                 ok = 0
         flag = torch.tensor([ok], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         self.shared_host = bool(int(flag.item()))
         if self.shared_host:
-            full = self._shm.view(2, self.ih, self.iw)
-            self.host_out = {"classes": full[0, self.own0:self.own1], "heatmap": full[1, self.own0:self.own1]}
+            self.host_out = views
             return
-        if self._shm is not None and ok:
-            self.capi.host_unregister(self._shm.data_ptr(), nbytes)
-        self._shm = None
+        for ptr in self._regs:
+            self.capi.host_unregister(ptr)
+        self._regs, self._shm = [], None
         dist.barrier()
         if self.rank == 0 and self._shm_path and os.path.exists(self._shm_path):
             os.unlink(self._shm_path)
@@ -419,7 +426,8 @@ class Runner:
     def release_host(self):
         if self.world > 1 and getattr(self, "_shm", None) is not None:
             import torch.distributed as dist
-            self.capi.host_unregister(self._shm.data_ptr(), 2 * self.ih * self.iw)
+            for ptr in self._regs:
+                self.capi.host_unregister(ptr)
             del self.host_out, self._shm
             dist.barrier()
             if self.rank == 0:
@@ -573,19 +581,31 @@ def main():
             args.no_e2e = True
             e2e = {"skipped": f"host buffers of {need / 1e9:.1f} GB exceed 40 % of the available host memory"}
     if not args.no_e2e:
-        ctx.set_option("stage_timing", 0)
-        R.prepare_host()
-        R.step_host()
-        e_ms = timed(R.step_host, args.steps) / args.steps
-        h2d = torch.tensor([int(R.host_raster.numel())], device="cuda", dtype=torch.int64)
+        # a failure here (host memory, shared mapping) must not lose the device-resident line: every rank takes the same
+        # decision, the error is reported in the line
+        err = None
+        try:
+            ctx.set_option("stage_timing", 0)
+            R.prepare_host()
+            R.step_host()
+        except Exception as ex:       # noqa: BLE001
+            err = repr(ex)[:300]
+        bad = torch.tensor([1 if err else 0], device="cuda")
         if n_gpus > 1:
-            dist.all_reduce(h2d)
-        e2e = {"value": mpx / (e_ms * 1e-3), "unit": "Mpx/s", "ms_per_step": e_ms, "steps": args.steps,
-               "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(2 * ih * iw),
-               "how": "pinned band raster -> wsi_run_slide(WSI_MEM_HOST) -> u8 mask + heatmap in host memory"
-                      + ("" if n_gpus == 1 else ("; every rank writes its rows into one POSIX-shared, page-locked host buffer over its own PCIe link"
-                                                 if R.shared_host else "; every rank keeps its rows in its own pinned host buffer (/dev/shm too small for one shared result)"))}
-        R.release_host()
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            e2e = {"error": err or "another rank failed to prepare its host buffers"}
+        else:
+            e_ms = timed(R.step_host, args.steps) / args.steps
+            h2d = torch.tensor([int(R.host_raster.numel())], device="cuda", dtype=torch.int64)
+            if n_gpus > 1:
+                dist.all_reduce(h2d)
+            e2e = {"value": mpx / (e_ms * 1e-3), "unit": "Mpx/s", "ms_per_step": e_ms, "steps": args.steps,
+                   "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(2 * ih * iw),
+                   "how": "pinned band raster -> wsi_run_slide(WSI_MEM_HOST) -> u8 mask + heatmap in host memory"
+                          + ("" if n_gpus == 1 else ("; every rank writes its rows into one POSIX-shared, page-locked host buffer over its own PCIe link"
+                                                     if R.shared_host else "; every rank keeps its rows in its own pinned host buffer (a shared result could not be page-locked)"))}
+            R.release_host()
 
     if rank == 0:
         conv = stats["conv"]

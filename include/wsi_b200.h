@@ -148,7 +148,7 @@ WSI_API int wsi_ipc_free(wsi_ctx* ctx, void* dev_ptr);       /* on the rank that
 /* Page-lock / release caller-owned host memory (a result buffer shared between the ranks' processes): wsi_run_slide's
  * strip-wise downloads into it are then asynchronous DMA.  WSI_ERR_NOMEM when the platform refuses (nothing stays locked). */
 WSI_API int wsi_host_register(void* ptr, int64_t bytes);
-WSI_API int wsi_host_unregister(void* ptr, int64_t bytes);
+WSI_API int wsi_host_unregister(void* ptr);
 
 /* ---- the hot path (replaces the loop of predict_tumorbed, utils/eval.py:190-228) ------------- */
 WSI_API int wsi_run_slide(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* tiles_xy, int64_t n_tiles,

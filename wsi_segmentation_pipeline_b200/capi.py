@@ -97,7 +97,7 @@ def lib() -> C.CDLL:
                                          vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
         "wsi_check": (C.c_int, [vp, vp]),
         "wsi_host_register": (C.c_int, [vp, i64]),
-        "wsi_host_unregister": (C.c_int, [vp, i64]),
+        "wsi_host_unregister": (C.c_int, [vp]),
         "wsi_morph": (C.c_int, [vp, vp, i64, i64, C.c_int, C.c_int, vp, C.c_int, vp]),
         "wsi_tumor_bed": (C.c_int, [vp, vp, i64, i64, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(i64), C.c_int, vp]),
         "wsi_overlay": (C.c_int, [vp, vp, vp, i64, i64, C.c_int, vp, vp, vp, vp, C.c_int, vp]),
@@ -185,8 +185,8 @@ def host_register(ptr: int, nbytes: int) -> bool:
     return lib().wsi_host_register(C.c_void_p(ptr), int(nbytes)) == WSI_OK
 
 
-def host_unregister(ptr: int, nbytes: int):
-    lib().wsi_host_unregister(C.c_void_p(ptr), int(nbytes))
+def host_unregister(ptr: int):
+    lib().wsi_host_unregister(C.c_void_p(ptr))
 
 
 def hull_rows(xmin: np.ndarray, xmax: np.ndarray):

@@ -73,19 +73,21 @@ inline float bf16_bits_to_f32(uint16_t b) {
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  bool owned = true;        // false: a view into another buffer (never freed here)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), owned(o.owned) { o.p = nullptr; o.bytes = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; owned = o.owned; o.p = nullptr; o.bytes = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     bytes = 0;
+    owned = true;
   }
   void alloc(size_t n) {
     if (n <= bytes && p) return;

@@ -91,6 +91,7 @@ struct wsi_ctx {
   int64_t batch_tiles = 0;
   int stage_timing = 0;
   int op_trace = 0;                // per-conv CUDA events (wsi_op_stats); set before the plan is built
+  int d5_sub = 0;                  // > 0: the last decoder level runs in sub-batches of this many tiles (its intermediate stays in L2)
   int precision = WSI_PRECISION_BF16;
   DevBuf lut;        // f32 [3][256] normalise table
   DevBuf err_flag;   // int, set by a timed-out barrier wait inside the conv kernel
@@ -223,7 +224,22 @@ struct NetPlan {
   DevBuf pooled;                 // CLS head: the pooled 512-vectors next to the logits (multi-patch ensemble head reads them)
   int n1 = 0, n2 = 0, out_dim = 0;
   Act* x4 = nullptr;
-  ConvOp* head_op = nullptr;     // SEG: the last decoder conv (fused 1x1 head); its fp32 logits output is re-pointed per batch
+  // SEG: the last decoder conv(s) (fused 1x1 head) and the tile offset of each; their fp32 logits output is re-pointed per batch
+  std::vector<std::pair<ConvOp*, int>> head_ops;
+  void set_logits_base(float* base) {
+    for (auto& h : head_ops) h.first->set_head_out(base + (size_t)h.second * ph * pw * 4);
+  }
+  // a non-owning view of images [n0, n0 + nb) of an activation
+  Act* new_view(Act* base, int n0, int nb) {
+    acts.emplace_back(new Act());
+    Act* a = acts.back().get();
+    a->N = nb; a->H = base->H; a->W = base->W; a->C = base->C; a->layout = base->layout; a->planes = base->planes;
+    const size_t img = base->bytes() / (size_t)base->N;
+    a->buf.p = static_cast<char*>(base->buf.p) + (size_t)n0 * img;
+    a->buf.bytes = (size_t)nb * img;
+    a->buf.owned = false;
+    return a;
+  }
   double conv_flops = 0, stem_flops = 0;   // per batch of `cap` tiles (algorithmic: 2*MAC, no padding)
   std::vector<Act*> feats;                 // [x4, x3, x2, x1, x0]
   // WSI_CONV_TRACE=1: per-op device time (dev tool; events around every conv launch)
@@ -406,6 +422,30 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
       const size_t ia = 2 * (size_t)(i - 1), ib = ia + 1;
       const bool a_planar = plan[ib].row;      // consumer is a row kernel; every producer (row kernels, TMA kernel) can write planar
       const bool b_planar = (ib + 1 < plan.size()) && plan[ib].row && plan[ib + 1].row;
+      const int sub = (i == 5 && !precise && c->d5_sub > 0 && c->d5_sub < cap) ? c->d5_sub : 0;
+      if (sub > 0) {
+        // Last level in sub-batches: d5a writes `sub` tiles of the 16-channel full-resolution intermediate (8.4 MB per 512^2
+        // tile) into ONE small buffer and d5b consumes it at once, sub-batch after sub-batch — the intermediate is
+        // overwritten in L2 before it is ever written back to HBM.
+        const HostTensor& wa = conv_weight(c, q + "0.block.0.weight", co, ci, 3);
+        const Folded fa = fold_bn(c, q + "0.block.1", co);
+        const HostTensor& wb = conv_weight(c, q + "1.block.0.weight", co, co, 3);
+        const Folded fb_ = fold_bn(c, q + "1.block.1", co);
+        const HostTensor& fw = conv_weight(c, "decoder.final_conv.weight", 4, 16, 1);
+        const HostTensor& fb = weight(c, "decoder.final_conv.bias");
+        WSI_REQUIRE(fb.numel() == 4, WSI_ERR_NOMODEL, "decoder.final_conv.bias must have 4 entries");
+        Act* a_sub = new_act(sub, 2 * x->H, 2 * x->W, co, a_planar ? LAYOUT_PLANAR : LAYOUT_NHWC);
+        for (int n0 = 0; n0 < cap; n0 += sub) {
+          const int nb = std::min(sub, cap - n0);
+          Act* xv = new_view(x, n0, nb);
+          Act* av = new_view(a_sub, 0, nb);
+          add_conv({ConvInputPart{xv->view(), true}}, plan[ia].sp, wa.data.data(), &fa, nullptr, av);
+          add_conv({ConvInputPart{av->view(), false}}, plan[ib].sp, wb.data.data(), &fb_, nullptr, nullptr, fw.data.data(), fb.data.data(),
+                   logits.as<float>() + (size_t)n0 * ph * pw * 4);
+          head_ops.push_back({ops.back().get(), n0});
+        }
+        continue;
+      }
       Act* a = new_act(cap, 2 * x->H, 2 * x->W, co, a_planar ? LAYOUT_PLANAR : LAYOUT_NHWC);
       {
         const HostTensor& w = conv_weight(c, q + "0.block.0.weight", co, ci, 3);
@@ -426,7 +466,7 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
         WSI_REQUIRE(fb.numel() == 4, WSI_ERR_NOMODEL, "decoder.final_conv.bias must have 4 entries");
         add_conv({ConvInputPart{a->view(), false}}, plan[ib].sp, w.data.data(), &f, nullptr, nullptr, fw.data.data(), fb.data.data(),
                  logits.as<float>());
-        head_op = ops.back().get();
+        head_ops.push_back({ops.back().get(), 0});
       }
     }
     out_dim = 4;
@@ -873,7 +913,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
                     nullptr, s, &c->lc, plan->in_planes(), plan->in_plane_stride());
     }
     if (head == WSI_HEAD_SEG) {
-      plan->head_op->set_head_out(c->logit_ring.as<float>() + (t0 % ring_cap) * tile_elems);
+      plan->set_logits_base(c->logit_ring.as<float>() + (t0 % ring_cap) * tile_elems);
       plan->run(c, s);
       pending_logit_bytes += (double)n * tile_px * 16.0;
       const int64_t e = t0 + n, y_ready = ready_after(e);
@@ -935,7 +975,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
 
 // one batch through the network: x f32 NCHW (normalised) or tiles cut from a raster
 static void forward_common(wsi_ctx* c, NetPlan* plan, int n, int head, float* out, int mem, cudaStream_t s) {
-  if (plan->head_op) plan->head_op->set_head_out(plan->logits.as<float>());   // wsi_run_slide points it into its logit ring
+  plan->set_logits_base(plan->logits.as<float>());                            // wsi_run_slide points them into its logit ring
   plan->run(c, s);
   const int ph = plan->ph, pw = plan->pw;
   const size_t out_elems = (head == WSI_HEAD_SEG) ? (size_t)n * 4 * ph * pw : (size_t)n * plan->out_dim;
@@ -1032,6 +1072,7 @@ int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value) {
   if (k == "batch_tiles") { WSI_REQUIRE(value >= 0 && value <= 4096, WSI_ERR_INVALID, "batch_tiles out of range"); ctx->batch_tiles = value; }
   else if (k == "stage_timing") ctx->stage_timing = value ? 1 : 0;
   else if (k == "op_trace") { ctx->op_trace = value ? 1 : 0; ctx->plan.reset(); }
+  else if (k == "d5_sub") { WSI_REQUIRE(value >= 0 && value <= 4096, WSI_ERR_INVALID, "d5_sub out of range"); ctx->d5_sub = (int)value; ctx->plan.reset(); }
   else if (k == "precision") {
     WSI_REQUIRE(value == WSI_PRECISION_BF16 || value == WSI_PRECISION_FP32, WSI_ERR_INVALID, "precision must be WSI_PRECISION_BF16 (0) or WSI_PRECISION_FP32 (1)");
     ctx->precision = (int)value;
@@ -1479,32 +1520,26 @@ int wsi_ipc_free(wsi_ctx* ctx, void* dev_ptr) {
   WSI_API_END(ctx)
 }
 
-// Page-lock caller-owned host memory (e.g. a POSIX-shared result buffer) so that copies to / from it are asynchronous DMA.
-// Registers in <= 1 GiB pieces; on failure everything registered so far is released, the CUDA error state is cleared and
-// WSI_ERR_NOMEM is returned (the caller falls back to pageable or private pinned memory).
+// Page-lock caller-owned host memory (e.g. this rank's rows of a POSIX-shared result buffer) so that copies to / from it are
+// asynchronous DMA.  One registration for the whole range (a copy may not span two registrations).  On failure the CUDA
+// error state is cleared and WSI_ERR_NOMEM is returned: the caller falls back to pageable or private pinned memory.
 int wsi_host_register(void* ptr, int64_t bytes) {
   wsi_ctx* none = nullptr;
   WSI_API_BEGIN
   WSI_REQUIRE(ptr && bytes > 0, WSI_ERR_INVALID, "bad argument");
-  const int64_t piece = 1LL << 30;
-  for (int64_t off = 0; off < bytes; off += piece) {
-    cudaError_t e = cudaHostRegister(static_cast<char*>(ptr) + off, (size_t)std::min(piece, bytes - off), cudaHostRegisterPortable);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      for (int64_t o2 = 0; o2 < off; o2 += piece) cudaHostUnregister(static_cast<char*>(ptr) + o2);
-      cudaGetLastError();
-      WSI_THROW(WSI_ERR_NOMEM, "cudaHostRegister failed after %lld bytes: %s", (long long)off, cudaGetErrorString(e));
-    }
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    WSI_THROW(WSI_ERR_NOMEM, "cudaHostRegister(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e));
   }
   WSI_API_END(none)
 }
 
-int wsi_host_unregister(void* ptr, int64_t bytes) {
+int wsi_host_unregister(void* ptr) {
   wsi_ctx* none = nullptr;
   WSI_API_BEGIN
-  WSI_REQUIRE(ptr && bytes > 0, WSI_ERR_INVALID, "bad argument");
-  const int64_t piece = 1LL << 30;
-  for (int64_t off = 0; off < bytes; off += piece) cudaHostUnregister(static_cast<char*>(ptr) + off);
+  WSI_REQUIRE(ptr, WSI_ERR_INVALID, "bad argument");
+  cudaHostUnregister(ptr);
   cudaGetLastError();
   WSI_API_END(none)
 }
