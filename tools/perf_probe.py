@@ -23,9 +23,6 @@ def main():
     head = capi.HEAD_SEG if arch == "unet" else capi.HEAD_CLS
     ctx.set_option("stage_timing", 1)
     ctx.set_option("batch_tiles", batch)
-    import os
-    if os.environ.get("WSI_D5_SUB"):
-        ctx.set_option("d5_sub", int(os.environ["WSI_D5_SUB"]))
     rgb = ctx.synth_slide(size, size, 1234)
     tiles = capi.plan_tiles(size, size, tile, tile, stride, stride)
     sl = ctx.slide_desc(rgb, size, size, tile, tile)

@@ -91,7 +91,6 @@ struct wsi_ctx {
   int64_t batch_tiles = 0;
   int stage_timing = 0;
   int op_trace = 0;                // per-conv CUDA events (wsi_op_stats); set before the plan is built
-  int d5_sub = 0;                  // > 0: the last decoder level runs in sub-batches of this many tiles (its intermediate stays in L2)
   int precision = WSI_PRECISION_BF16;
   DevBuf lut;        // f32 [3][256] normalise table
   DevBuf err_flag;   // int, set by a timed-out barrier wait inside the conv kernel
@@ -228,17 +227,6 @@ struct NetPlan {
   std::vector<std::pair<ConvOp*, int>> head_ops;
   void set_logits_base(float* base) {
     for (auto& h : head_ops) h.first->set_head_out(base + (size_t)h.second * ph * pw * 4);
-  }
-  // a non-owning view of images [n0, n0 + nb) of an activation
-  Act* new_view(Act* base, int n0, int nb) {
-    acts.emplace_back(new Act());
-    Act* a = acts.back().get();
-    a->N = nb; a->H = base->H; a->W = base->W; a->C = base->C; a->layout = base->layout; a->planes = base->planes;
-    const size_t img = base->bytes() / (size_t)base->N;
-    a->buf.p = static_cast<char*>(base->buf.p) + (size_t)n0 * img;
-    a->buf.bytes = (size_t)nb * img;
-    a->buf.owned = false;
-    return a;
   }
   double conv_flops = 0, stem_flops = 0;   // per batch of `cap` tiles (algorithmic: 2*MAC, no padding)
   std::vector<Act*> feats;                 // [x4, x3, x2, x1, x0]
@@ -422,30 +410,6 @@ void NetPlan::build(wsi_ctx* c, int arch_, int head_, int cap_, int ph_, int pw_
       const size_t ia = 2 * (size_t)(i - 1), ib = ia + 1;
       const bool a_planar = plan[ib].row;      // consumer is a row kernel; every producer (row kernels, TMA kernel) can write planar
       const bool b_planar = (ib + 1 < plan.size()) && plan[ib].row && plan[ib + 1].row;
-      const int sub = (i == 5 && !precise && c->d5_sub > 0 && c->d5_sub < cap) ? c->d5_sub : 0;
-      if (sub > 0) {
-        // Last level in sub-batches: d5a writes `sub` tiles of the 16-channel full-resolution intermediate (8.4 MB per 512^2
-        // tile) into ONE small buffer and d5b consumes it at once, sub-batch after sub-batch — the intermediate is
-        // overwritten in L2 before it is ever written back to HBM.
-        const HostTensor& wa = conv_weight(c, q + "0.block.0.weight", co, ci, 3);
-        const Folded fa = fold_bn(c, q + "0.block.1", co);
-        const HostTensor& wb = conv_weight(c, q + "1.block.0.weight", co, co, 3);
-        const Folded fb_ = fold_bn(c, q + "1.block.1", co);
-        const HostTensor& fw = conv_weight(c, "decoder.final_conv.weight", 4, 16, 1);
-        const HostTensor& fb = weight(c, "decoder.final_conv.bias");
-        WSI_REQUIRE(fb.numel() == 4, WSI_ERR_NOMODEL, "decoder.final_conv.bias must have 4 entries");
-        Act* a_sub = new_act(sub, 2 * x->H, 2 * x->W, co, a_planar ? LAYOUT_PLANAR : LAYOUT_NHWC);
-        for (int n0 = 0; n0 < cap; n0 += sub) {
-          const int nb = std::min(sub, cap - n0);
-          Act* xv = new_view(x, n0, nb);
-          Act* av = new_view(a_sub, 0, nb);
-          add_conv({ConvInputPart{xv->view(), true}}, plan[ia].sp, wa.data.data(), &fa, nullptr, av);
-          add_conv({ConvInputPart{av->view(), false}}, plan[ib].sp, wb.data.data(), &fb_, nullptr, nullptr, fw.data.data(), fb.data.data(),
-                   logits.as<float>() + (size_t)n0 * ph * pw * 4);
-          head_ops.push_back({ops.back().get(), n0});
-        }
-        continue;
-      }
       Act* a = new_act(cap, 2 * x->H, 2 * x->W, co, a_planar ? LAYOUT_PLANAR : LAYOUT_NHWC);
       {
         const HostTensor& w = conv_weight(c, q + "0.block.0.weight", co, ci, 3);
@@ -1072,7 +1036,6 @@ int wsi_set_option(wsi_ctx* ctx, const char* key, int64_t value) {
   if (k == "batch_tiles") { WSI_REQUIRE(value >= 0 && value <= 4096, WSI_ERR_INVALID, "batch_tiles out of range"); ctx->batch_tiles = value; }
   else if (k == "stage_timing") ctx->stage_timing = value ? 1 : 0;
   else if (k == "op_trace") { ctx->op_trace = value ? 1 : 0; ctx->plan.reset(); }
-  else if (k == "d5_sub") { WSI_REQUIRE(value >= 0 && value <= 4096, WSI_ERR_INVALID, "d5_sub out of range"); ctx->d5_sub = (int)value; ctx->plan.reset(); }
   else if (k == "precision") {
     WSI_REQUIRE(value == WSI_PRECISION_BF16 || value == WSI_PRECISION_FP32, WSI_ERR_INVALID, "precision must be WSI_PRECISION_BF16 (0) or WSI_PRECISION_FP32 (1)");
     ctx->precision = (int)value;
