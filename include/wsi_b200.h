@@ -28,6 +28,7 @@ extern "C" {
 #endif
 
 typedef struct wsi_ctx wsi_ctx;
+typedef struct wsi_tiff wsi_tiff;       /* an open TIFF / SVS file (slide ingestion) */
 
 typedef enum {
   WSI_OK = 0,
@@ -189,6 +190,24 @@ WSI_API int wsi_plan_tiles_gpu(wsi_ctx* ctx, int64_t ih, int64_t iw, int32_t ph,
  * All three buffers in `mem` memory.                                                                              */
 WSI_API int wsi_resize_argmax(wsi_ctx* ctx, const float* canvas, int64_t H, int64_t W, int64_t H2, int64_t W2,
                       uint8_t* classes, float* pred_or_null, int mem, void* stream);
+
+/* ---- slide ingestion: JPEG-compressed tiled / stripped TIFF and Aperio SVS -> raster rows in HBM -------
+ * Replaces openslide.OpenSlide(path) + read_region(...).convert('RGB') (utils/dataset.py:121,175-178; utils/eval.py:263) for
+ * rasters still on disk: a row band of one pyramid level (TIFF directory `level`) is decoded by nvJPEG on the GPU straight
+ * into the u8 [rows][W][3] device raster that wsi_run_slide / wsi_find_nuclei read.  Classic TIFF and BigTIFF, little-endian,
+ * compression 7 (JPEG) with shared JPEGTables, photometric YCbCr or RGB.  Decoded pixels may differ from libjpeg's by a
+ * level or two (IDCT / chroma upsampling are decoder-specific).  WSI_ERR_UNSUPPORTED without libnvjpeg or for other codecs. */
+WSI_API int wsi_tiff_open(const char* path, wsi_tiff** out);
+WSI_API int wsi_tiff_close(wsi_tiff* t);
+WSI_API const char* wsi_tiff_last_error(wsi_tiff* t);
+WSI_API int wsi_tiff_levels(wsi_tiff* t);                      /* number of image directories */
+WSI_API int wsi_tiff_level_info(wsi_tiff* t, int level, int64_t* W, int64_t* H, int32_t* tile_w, int32_t* tile_h, int32_t* compression,
+                        int32_t* photometric);
+/* host-only: the complete JPEG stream of tile / strip `unit` (JPEGTables spliced in); *len = its size (buf may be NULL) */
+WSI_API int wsi_tiff_unit_stream(wsi_tiff* t, int level, int64_t unit, uint8_t* buf, int64_t cap, int64_t* len);
+/* rows [row0, row0 + rows) of `level` -> rgb_dev (device, row_stride >= 3 * W bytes); returns when the rows are decoded */
+WSI_API int wsi_tiff_read_rows(wsi_ctx* ctx, wsi_tiff* t, int level, int64_t row0, int64_t rows, uint8_t* rgb_dev, int64_t row_stride,
+                       void* stream);
 
 /* ---- tumour-bed post-processing of the outputs -------------------------------------------------
  * cv2.morphologyEx / cv2.erode / cv2.dilate with an np.ones((k, k)) kernel, default anchor and border (utils/eval.py:93,96;

@@ -146,3 +146,45 @@ def test_hull_rows_matches_restated_convex_hull_image():
                 got[y, max(int(xl[y]), 0):min(int(xr[y]), W - 1) + 1] = True
         np.testing.assert_array_equal(got, O.convex_hull_image(img), err_msg=f"trial {trial} ({H}x{W})")
         assert (got | ~(img != 0)).all()                      # the hull contains the set
+
+
+def test_tiff_directory_and_jpeg_stream_splicing(tmp_path):
+    """SURVEY 8f rank 4, host half (no GPU): the TIFF / SVS directory parser and the JPEGTables splice.  Every tile / strip
+    stream the library hands to nvJPEG decodes, with libjpeg (PIL), to exactly what libtiff + libjpeg (PIL's TIFF reader)
+    decodes from the file."""
+    import io
+    from PIL import Image
+    from tiff_fixtures import write_stripped, write_tiled_pyramid
+    from wsi_segmentation_pipeline_b200 import synth
+    rgb = synth.synth_slide(300, 421, 5)
+    # (1) stripped, shared JPEGTables, photometric RGB and YCbCr (PIL + libtiff writer)
+    for ycbcr in (False, True):
+        p = str(tmp_path / f"s{int(ycbcr)}.tif")
+        write_stripped(p, rgb, ycbcr=ycbcr)
+        ts = capi.TiffSlide(p)
+        assert ts.level_count == 1 and ts.level_dimensions[0] == (421, 300)
+        lv = ts.levels[0]
+        assert lv["compression"] == 7 and lv["photometric"] == (6 if ycbcr else 2) and lv["tile_w"] == 421
+        ref = np.asarray(Image.open(p).convert("RGB"))
+        rows = []
+        for k in range(-(-300 // lv["tile_h"])):
+            # photometric RGB: libtiff labels the JPEG components 'R', 'G', 'B', which libjpeg takes unconverted
+            rows.append(np.asarray(Image.open(io.BytesIO(ts.unit_stream(0, k))).convert("RGB")))
+        got = np.concatenate(rows)[:300]
+        assert got.shape == ref.shape
+        np.testing.assert_array_equal(got, ref)                # same libjpeg, same bytes: the splice is exact
+        ts.close()
+    # (2) tiled pyramid, one directory per level (SVS-like), self-contained JPEG tiles
+    p = str(tmp_path / "pyr.tif")
+    lv0 = synth.synth_slide(500, 700, 9)
+    write_tiled_pyramid(p, [lv0, lv0[::2, ::2].copy(), lv0[::4, ::4].copy()], tile=240)
+    ts = capi.TiffSlide(p)
+    assert ts.level_count == 3 and ts.level_dimensions == ((700, 500), (350, 250), (175, 125))
+    assert ts.level_downsamples == (1.0, 2.0, 4.0) and ts.levels[0]["tile_w"] == 240 and ts.levels[0]["tile_h"] == 240
+    t4 = np.asarray(Image.open(io.BytesIO(ts.unit_stream(0, 4))).convert("RGB"))          # tile (row 1, col 1)
+    assert np.abs(t4[:240, :240].astype(int) - lv0[240:480, 240:480].astype(int)).mean() < 3.0     # lossy, but the right tile
+    with pytest.raises(capi.WsiError):
+        ts.unit_stream(0, 99)
+    ts.close()
+    with pytest.raises(capi.WsiError):
+        capi.TiffSlide(str(tmp_path / "missing.tif"))

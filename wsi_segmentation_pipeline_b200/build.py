@@ -22,7 +22,7 @@ OBJ = os.path.join(HERE, "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
-SOURCES = ["engine.cu", "conv_igemm.cu", "conv_rowtile.cu", "conv_rowstream.cu", "conv_upstream.cu", "kernels.cu", "postproc.cu", "planner.cpp"]
+SOURCES = ["engine.cu", "conv_igemm.cu", "conv_rowtile.cu", "conv_rowstream.cu", "conv_upstream.cu", "kernels.cu", "postproc.cu", "tiff_ingest.cu", "planner.cpp"]
 
 
 def _nvcc() -> str:

@@ -34,6 +34,8 @@ SYMBOLS = (
     "wsi_forward_batch_tta", "wsi_debug_umma_shift", "wsi_check", "wsi_debug_conv_f32", "wsi_op_stats",
     "wsi_ipc_alloc", "wsi_ipc_open", "wsi_ipc_close", "wsi_ipc_free",
     "wsi_morph", "wsi_tumor_bed", "wsi_overlay", "wsi_hull_rows", "wsi_host_register", "wsi_host_unregister",
+    "wsi_tiff_open", "wsi_tiff_close", "wsi_tiff_last_error", "wsi_tiff_levels", "wsi_tiff_level_info", "wsi_tiff_unit_stream",
+    "wsi_tiff_read_rows",
 )
 
 
@@ -96,6 +98,13 @@ def lib() -> C.CDLL:
         "wsi_debug_conv_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
         "wsi_check": (C.c_int, [vp, vp]),
+        "wsi_tiff_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "wsi_tiff_close": (C.c_int, [vp]),
+        "wsi_tiff_last_error": (C.c_char_p, [vp]),
+        "wsi_tiff_levels": (C.c_int, [vp]),
+        "wsi_tiff_level_info": (C.c_int, [vp, C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "wsi_tiff_unit_stream": (C.c_int, [vp, C.c_int, i64, vp, i64, C.POINTER(i64)]),
+        "wsi_tiff_read_rows": (C.c_int, [vp, vp, C.c_int, i64, i64, vp, i64, vp]),
         "wsi_host_register": (C.c_int, [vp, i64]),
         "wsi_host_unregister": (C.c_int, [vp]),
         "wsi_morph": (C.c_int, [vp, vp, i64, i64, C.c_int, C.c_int, vp, C.c_int, vp]),
@@ -644,3 +653,59 @@ def device_u8_tensor(ptr: int, shape, device: int):
     """A torch u8 view of device memory the library (or a peer process) owns."""
     import torch
     return torch.as_tensor(_DevPtr(ptr, shape), device=torch.device("cuda", device))
+
+
+class TiffSlide:
+    """An on-disk slide (JPEG-compressed TIFF / Aperio SVS) with OpenSlide's attribute names (``level_dimensions``,
+    ``level_downsamples``, ``level_count``; utils/dataset.py:121-126).  Pixels are decoded on the GPU by nvJPEG straight into a
+    device raster (``read_level``); there is no CPU decode path in this package."""
+
+    def __init__(self, path: str):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        st = self._lib.wsi_tiff_open(os.fsencode(path), C.byref(self._h))
+        if st != WSI_OK:
+            raise WsiError(st, (self._lib.wsi_last_error(None) or b"").decode("utf-8", "replace"))
+        self.path = path
+        self.level_count = int(self._lib.wsi_tiff_levels(self._h))
+        self.levels = []
+        for lv in range(self.level_count):
+            W, H = C.c_int64(), C.c_int64()
+            tw, th, comp, ph = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            self._check(self._lib.wsi_tiff_level_info(self._h, lv, C.byref(W), C.byref(H), C.byref(tw), C.byref(th), C.byref(comp), C.byref(ph)))
+            self.levels.append({"W": W.value, "H": H.value, "tile_w": tw.value, "tile_h": th.value, "compression": comp.value, "photometric": ph.value})
+        self.level_dimensions = tuple((lv["W"], lv["H"]) for lv in self.levels)
+        w0 = self.levels[0]["W"]
+        self.level_downsamples = tuple(float(w0) / lv["W"] for lv in self.levels)
+
+    def _check(self, st):
+        if st != WSI_OK:
+            raise WsiError(st, (self._lib.wsi_tiff_last_error(self._h) or b"").decode("utf-8", "replace"))
+
+    def unit_stream(self, level: int, unit: int) -> bytes:
+        """Host-only: the spliced JPEG stream of tile / strip ``unit`` (what nvJPEG is handed)."""
+        n = C.c_int64(0)
+        self._check(self._lib.wsi_tiff_unit_stream(self._h, level, unit, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(self._lib.wsi_tiff_unit_stream(self._h, level, unit, buf, n.value, C.byref(n)))
+        return bytes(buf.raw[:n.value])
+
+    def read_level(self, ctx: "Context", level: int, row0: int = 0, rows: Optional[int] = None, stream=None):
+        """Rows [row0, row0 + rows) of ``level`` as a CUDA u8 tensor [rows, W, 3] (nvJPEG on ``ctx``'s device)."""
+        import torch
+        W, H = self.level_dimensions[level]
+        rows = H - row0 if rows is None else rows
+        out = torch.empty((rows, W, 3), dtype=torch.uint8, device=torch.device("cuda", ctx.device))
+        self._check(self._lib.wsi_tiff_read_rows(ctx._h, self._h, level, row0, rows, C.c_void_p(out.data_ptr()), 3 * W, _stream_ptr(stream)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.wsi_tiff_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1618,6 +1618,11 @@ int wsi_stage_reset(wsi_ctx* ctx) {
 
 }  // extern "C"
 
+namespace wsi {
+int ctx_device(const wsi_ctx* c) { return c->device; }
+LaunchCounter* ctx_launch_counter(wsi_ctx* c) { return &c->lc; }
+}  // namespace wsi
+
 // ---- tumour-bed post-processing ---------------------------------------------------------------
 namespace wsi {
 

@@ -61,8 +61,13 @@ class ArraySlide:
         return Image.fromarray(out, "RGBA")
 
 
-def _level_raster(scan, level: int) -> np.ndarray:
-    """Scan-level raster u8 [ih, iw, 3] of an OpenSlide-like object."""
+def _level_raster(scan, level: int, engine=None):
+    """Scan-level raster u8 [ih, iw, 3] of an OpenSlide-like object (numpy), or — for an on-disk ``capi.TiffSlide`` — a
+    CUDA tensor decoded by nvJPEG straight into HBM (``wsi_tiff_read_rows``; needs ``engine``)."""
+    if isinstance(scan, capi.TiffSlide):
+        if engine is None:
+            raise RuntimeError("a TiffSlide is decoded on the GPU (nvJPEG): pass engine=capi.Context(...) — no CPU decode path")
+        return scan.read_level(engine, level)
     if hasattr(scan, "level_array"):
         a = scan.level_array(level)
         if a is not None:
@@ -80,14 +85,14 @@ class Dataset_wsi:
         test of the tile plan run on the GPU (wsi_find_nuclei / wsi_plan_tiles_gpu).  With engine None a mask must be
         given (the reference's cached mask PNG, utils/dataset.py:131-134) and the host C++ planner enumerates the tiles;
         there is no CPU implementation of find_nuclei in this package."""
-        self.scan, self.params, self.scan_level = scan, params, scan_level
+        self.scan, self.params, self.scan_level, self._engine = scan, params, scan_level, engine
         self.datalist, self.tiles = [], np.zeros((0, 2), np.int32)
         self.mask = mask
         if len(scan.level_dimensions) - 1 < scan_level:     # utils/dataset.py:123-124: slide silently skipped
             return
         self.params.iw, self.params.ih = scan.level_dimensions[scan_level]
         if self.mask is None:                                # :131-134
-            thumb = _level_raster(scan, 2)
+            thumb = _level_raster(scan, 2, engine)
             if engine is None:
                 raise RuntimeError("no foreground mask for this slide and no engine: find_nuclei runs on the GPU only "
                                    "(pass engine=capi.Context(...) or a cached mask) — no CPU fallback")
@@ -103,7 +108,7 @@ class Dataset_wsi:
 
     def raster(self) -> np.ndarray:
         if self._raster is None:
-            self._raster = _level_raster(self.scan, self.scan_level)
+            self._raster = _level_raster(self.scan, self.scan_level, self._engine)
         return self._raster
 
 
@@ -122,8 +127,9 @@ class Dataset_wsis:
         if isinstance(svs_pth, Mapping):
             scans = {k: (v, k) for k, v in svs_pth.items()}
         else:
-            import openslide  # noqa: F401  (not installed in the build image; real slides need it)
-            scans = {os.path.basename(p): (openslide.OpenSlide(p), p) for p in sorted(glob.glob(f"{svs_pth}/Case*/*.svs"))}
+            # the reference opens these with openslide (utils/dataset.py:90-96); here the TIFF / SVS container is parsed by the
+            # library and the JPEG tiles are decoded on the GPU (capi.TiffSlide, wsi_tiff_*)
+            scans = {os.path.basename(p): (capi.TiffSlide(p), p) for p in sorted(glob.glob(f"{svs_pth}/Case*/*.svs"))}
         for key, (scan, path) in scans.items():
             mask = None if masks is None else masks.get(key)
             msk_pth = f"{wsi_mask_pth}/{key}.png" if wsi_mask_pth else None

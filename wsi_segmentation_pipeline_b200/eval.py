@@ -80,8 +80,11 @@ def predict_tumorbed(model, dataset, ep, mode: str = "seg", args=None, return_ou
             Image.fromarray(heat).save(f"{a.val_save_pth}/{ep}/{key}_{a.tile_stride_w}_heatmap.png")     # :229
             if a.save_overlay:                                                                            # :262-267
                 scan = entry["scan"]
-                img = np.ascontiguousarray(np.asarray(scan.read_region((0, 0), 2, scan.level_dimensions[2]).convert("RGB")), dtype=np.uint8)
-                over = ctx.overlay_heat(img, np.ascontiguousarray(heat))            # img * 0.75 + 255 * (heat > 255 * 0.99) * 0.25, on the device
+                if isinstance(scan, capi.TiffSlide):                                  # thumbnail decoded on the GPU, blended there
+                    over = ctx.overlay_heat(scan.read_level(ctx, 2), r["heatmap"].cuda()).cpu().numpy()
+                else:
+                    img = np.ascontiguousarray(np.asarray(scan.read_region((0, 0), 2, scan.level_dimensions[2]).convert("RGB")), dtype=np.uint8)
+                    over = ctx.overlay_heat(img, np.ascontiguousarray(heat))        # img * 0.75 + 255 * (heat > 255 * 0.99) * 0.25, on the device
                 Image.fromarray(over).save(f"{a.val_save_pth}/{ep}/{key}_{a.tile_stride_w}_overlay.png")
         if return_outputs:
             outputs[key] = {"classes": classes, "heatmap": heat}
