@@ -114,11 +114,13 @@ def batch(path, bench_json=None):
         if "conv_" in k or "stem" in k:
             conv_t += a["us"]
             conv_tx += a["tensor_x_us"]
+        def sig(n):          # (kernel base name, first template integer)
+            m = re.search(r"([A-Za-z_0-9]+)\s*<\s*(\d+)", n)
+            return (m.group(1), m.group(2)) if m else (re.sub(r"^void\s+", "", n).strip(), "")
         lv = None
         for name, rws in live.items():
-            base = name.split("<")[0]
-            if base in k and (("<" not in name) or all(tok in k.replace(" ", "") for tok in re.findall(r"\d+", name)[:1])):
-                lv = rws
+            if sig(name) == sig(k):
+                lv = (lv or []) + rws
         lms = sum(r["ms"] for r in lv) if lv else ""
         ltf = (sum(r["tflops"] * r["ms"] for r in lv) / max(sum(r["ms"] for r in lv), 1e-9)) if lv else ""
         lgb = (sum(r["gbs"] * r["ms"] for r in lv) / max(sum(r["ms"] for r in lv), 1e-9)) if lv else ""
