@@ -100,7 +100,7 @@ struct wsi_ctx {
   std::vector<EventSpan> spans;
   std::vector<cudaEvent_t> event_pool;
   // scratch reused across slides
-  DevBuf raster, maskbuf, logit_ring, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, rect_rows, tile_logits, scratch_f32, counts;
+  DevBuf raster, maskbuf, logit_ring, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, rect_rows, rect_bx, rect_by, rect_cellx, rect_celly, cls_cells, tile_logits, scratch_f32, counts;
   // copy streams: chunked raster upload / strip-wise output download overlap the compute on the caller's stream
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // pinned staging for the per-slide index arrays (tile list, rect index): uploaded without a stream sync
@@ -730,11 +730,43 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
     }
   }
   rowstart.push_back((int32_t)T);
+  int cls_nbx = 0, cls_nby = 0;
   // index arrays -> pinned staging -> device, stream-ordered (no host sync)
   {
     if (c->idx_pending) { CUDA_CHECK(cudaEventSynchronize(c->idx_event)); c->idx_pending = false; }
     const size_t n_xy = (size_t)2 * T, n_tx = (size_t)T, n_ry = rowy.size(), n_rs = rowstart.size(), n_ri = rowy.size() * 8;
-    c->idx_host.alloc((n_xy + n_tx + n_ry + n_rs + n_ri + 8) * sizeof(int32_t));
+    // CLS: the canvas cut at every tile edge (cells of constant summed logits) and the cell index of every column / owned row
+    std::vector<int32_t> bx, by, cellx, celly;
+    if (head == WSI_HEAD_CLS) {
+      bx.push_back(0);
+      for (int64_t i = 0; i < T; ++i) {
+        bx.push_back((int32_t)std::min<int64_t>(std::max<int64_t>(txs[i], 0), W2));
+        bx.push_back((int32_t)std::min<int64_t>(std::max<int64_t>((int64_t)txs[i] + dx, 0), W2));
+      }
+      std::sort(bx.begin(), bx.end());
+      bx.erase(std::unique(bx.begin(), bx.end()), bx.end());
+      while (!bx.empty() && bx.back() >= W2) bx.pop_back();
+      by.push_back((int32_t)own0);
+      for (int32_t ry : rowy) {
+        by.push_back((int32_t)std::min<int64_t>(std::max<int64_t>(ry, own0), own1));
+        by.push_back((int32_t)std::min<int64_t>(std::max<int64_t>((int64_t)ry + dy, own0), own1));
+      }
+      std::sort(by.begin(), by.end());
+      by.erase(std::unique(by.begin(), by.end()), by.end());
+      while (!by.empty() && by.back() >= own1) by.pop_back();
+      cellx.resize((size_t)W2);
+      for (size_t k = 0; k < bx.size(); ++k) {
+        const int64_t x1 = (k + 1 < bx.size()) ? bx[k + 1] : W2;
+        for (int64_t x = bx[k]; x < x1; ++x) cellx[(size_t)x] = (int32_t)k;
+      }
+      celly.resize((size_t)orows);
+      for (size_t k = 0; k < by.size(); ++k) {
+        const int64_t y1 = (k + 1 < by.size()) ? by[k + 1] : own1;
+        for (int64_t y = by[k]; y < y1; ++y) celly[(size_t)(y - own0)] = (int32_t)k;
+      }
+    }
+    const size_t n_cl = bx.size() + by.size() + cellx.size() + celly.size();
+    c->idx_host.alloc((n_xy + n_tx + n_ry + n_rs + n_ri + n_cl + 8) * sizeof(int32_t));
     int32_t* h = static_cast<int32_t*>(c->idx_host.p);
     int32_t *h_xy = h, *h_tx = h + n_xy, *h_ry = h_tx + n_tx, *h_rs = h_ry + n_ry, *h_ri = h_rs + n_rs;
     h_ri += (4 - ((h_ri - h) & 3)) & 3;                       // RowInfo entries are read with 16-byte loads
@@ -767,6 +799,17 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
     up(c->rect_rowy, h_ry, n_ry);
     up(c->rect_rowstart, h_rs, n_rs);
     up(c->rect_rows, h_ri, n_ri);
+    if (head == WSI_HEAD_CLS) {
+      int32_t* h_cl = h_ri + n_ri;
+      auto put = [&](DevBuf& b, const std::vector<int32_t>& v) {
+        if (!v.empty()) memcpy(h_cl, v.data(), v.size() * sizeof(int32_t));
+        up(b, h_cl, v.size());
+        h_cl += v.size();
+      };
+      put(c->rect_bx, bx); put(c->rect_by, by); put(c->rect_cellx, cellx); put(c->rect_celly, celly);
+      cls_nbx = (int)bx.size();
+      cls_nby = (int)by.size();
+    }
     CUDA_CHECK(cudaEventRecord(c->idx_event, s));
     c->idx_pending = true;
   }
@@ -905,9 +948,9 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   } else {
     {
       StageScope scope(c, s, ST_STITCH, (double)T * 16.0 + (double)plane * (mask_dev ? 3.0 : 2.0));
-      int r_lo, r_hi;
-      row_range(own0, own1, &r_lo, &r_hi);
-      launch_stitch_finalise_cls(ri, c->tile_logits.as<float4>(), (int)T, own0, own1, r_lo, r_hi, fa, s, &c->lc);
+      c->cls_cells.alloc((size_t)std::max(cls_nbx, 1) * std::max(cls_nby, 1) * cls_cell_bytes());
+      launch_stitch_finalise_cls(ri, c->tile_logits.as<float4>(), (int)T, c->rect_bx.as<int32_t>(), cls_nbx, c->rect_by.as<int32_t>(), cls_nby,
+                                 c->rect_cellx.as<int32_t>(), c->rect_celly.as<int32_t>(), c->cls_cells.p, fa, s, &c->lc);
     }
     download_rows(own0, own1);
   }

@@ -560,35 +560,68 @@ void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int rin
   if (lc) lc->n++;
 }
 
-// cls: pred_src [C] broadcast over the tile rectangle (utils/eval.py:210-215); tile_logits f32 [T][4] in sorted order
-__global__ void __launch_bounds__(256) stitch_finalise_cls_kernel(RectIndex ri, const float4* __restrict__ tile_logits, int T, int r_lo, int r_hi, int y0,
-                                                                   FinaliseArgs a) {
-  const int Y = y0 + blockIdx.x;
-  const int X0 = blockIdx.y * 256;
-  const int X = X0 + threadIdx.x;
-  const bool live = X < a.W2;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for_each_candidate(ri, 0, T, r_lo, r_hi, X0, 256, Y, [&](int i, int tx, int) {
-    const int ox = X - tx;
-    if (live && ox >= 0 && ox < ri.dx) {
-      const float4 v = __ldg(tile_logits + i);
+// cls: pred_src [C] broadcast over the tile rectangle (utils/eval.py:210-215); tile_logits f32 [T][4] in sorted order.
+// The summed logits are piecewise constant: they only change where a tile starts or ends.  The host cuts the canvas at
+// every tile edge (x breakpoints Bx, y breakpoints By) and gives every column / row its cell index; ONE thread per CELL
+// sums the covering tiles (double, sorted order) and runs the softmax / floor / argmax once, then the paint kernel writes
+// 2 bytes per pixel from the cell table.  (The first version re-did the sum and the double-precision softmax per PIXEL:
+// 189 ms at 4x coverage and 804 ms at 64x coverage on a 50k x 50k canvas for 5 GB of output — 0.1-0.4 % of HBM speed.)
+struct ClsCell { double s[4]; double p[4]; double h; uint8_t cls; uint8_t pad[7]; };      // 80 bytes
+
+__global__ void __launch_bounds__(128) cls_cells_kernel(RectIndex ri, const float4* __restrict__ tile_logits, int T, const int32_t* __restrict__ bx, int nbx,
+                                                         const int32_t* __restrict__ by, int nby, FinaliseArgs a, ClsCell* __restrict__ cells) {
+  const int64_t n = (int64_t)nbx * nby;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(c / nbx), i = (int)(c - (int64_t)j * nbx);
+    const int X = __ldg(bx + i), Y = __ldg(by + j);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for_each_cover(ri, 0, T, X, Y, [&](int t, int, int) {
+      const float4 v = __ldg(tile_logits + t);
       s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
-    }
-  });
-  if (!live) return;
-  const int64_t idx = (int64_t)(Y - a.own0) * a.W2 + X, plane = (a.own1 - a.own0) * a.W2;
-  const double mv = a.mask ? (double)a.mask[idx] : 1.0;
-  const PixelOut o = finalise_pixel(s0, s1, s2, s3, mv, a.class_probs, a.heat_mode);
-  write_pixel(a, idx, plane, s0, s1, s2, s3, o);
+    });
+    const PixelOut o = finalise_pixel(s0, s1, s2, s3, 1.0, a.class_probs, a.heat_mode);
+    ClsCell q;
+    q.s[0] = s0; q.s[1] = s1; q.s[2] = s2; q.s[3] = s3;
+    q.p[0] = o.p[0]; q.p[1] = o.p[1]; q.p[2] = o.p[2]; q.p[3] = o.p[3];
+    q.h = (a.heat_mode == 1) ? o.p[1] : (o.p[2] + o.p[3]);
+    q.cls = o.cls;
+    cells[c] = q;
+  }
 }
 
-void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, int64_t y0, int64_t y1, int r_lo, int r_hi, const FinaliseArgs& a,
-                                cudaStream_t s, LaunchCounter* lc) {
-  if (y1 <= y0 || a.W2 <= 0) return;
-  dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256));
-  stitch_finalise_cls_kernel<<<grid, 256, 0, s>>>(ri, tile_logits, T, r_lo, r_hi, (int)y0, a);
+__global__ void __launch_bounds__(256) cls_paint_kernel(const ClsCell* __restrict__ cells, const int32_t* __restrict__ cellx, const int32_t* __restrict__ celly,
+                                                         int nbx, int y0, FinaliseArgs a) {
+  const int Y = y0 + blockIdx.x;
+  const int X = blockIdx.y * 256 + threadIdx.x;
+  if (X >= a.W2) return;
+  const ClsCell* q = cells + (int64_t)__ldg(celly + (Y - (int)a.own0)) * nbx + __ldg(cellx + X);
+  const int64_t idx = (int64_t)(Y - a.own0) * a.W2 + X, plane = (a.own1 - a.own0) * a.W2;
+  const double mv = a.mask ? (double)a.mask[idx] : 1.0;
+  const double hv = 255.0 * (mv * q->h);
+  a.classes[idx] = q->cls;
+  a.heatmap[idx] = (uint8_t)(int)fmin(hv, 255.0);
+  if (a.canvas_out) {
+    a.canvas_out[idx] = (float)q->s[0]; a.canvas_out[plane + idx] = (float)q->s[1]; a.canvas_out[2 * plane + idx] = (float)q->s[2];
+    a.canvas_out[3 * plane + idx] = (float)q->s[3];
+  }
+  if (a.probs_out) {
+    a.probs_out[idx] = (float)q->p[0]; a.probs_out[plane + idx] = (float)q->p[1]; a.probs_out[2 * plane + idx] = (float)q->p[2];
+    a.probs_out[3 * plane + idx] = (float)q->p[3];
+  }
+}
+
+size_t cls_cell_bytes() { return sizeof(ClsCell); }
+
+void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const int32_t* bx, int nbx, const int32_t* by, int nby,
+                                const int32_t* cellx, const int32_t* celly, void* cells, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc) {
+  if (a.own1 <= a.own0 || a.W2 <= 0) return;
+  const int64_t n = (int64_t)nbx * nby;
+  cls_cells_kernel<<<(int)std::min<int64_t>(ceil_div(n, 128), 148 * 16), 128, 0, s>>>(ri, tile_logits, T, bx, nbx, by, nby, a, static_cast<ClsCell*>(cells));
   CUDA_CHECK(cudaGetLastError());
-  if (lc) lc->n++;
+  dim3 grid((unsigned)(a.own1 - a.own0), (unsigned)ceil_div(a.W2, 256));
+  cls_paint_kernel<<<grid, 256, 0, s>>>(static_cast<const ClsCell*>(cells), cellx, celly, nbx, (int)a.own0, a);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n += 2;
 }
 
 __global__ void __launch_bounds__(256) counts_kernel(RectIndex ri, int T, int64_t W2, int64_t own0, int64_t own1, int32_t* __restrict__ counts) {

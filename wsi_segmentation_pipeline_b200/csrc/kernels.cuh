@@ -70,9 +70,12 @@ void launch_nhwc4_to_nchw(const float* x, int n, int h, int w, float* y, cudaStr
 void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int ring_cap, int t_lo, int t_hi, int r_lo, int r_hi, int64_t y0, int64_t y1,
                                 const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc);
 // ([r_lo, r_hi): the tile rows that can touch canvas rows [y0, y1), found by the host)
-// K6+K7 (cls): per-tile logits [T][4] (sorted order) broadcast over rectangles, summed per pixel and finalised
-void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, int64_t y0, int64_t y1, int r_lo, int r_hi, const FinaliseArgs& a,
-                                cudaStream_t s, LaunchCounter* lc);
+// K6+K7 (cls): per-tile logits [T][4] (sorted order) broadcast over rectangles.  bx [nbx] / by [nby]: the canvas cut at every
+// tile edge (first pixel of each cell, ascending; the host builds them); cellx [W2] / celly [owned rows]: cell index of every
+// column / owned row; cells: scratch of nbx * nby * cls_cell_bytes().  One sum + softmax per CELL, 2 bytes written per pixel.
+size_t cls_cell_bytes();
+void launch_stitch_finalise_cls(const RectIndex& ri, const float4* tile_logits, int T, const int32_t* bx, int nbx, const int32_t* by, int nby,
+                                const int32_t* cellx, const int32_t* celly, void* cells, const FinaliseArgs& a, cudaStream_t s, LaunchCounter* lc);
 // coverage counts from the rect index
 void launch_counts(const RectIndex& ri, int T, int64_t W2, int64_t own0, int64_t own1, int32_t* counts,
                    cudaStream_t s, LaunchCounter* lc);
