@@ -1,7 +1,9 @@
 #!/bin/bash
-# final regression on a fresh box: smoke(), full pytest -m gpu, default bench, reference arm (bounded)
+# end-of-round evidence: full GPU suite, smoke, default bench (20 steps like the driver), configs[4] sweep
 mkdir -p gpurun_out
-echo "=== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?"; tail -n 6 gpurun_out/smoke.log | cut -c1-200
-echo "=== pytest -m gpu"; timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?"; tail -n 3 gpurun_out/pytest_gpu.log
-echo "=== bench (defaults)"; timeout 1200 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "exit $?"; wc -l gpurun_out/bench_default.json; cut -c1-260 gpurun_out/bench_default.json
-echo "=== bench --impl reference"; timeout 1200 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit $?"; wc -l gpurun_out/bench_ref.json; cut -c1-300 gpurun_out/bench_ref.json
+echo "=== pytest -m gpu"; timeout 1800 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?"; tail -n 4 gpurun_out/pytest_gpu.log | cut -c1-200
+echo "=== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+echo "=== bench (driver settings)"; timeout 1500 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit $?"; cut -c1-300 gpurun_out/bench.json; tail -n 2 gpurun_out/bench.err
+echo "=== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit $?"; cut -c1-300 gpurun_out/bench_ref.json
+echo "=== c5"; timeout 1500 python bench.py --config c5 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "exit $?"; cut -c1-200 gpurun_out/bench_c5.json
+echo "=== c4"; timeout 900 python bench.py --config c4 --steps 3 --warmup 1 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "exit $?"; cat gpurun_out/bench_c4.json | cut -c1-1500
