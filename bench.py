@@ -131,7 +131,7 @@ def workload_config(cfg, n_gpus, ih, iw, tile, stride, T, scaling):
     return {"workload": f"{names[cfg]}: {model} on a synthetic {iw}x{ih} H&E slide, {tile}px tiles stride {stride}, "
                         f"all-foreground mask, random-init calibrated weights",
             "tiles": int(T), "tile": tile, "stride": stride, "slide_wh": [iw, ih],
-            "parallelism": f"row-bands x{n_gpus} ({scaling} scaling; halo = tile overlap, no data-path collective, one final NCCL exchange of the u8 band outputs to rank 0)",
+            "parallelism": f"row-bands x{n_gpus} ({scaling} scaling; halo = tile overlap, no data-path collective; how the u8 band outputs reach rank 0: see `gather`)",
             "l2_policy": "inputs larger than L2 (band raster >= 1.2 GB, logit ring >= 3 GB per GPU)"}
 
 
