@@ -9,7 +9,13 @@
  * the ABI; the caller owns every buffer it passes in; the library owns wsi_ctx and anything it
  * returns through an out-pointer (release with wsi_free).  A wsi_ctx is bound to one CUDA device
  * and is not thread-safe (one per GPU / process).  All device work is ordered on the `stream`
- * argument (a cudaStream_t passed as void*, NULL = the legacy default stream).  There is no CPU
+ * argument (a cudaStream_t passed as void*, NULL = the legacy default stream); the context's two
+ * copy streams (chunked raster upload, strip-wise result download) are ordered against it with
+ * events.  Calls whose inputs AND outputs are device pointers never synchronise the host (small index
+ * arrays travel through the context's pinned staging); calls with WSI_MEM_HOST outputs return when
+ * those outputs are complete.  A device-side failure inside an asynchronous call (the conv kernels'
+ * pipeline barriers time out instead of hanging) raises a sticky flag that the next synchronising
+ * call, or wsi_check, reports.  Device pointers need no particular alignment.  There is no CPU
  * fallback: without a CUDA device wsi_ctx_create fails with WSI_ERR_CUDA.
  */
 #ifndef WSI_B200_H

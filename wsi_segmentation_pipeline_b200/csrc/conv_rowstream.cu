@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           float yv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float sc = (BN <= 32) ? r_scale[(BN <= 32) ? c + j : 0] : s_scale[c + j];
-            const float bi = (BN <= 32) ? r_bias[(BN <= 32) ? c + j : 0] : s_bias[c + j];
+            const float sc = (BN <= 32) ? r_scale[(BN <= 32) ? c + j : 0] : p.k.scale[c + j];
+            const float bi = (BN <= 32) ? r_bias[(BN <= 32) ? c + j : 0] : p.k.bias[c + j];
             yv[j] = fmaf(__uint_as_float(v[j]), sc, bi);
           }
           if (has_res) {
@@ -635,21 +635,25 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
             // d5b + final_conv: BN, ReLU and the 16 -> 4 head as packed FMAs; constants are broadcast smem reads.
             // Lane .x of every pair carries the even channels, .y the odd ones: the same two summation chains per
             // logit as the scalar formulation, so the result is bit-identical.
+            // (constants: compile-time offsets into the parameter bank — FFMA with a c[][] operand, no shared-memory
+            //  loads; the even / odd summation chains of the earlier packed-FMA formulation are kept, so results are
+            //  bit-identical with it)
             float2 y2[8];
 #pragma unroll
             for (int jp = 0; jp < 8; ++jp) {
-              const float2 sc = reinterpret_cast<const float2*>(s_scale)[jp], bi = reinterpret_cast<const float2*>(s_bias)[jp];
-              y2[jp] = ffma2(make_float2(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])), sc, bi);
-              y2[jp].x = fmaxf(y2[jp].x, lo);
-              y2[jp].y = fmaxf(y2[jp].y, lo);
+              y2[jp].x = fmaxf(fmaf(__uint_as_float(v[2 * jp]), p.k.scale[2 * jp], p.k.bias[2 * jp]), lo);
+              y2[jp].y = fmaxf(fmaf(__uint_as_float(v[2 * jp + 1]), p.k.scale[2 * jp + 1], p.k.bias[2 * jp + 1]), lo);
             }
             float* hp = reinterpret_cast<float*>(&hacc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              float2 acc = make_float2(0.f, 0.f);
+              float ae = 0.f, ao = 0.f;
 #pragma unroll
-              for (int jp = 0; jp < 8; ++jp) acc = ffma2(y2[jp], reinterpret_cast<const float2*>(s_hw + k * 16)[jp], acc);
-              hp[k] = (acc.x + acc.y) + s_hb[k];
+              for (int jp = 0; jp < 8; ++jp) {
+                ae = fmaf(y2[jp].x, p.k.head[k * 16 + 2 * jp], ae);
+                ao = fmaf(y2[jp].y, p.k.head[k * 16 + 2 * jp + 1], ao);
+              }
+              hp[k] = (ae + ao) + p.k.head[64 + k];
             }
             if (valid && p.out != nullptr) {
 #pragma unroll
@@ -658,8 +662,8 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
           } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float sc = kRegSB ? r_scale[kRegSB ? c + j : 0] : s_scale[c + j];
-            const float bi = kRegSB ? r_bias[kRegSB ? c + j : 0] : s_bias[c + j];
+            const float sc = kRegSB ? r_scale[kRegSB ? c + j : 0] : p.k.scale[c + j];
+            const float bi = kRegSB ? r_bias[kRegSB ? c + j : 0] : p.k.bias[c + j];
             yv[j] = fmaf(__uint_as_float(v[j]), sc, bi);
           }
           }
@@ -777,6 +781,7 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   upload(scale_, sc);
   upload(bias_, bi);
   p.w = w_.as<bf16>(); p.scale = scale_.as<float>(); p.bias = bias_.as<float>();
+  for (int j = 0; j < BN; ++j) { p.k.scale[j] = sc[j]; p.k.bias[j] = bi[j]; }
   flops_ = 2.0 * N * OH * OW * (double)BN * C * 9;
   if (spec.head) {
     WSI_REQUIRE(head_w && head_b && head_out, WSI_ERR_INVALID, "fused head needs weights and an output");
@@ -784,6 +789,8 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
     upload(headw_, hw);
     upload(headb_, hb);
     p.head_w = headw_.as<float>(); p.head_b = headb_.as<float>(); p.head_out = head_out;
+    for (int j = 0; j < 64; ++j) p.k.head[j] = hw[j];
+    for (int j = 0; j < 4; ++j) p.k.head[64 + j] = hb[j];
     flops_ += 2.0 * N * OH * OW * 16 * 4;
   }
   const int w_bytes = p.nslabs * 3 * 2 * 3 * BN * 16;

@@ -49,6 +49,7 @@ struct StreamParams {
   const float* head_w;
   const float* head_b;
   float* head_out;
+  EpiConst k;                    // scale / bias / head in the parameter (constant) bank: what the epilogues read
   int* error_flag;
   int dbg;                       // timing experiments only (WSI_STREAM_DBG; results are garbage): 1 no MMAs, 2 no loads, 4 independent MMAs,
                                  // 3 epilogue drains nothing

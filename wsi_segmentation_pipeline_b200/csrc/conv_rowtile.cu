@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_rowtile_kernel(const __g
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          y[j] = fmaxf(fmaf(__uint_as_float(v0[j]) + __uint_as_float(v1[j]), s_scale[h * 32 + j], s_bias[h * 32 + j]), 0.f);
+          y[j] = fmaxf(fmaf(__uint_as_float(v0[j]) + __uint_as_float(v1[j]), p.k.scale[h * 32 + j], p.k.bias[h * 32 + j]), 0.f);
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -532,6 +532,7 @@ void RowStemOp::build(const void* padded_tiles, int n, int ph, int pw, const flo
   upload(scale_, sc);
   upload(bias_, bi);
   p.w = w_.as<bf16>(); p.scale = scale_.as<float>(); p.bias = bias_.as<float>();
+  for (int jj = 0; jj < 64; ++jj) { p.k.scale[jj] = sc[jj]; p.k.bias[jj] = bi[jj]; }
   flops_ = 2.0 * n * p.OH * p.OW * 64.0 * 147.0;
   p.stages = 8;
   smem_ = 128 + 28 * 64 * 16 + 512 + p.stages * kStemStageBytes + 256;

@@ -57,6 +57,16 @@ struct PlanarDims {
   __host__ __device__ size_t bytes(int N_) const { return (size_t)N_ * (H + 2) * KC * P * Wrow * 16; }
 };
 
+// Epilogue constants carried IN the kernel parameter struct: folded-BN scale / bias and the fused 1x1 head live in the
+// constant bank, so `fmaf(acc, k.scale[j], k.bias[j])` with a compile-time j is an FFMA with a c[][] operand — no load
+// instruction.  (Round 1 broadcast them from shared memory: ncu showed the LSU shared-memory pipe at 88 % in the d5b
+// kernel — 52 broadcast LDS per output row and warp — and at 56-59 % in the other row kernels.)
+struct EpiConst {
+  float scale[64];
+  float bias[64];
+  float head[68];      // [4][16] head weights, then the 4 head biases
+};
+
 struct RowPart {
   const uint8_t* base;   // planar tensor
   PlanarDims d;
@@ -133,6 +143,7 @@ struct StemParams {
   const bf16* w;                 // [28 k-chunks][64][8] bf16
   const float* scale;            // [64]
   const float* bias;             // [64]
+  EpiConst k;                    // the same constants in the parameter (constant) bank
   uint8_t* out;                  // bf16, NHWC [N,OH,OW,64] or parity-planar
   int out_layout;                // LAYOUT_NHWC or LAYOUT_PLANAR_PARITY
   PlanarDims od;

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_upstream_kernel(const __gr
 #pragma unroll
               for (int tt = 0; tt < 4; ++tt) {
                 const int jx = 8 * kk + 2 * tt;
-                const float sa = s_scale[c + jx], sb = s_scale[c + jx + 1], ba = s_bias[c + jx], bb = s_bias[c + jx + 1];
+                const float sa = p.k.scale[c + jx], sb = p.k.scale[c + jx + 1], ba = p.k.bias[c + jx], bb = p.k.bias[c + jx + 1];
                 __nv_bfloat162 e = __floats2bfloat162_rn(fmaxf(fmaf(__uint_as_float(v0[jx]), sa, ba), lo_clamp),
                                                          fmaxf(fmaf(__uint_as_float(v0[jx + 1]), sb, bb), lo_clamp));
                 __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(fmaf(__uint_as_float(v1[jx]), sa, ba), lo_clamp),
@@ -467,6 +467,7 @@ void UpStreamOp::build(const std::vector<ConvInputPart>& parts, const ConvSpec& 
   upload(scale_, sc);
   upload(bias_, bi);
   p.scale = scale_.as<float>(); p.bias = bias_.as<float>();
+  for (int j = 0; j < BN; ++j) { p.k.scale[j] = sc[j]; p.k.bias[j] = bi[j]; }
   flops_ = 2.0 * N * p.OH * p.OW * (double)BN * cin * 9;
 
   p.stage_bytes = std::max(2 * p.nslabs_u, 4 * p.nslabs_s) * kRowRunBytes;

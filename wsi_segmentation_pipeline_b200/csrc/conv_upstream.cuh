@@ -46,6 +46,7 @@ struct UpParams {
   int w_bytes, wskip_off;
   const float* scale;
   const float* bias;
+  EpiConst k;                    // scale / bias in the parameter (constant) bank: what the epilogue reads
   int relu;
   uint8_t* out;                  // planar output
   PlanarDims od;
