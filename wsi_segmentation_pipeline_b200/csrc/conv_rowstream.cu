@@ -411,9 +411,7 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
   const int w_bytes = p.nslabs * 3 * 2 * 3 * BN * 16;
   uint8_t* s_w = smem;
   float* s_scale = reinterpret_cast<float*>(smem + w_bytes);
-  float* s_bias = s_scale + BN;
-  float* s_hw = s_bias + BN;
-  float* s_hb = s_hw + 64;
+  float* s_bias = s_scale + BN;          // (the fused head and, for BN > 16, scale / bias are read from the parameter bank: p.k)
   uint8_t* s_stage = smem + ((w_bytes + (2 * BN + 68) * 4 + 127) & ~127);
   const int S = p.stages;
   const int stage_bytes = p.nslabs * 2 * kRun2Bytes;
@@ -431,8 +429,6 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
     uint4* dst = reinterpret_cast<uint4*>(s_w);
     for (int i = threadIdx.x; i < w_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     for (int i = threadIdx.x; i < BN; i += blockDim.x) { s_scale[i] = p.scale[i]; s_bias[i] = p.bias[i]; }
-    if (HEAD)
-      for (int i = threadIdx.x; i < 68; i += blockDim.x) s_hw[i] = (i < 64) ? p.head_w[i] : p.head_b[i - 64];
     uint4* st = reinterpret_cast<uint4*>(s_stage);
     for (int i = threadIdx.x; i < S * stage_bytes / 16; i += blockDim.x) st[i] = make_uint4(0, 0, 0, 0);
     sptx::fence_proxy_async();
