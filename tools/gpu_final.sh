@@ -7,3 +7,4 @@ echo "=== bench (driver settings)"; timeout 1500 python bench.py --steps 20 --wa
 echo "=== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit $?"; cut -c1-300 gpurun_out/bench_ref.json
 echo "=== c5"; timeout 1500 python bench.py --config c5 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "exit $?"; cut -c1-200 gpurun_out/bench_c5.json
 echo "=== c4"; timeout 900 python bench.py --config c4 --steps 3 --warmup 1 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "exit $?"; cat gpurun_out/bench_c4.json | cut -c1-1500
+echo "=== ncu batch"; bash tools/gpu_ncu_r2.sh
