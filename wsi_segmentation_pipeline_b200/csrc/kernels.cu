@@ -2,6 +2,8 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 namespace wsi {
 
@@ -13,11 +15,17 @@ namespace wsi {
 //   reference's exact fp32 op order and rounds it to bf16 once, so the kernel is a byte gather.
 //   Output is the stem's operand layout: [n][ph+6][pw+8][4] bf16, zero border (3 top/left), ch 3 = 0.
 // =============================================================================================
-template <int PLANES>
+// ARITH (throughput mode only): bf16(fmaf(float(u8), a_c, b_c)) with a_c = 1 / (255 std_c), b_c = -mean_c / std_c instead
+// of the table lookup — the host has verified that this reproduces ALL 768 table entries bit for bit (launch_gather),
+// so the output is unchanged; it removes the three data-dependent shared-memory lookups per pixel (bank conflicts on
+// tissue pixels) and leaves the byte loads and one 8-byte store.
+struct GatherAffine { float a[3], b[3]; };
+
+template <int PLANES, bool ARITH = false>
 __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t row0,
                                                       const int32_t* __restrict__ tiles_xy, int n_tiles, int ph, int pw,
                                                       const float* __restrict__ lut, bf16* __restrict__ padded,
-                                                      float* __restrict__ norm_out, int64_t plane_stride) {
+                                                      float* __restrict__ norm_out, int64_t plane_stride, GatherAffine aff) {
   // s_lut: the 3x256 possible outputs of Normalize(ToTensor(u8)) in fp32 (host-built, reference op order), rounded to
   // bf16 — and, for the fp32-emulated precision (planes == 3), the bf16 remainders b = rn(v - a), c = rn(v - a - b)
   __shared__ float s_f32[768];
@@ -50,17 +58,30 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
     const uint8_t* src = rgb + (int64_t)(y0 + r - row0) * row_stride + (int64_t)x0 * 3;
     bf16* dst = padded ? padded + ((int64_t)t * (ph + 6) + (r + 3)) * pitch + 3 * 4 : nullptr;
     float* q0 = norm_out ? norm_out + (int64_t)t * 3 * ph * pw + (int64_t)r * pw : nullptr;
-    for (int xb = 0; xb < pw; xb += 128) {                                 // 4 pixels per lane in flight
-      uint8_t c[4][3];
+    constexpr int kPx = 8;                                                 // pixels per lane in flight (24 byte loads): the kernel is
+    for (int xb = 0; xb < pw; xb += 32 * kPx) {                            // latency-bound (ncu: issue 45 %, DRAM 30 %, nothing saturated)
+      uint8_t c[kPx][3];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kPx; ++k) {
         const int x = xb + 32 * k + lane;
         if (x < pw) { c[k][0] = __ldg(src + 3 * x); c[k][1] = __ldg(src + 3 * x + 1); c[k][2] = __ldg(src + 3 * x + 2); }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kPx; ++k) {
         const int x = xb + 32 * k + lane;
         if (x >= pw) continue;
+        if (ARITH) {
+          // exact u8 -> float without a conversion instruction: 2^23 + c is representable, subtract 2^23
+          const float f0 = __uint_as_float(0x4B000000u | c[k][0]) - 8388608.f, f1 = __uint_as_float(0x4B000000u | c[k][1]) - 8388608.f,
+                      f2 = __uint_as_float(0x4B000000u | c[k][2]) - 8388608.f;
+          const __nv_bfloat162 lo2 = __floats2bfloat162_rn(fmaf(f0, aff.a[0], aff.b[0]), fmaf(f1, aff.a[1], aff.b[1]));
+          const __nv_bfloat162 hi2 = __floats2bfloat162_rn(fmaf(f2, aff.a[2], aff.b[2]), 0.f);
+          uint2 o;
+          o.x = *reinterpret_cast<const uint32_t*>(&lo2);
+          o.y = *reinterpret_cast<const uint32_t*>(&hi2);
+          *reinterpret_cast<uint2*>(dst + 4 * x) = o;
+          continue;
+        }
         if (dst) {
 #pragma unroll
           for (int j = 0; j < PLANES; ++j) {
@@ -84,14 +105,37 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
   }
 }
 
+// Does bf16(fmaf(v, a, b)) reproduce the reference-order table ((v / 255) - mean) / std rounded to bf16 for every u8 value?
+// (It does for the ImageNet statistics of myargs.py:127-130; checked here once, so the arithmetic path can never change
+// a result.)
+static bool gather_affine(GatherAffine* aff) {
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int ch = 0; ch < 3; ++ch) {
+    volatile float a = 1.0f / (255.0f * stdv[ch]);
+    volatile float b = -mean[ch] / stdv[ch];
+    aff->a[ch] = a; aff->b[ch] = b;
+    for (int v = 0; v < 256; ++v) {
+      volatile float t0 = (float)v / 255.0f;
+      volatile float t1 = t0 - mean[ch];
+      volatile float ref = t1 / stdv[ch];
+      const float y = std::fma((float)v, (float)a, (float)b);
+      if (f32_to_bf16_bits(y) != f32_to_bf16_bits(ref)) return false;
+    }
+  }
+  return true;
+}
+
 void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n, int ph,
                    int pw, const float* lut_dev, bf16* padded, float* norm_out, cudaStream_t s, LaunchCounter* lc, int planes,
                    int64_t plane_stride) {
   if (n <= 0) return;
+  static GatherAffine aff;
+  static const bool affine_ok = gather_affine(&aff) && getenv("WSI_GATHER_LUT") == nullptr;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div((int64_t)n * ph, 8), 148 * 8);
   // (a per-lane, bank-conflict-free copy of the table — 96 KB, 2 blocks per SM — was slower: 7.5 vs 6.1 ms per 8 280 tiles)
-  if (planes == 3) gather_kernel<3><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride);
-  else gather_kernel<1><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride);
+  if (planes == 3) gather_kernel<3><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride, aff);
+  else if (affine_ok && padded && !norm_out) gather_kernel<1, true><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride, aff);
+  else gather_kernel<1><<<grid, 256, 0, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, lut_dev, padded, norm_out, plane_stride, aff);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }
