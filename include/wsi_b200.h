@@ -94,6 +94,11 @@ typedef struct {
   const uint8_t* mask;     /* level-2 foreground mask rows [own0, own1), u8 {0,1} [own1-own0,W2];
                               NULL = all ones (utils/eval.py:219,225)                           */
   int32_t mask_mem;        /* wsi_mem_kind                                                      */
+  int32_t resize;          /* myargs.py:115 scan_resize r; 0 or 1 = off.  r > 1: ph x pw (= tile_h*r x tile_w*r,
+                              eval_tumorbed.py:39-40) windows are resized to tile_h x tile_w exactly as
+                              PIL.Image.resize((tile_w, tile_h)) does at its default filter
+                              (utils/dataset.py:180-181), the network runs on those, and SEG logits are
+                              nearest-upsampled x r before the slice-add (F.interpolate, utils/eval.py:202-206) */
 } wsi_slide_desc;
 
 /* Outputs of one slide/band, all optional except classes+heatmap; rows [own0, own1) only. */
@@ -131,6 +136,14 @@ WSI_API int wsi_plan_tiles(int64_t ih, int64_t iw, int32_t ph, int32_t pw, int32
                    const uint8_t* mask, int64_t mh, int64_t mw, double m,
                    int32_t** xy_out, int64_t* n_out);
 WSI_API void wsi_free(void* p);
+
+/* ---- tile resize tables of the scan_resize branch (host-only; utils/dataset.py:180-181 -> PIL.Image.resize) ---
+ * One axis of Pillow's antialiased bicubic resample in_size -> out_size as the library computes it (Pillow 12.2,
+ * libImaging/Resample.c): per output sample the window [bounds[2i], bounds[2i] + bounds[2i+1]) of input samples and
+ * its 22-bit fixed-point weights kk[i*ksize ...]; out = clip8((2^21 + sum(kk * in)) >> 22), horizontal pass first with a
+ * u8 intermediate.  wsi_run_slide uses exactly these tables on the device (wsi_slide_desc.resize).               */
+WSI_API int wsi_resample_ksize(int32_t in_size, int32_t out_size);
+WSI_API int wsi_resample_coeffs(int32_t in_size, int32_t out_size, int32_t* bounds /*[out_size][2]*/, int32_t* kk /*[out_size][ksize]*/);
 
 /* ---- row-band partition for multi-GPU (no reference counterpart) ----------------- */
 /* bands[k] = {own0, own1, row0, row1}: canvas rows owned, and scan-level raster rows needed

@@ -184,9 +184,10 @@ class UnetAdapter(nn.Module):
 # run the reference loop on one synthetic slide
 # ------------------------------------------------------------------------------------------
 def run_reference_predict_tumorbed(model, levels: dict, mask: np.ndarray, workdir: str, *, ph, pw, sh, sw,
-                                   mode, scan_level=2, batch=16, shuffle_seed=0, key="slide0.svs"):
+                                   mode, scan_level=2, batch=16, shuffle_seed=0, key="slide0.svs", scan_resize=1):
     """levels: {2: raster} (and {scan_level: raster} when scan_level != 2).  Returns dict with the
-    reference's tile list, f64 canvas, classes, probs, heatmap (as saved to PNG)."""
+    reference's tile list, f64 canvas, classes, probs, heatmap (as saved to PNG).  ph, pw: the Dataset params
+    (= tile * scan_resize, eval_tumorbed.py:39-40); args.tile_h / tile_w get ph / scan_resize."""
     from PIL import Image
     R = ref_modules()
     a = R.args
@@ -203,10 +204,10 @@ def run_reference_predict_tumorbed(model, levels: dict, mask: np.ndarray, workdi
     a.wsi_mask_pth = maskdir
     a.val_save_pth = os.path.join(workdir, "out")
     a.scan_level = scan_level
-    a.scan_resize = 1
+    a.scan_resize = scan_resize
     a.workers = 0
     a.num_classes = 4
-    a.tile_h, a.tile_w, a.tile_stride_h, a.tile_stride_w = ph, pw, sh, sw
+    a.tile_h, a.tile_w, a.tile_stride_h, a.tile_stride_w = ph // scan_resize, pw // scan_resize, sh, sw
     a.class_probs = [0.0, 0.0, 0.0, 0.0]
 
     ds = R.dataset.Dataset_wsis(root, {"ph": ph, "pw": pw, "sh": sh, "sw": sw}, bs=batch)
@@ -238,7 +239,7 @@ class _StopAfterScores(Exception):
 
 
 def run_reference_predict_wsis(model, levels: dict, mask: np.ndarray, workdir: str, *, ph, pw, sh, sw, scan_level=2,
-                               batch=16, shuffle_seed=0, key="slide0.svs"):
+                               batch=16, shuffle_seed=0, key="slide0.svs", scan_resize=1):
     """Runs the reference's predict_wsis (utils/eval.py:22-60 loop, :66-71 cv2.resize to level 2) on one synthetic
     slide and returns its tile list, the f64 scan-level canvas is not observable, so: `pred` = the RESIZED [C,H2,W2]
     array handed to `preprocessing.pred_to_mask` (:139), where the run is stopped — pred_to_mask itself has the tuple
@@ -260,10 +261,10 @@ def run_reference_predict_wsis(model, levels: dict, mask: np.ndarray, workdir: s
     a.wsi_mask_pth = maskdir
     a.val_save_pth = os.path.join(workdir, "out")
     a.scan_level = scan_level
-    a.scan_resize = 1
+    a.scan_resize = scan_resize
     a.workers = 0
     a.num_classes = 4
-    a.tile_h, a.tile_w, a.tile_stride_h, a.tile_stride_w = ph, pw, sh, sw
+    a.tile_h, a.tile_w, a.tile_stride_h, a.tile_stride_w = ph // scan_resize, pw // scan_resize, sh, sw
 
     ds = R.dataset.Dataset_wsis(root, {"ph": ph, "pw": pw, "sh": sh, "sw": sw}, bs=batch)
     tiles = list(ds.wsis[key]["iterator"].dataset.datalist)

@@ -23,6 +23,11 @@ Pinning status
   2x(conv3x3 no-bias + BN + ReLU), final 1x1 conv with bias).  **Parity for the U-Net model is
   UNPINNED** against smp itself; it is pinned only for the loop around it (the reference's own
   ``predict_tumorbed`` is run with this restated model to make the goldens).
+* ``pil_resize`` (the ``scan_resize != 1`` tile resize, utils/dataset.py:180-181) restates Pillow's
+  antialiased bicubic resample (third-party, not vendored, no version pinned by the reference; this
+  image has Pillow 12.2, whose ``Image.resize`` default for RGB is BICUBIC).  Pinned against the
+  installed Pillow itself (``tests/test_oracle_golden.py``) and against the unmodified reference run
+  with ``scan_resize = 2`` (``tests/golden/seg_resize2.npz``, ``wsis_resize2.npz``).
 """
 from __future__ import annotations
 
@@ -105,9 +110,68 @@ def normalise_tile(rgb_u8: np.ndarray) -> torch.Tensor:
     return t.sub_(mean).div_(std)
 
 
-def gather_tiles(raster: np.ndarray, tiles, ph, pw) -> torch.Tensor:
-    """read_region((ds*x, ds*y), level, (pw, ph)) on an in-memory scan-level raster, then the
+def _bicubic_weight(x: float) -> float:
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_resample_coeffs(in_size: int, out_size: int):
+    """One axis of Pillow's resample (libImaging/Resample.c: precompute_coeffs with the bicubic filter, support 2,
+    then normalize_coeffs_8bpc): per output sample (first input sample, count) and 22-bit fixed-point weights."""
+    import math
+    bits = 32 - 8 - 2
+    scale = in_size / out_size
+    fs = max(scale, 1.0)
+    support = 2.0 * fs
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / fs
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [_bicubic_weight((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = sum(k)
+        if ww != 0.0:
+            k = [v / ww for v in k]
+        for x, v in enumerate(k):
+            kk[xx, x] = int(-0.5 + v * (1 << bits)) if v < 0 else int(0.5 + v * (1 << bits))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def pil_resize(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
+    """``PIL.Image.fromarray(img).resize((out_w, out_h))`` for u8 [H,W,C] (utils/dataset.py:180-181: default filter,
+    BICUBIC for RGB in the Pillow of this image): horizontal pass then vertical pass, u8 intermediate,
+    out = clip8((2^21 + sum(k * in)) >> 22)."""
+    bits = 32 - 8 - 2
+
+    def one_axis(a, out_n):                                       # resample axis 1 of a [R, N, C]
+        b, k = pil_resample_coeffs(a.shape[1], out_n)
+        out = np.empty((a.shape[0], out_n, a.shape[2]), np.uint8)
+        a64 = a.astype(np.int64)
+        for xx in range(out_n):
+            x0, n = int(b[xx, 0]), int(b[xx, 1])
+            acc = (1 << (bits - 1)) + np.tensordot(a64[:, x0:x0 + n, :], k[xx, :n].astype(np.int64), axes=([1], [0]))
+            out[:, xx, :] = np.clip(acc >> bits, 0, 255)
+        return out
+
+    tmp = one_axis(np.ascontiguousarray(img), out_w)
+    return one_axis(tmp.transpose(1, 0, 2), out_h).transpose(1, 0, 2).copy()
+
+
+def gather_tiles(raster: np.ndarray, tiles, ph, pw, resize: int = 1) -> torch.Tensor:
+    """read_region((ds*x, ds*y), level, (pw, ph)) on an in-memory scan-level raster, (scan_resize != 1:
+    ``image.resize((tile_w, tile_h))`` with tile = window / scan_resize, utils/dataset.py:180-181), then the
     eval augmentor.  Tiles never leave the raster (the planner keeps x+pw <= iw-1)."""
+    if resize != 1:
+        return torch.stack([normalise_tile(pil_resize(raster[y:y + ph, x:x + pw], pw // resize, ph // resize)) for (x, y) in tiles])
     return torch.stack([normalise_tile(raster[y:y + ph, x:x + pw]) for (x, y) in tiles])
 
 
@@ -243,11 +307,13 @@ def model_forward(sd, arch: str, x: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # A8/A9: overlap-add  (utils/eval.py:179-215 predict_tumorbed, :42-60 predict_wsis)
 # --------------------------------------------------------------------------------------------
-def stitch(canvas: np.ndarray, tiles, logits: np.ndarray, ph, pw, m=1.0):
+def stitch(canvas: np.ndarray, tiles, logits: np.ndarray, ph, pw, m=1.0, up: int = 1):
     """canvas [C,H2,W2] f64 += per-tile logits; seg logits [T,C,ph,pw] or cls logits [T,C]
     broadcast over the tile rectangle.  numpy slicing clips silently at the canvas edge."""
     dx, dy = int(m * pw), int(m * ph)
     src = logits
+    if up != 1:                                        # F.interpolate(pred_src, (tile_h*r, tile_w*r)), default 'nearest' (utils/eval.py:202-206)
+        src = np.repeat(np.repeat(src, up, axis=-2), up, axis=-1)
     while canvas.ndim >= src.ndim:
         src = np.expand_dims(src, -1)
     for j, (x, y) in enumerate(tiles):
@@ -325,7 +391,7 @@ def finalise_heatmap(probs: np.ndarray, mask: np.ndarray, mode: str) -> np.ndarr
 
 
 def predict_tumorbed(sd, arch, raster, mask, ph, pw, sh, sw, mode, batch=16, m=1.0, tiles=None,
-                     class_probs=(0.0, 0.0, 0.0, 0.0)):
+                     class_probs=(0.0, 0.0, 0.0, 0.0), scan_resize: int = 1):
     """End-to-end restatement of utils/eval.py:155-229 for one slide whose scan-level raster is
     ``raster`` u8 [ih,iw,3] and whose level-2 canvas is [int(ih*m), int(iw*m)] (== mask.shape)."""
     ih, iw = raster.shape[:2]
@@ -336,10 +402,10 @@ def predict_tumorbed(sd, arch, raster, mask, ph, pw, sh, sw, mode, batch=16, m=1
     all_logits = []
     for i in range(0, len(tiles), batch):
         chunk = tiles[i:i + batch]
-        x = gather_tiles(raster, chunk, ph, pw)
+        x = gather_tiles(raster, chunk, ph, pw, scan_resize)           # ph, pw = tile * scan_resize (eval_tumorbed.py:39-40)
         y = model_forward(sd, arch, x).numpy()
         all_logits.append(y)
-        stitch(canvas, chunk, y, ph, pw, m)
+        stitch(canvas, chunk, y, ph, pw, m, scan_resize)
     classes, probs = threshold_probs(canvas, class_probs)
     heat = finalise_heatmap(probs, mask, mode)
     return {"tiles": tiles, "canvas": canvas, "classes": classes, "probs": probs, "heatmap": heat,
@@ -347,7 +413,7 @@ def predict_tumorbed(sd, arch, raster, mask, ph, pw, sh, sw, mode, batch=16, m=1
             "logits": np.concatenate(all_logits) if all_logits else np.zeros((0, C), np.float32)}
 
 
-def predict_wsis(sd, raster, mask, ph, pw, sh, sw, m=1.0, batch=16, tiles=None):
+def predict_wsis(sd, raster, mask, ph, pw, sh, sw, m=1.0, batch=16, tiles=None, scan_resize: int = 1):
     """utils/eval.py:22-81 for one slide, up to the argmax: the canvas lives at SCAN-LEVEL resolution (:44-47,
     tiles land unscaled, :56-60), is resized per class to the level-2 size == mask.shape (:66-71), then argmax (:81).
     ``m`` only enters the tile plan (foreground test of Dataset_wsi against the level-2 mask)."""
@@ -357,8 +423,8 @@ def predict_wsis(sd, raster, mask, ph, pw, sh, sw, m=1.0, batch=16, tiles=None):
     canvas = np.zeros((4, ih, iw), np.float64)
     for i in range(0, len(tiles), batch):
         chunk = tiles[i:i + batch]
-        y = model_forward(sd, "unet_seg", gather_tiles(raster, chunk, ph, pw)).numpy()
-        stitch(canvas, chunk, y, ph, pw, 1.0)
+        y = model_forward(sd, "unet_seg", gather_tiles(raster, chunk, ph, pw, scan_resize)).numpy()
+        stitch(canvas, chunk, y, ph, pw, 1.0, scan_resize)
     H2, W2 = mask.shape
     classes, pred = predict_wsis_scores(canvas, W2, H2)
     return {"tiles": tiles, "canvas": canvas, "pred": pred, "classes": classes}

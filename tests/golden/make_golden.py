@@ -12,6 +12,8 @@ Scenarios
   wsis_l2/l1  predict_wsis up to the argmax (scan_level 2: resize is the identity; scan_level 1: cv2.resize 4x down)
   resnet_fwd  resnets_shift.ResNet.forward (multi-patch) on a [2,16,3,64,64] batch
   normalise   standard_augmentor(True) on a PIL tile
+  seg_resize2/3, wsis_resize2   predict_tumorbed / predict_wsis with scan_resize = 2 / 3 (PIL resize of the tiles,
+              nearest re-interpolation of the logits); non-square tile for scan_resize 3
 """
 import os
 import sys
@@ -80,7 +82,7 @@ def plans():
     np.savez_compressed(os.path.join(OUT, "plan.npz"), **out)
 
 
-def predict(name, arch, ih, iw, ph, pw, sh, sw, mode, scan_level=2, seed=0):
+def predict(name, arch, ih, iw, ph, pw, sh, sw, mode, scan_level=2, seed=0, scan_resize=1):
     sd = O.random_state_dict("resnet18" if arch == "resnet18_cls" else "unet", seed)
     if arch == "resnet18_cls":
         model = H.ResNetClsAdapter(H.make_reference_resnet(sd))
@@ -95,10 +97,10 @@ def predict(name, arch, ih, iw, ph, pw, sh, sw, mode, scan_level=2, seed=0):
         mask = small_mask(ih // 4, iw // 4, 77)
     with tempfile.TemporaryDirectory() as td:
         r = H.run_reference_predict_tumorbed(model, levels, mask, td, ph=ph, pw=pw, sh=sh, sw=sw, mode=mode,
-                                             scan_level=scan_level, batch=7)
+                                             scan_level=scan_level, batch=7, scan_resize=scan_resize)
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
-        geom=np.array([ih, iw, ph, pw, sh, sw, scan_level], np.int32), seed=np.array(seed),
+        geom=np.array([ih, iw, ph, pw, sh, sw, scan_level], np.int32), seed=np.array(seed), scan_resize=np.array(scan_resize),
         mask=mask, tiles=np.array(r["tiles"], np.int32).reshape(-1, 2),
         canvas=r["canvas"].astype(np.float32), classes=r["classes"], heatmap=r["heatmap"],
         probs=r["probs"].astype(np.float32))
@@ -106,7 +108,7 @@ def predict(name, arch, ih, iw, ph, pw, sh, sw, mode, scan_level=2, seed=0):
           "classes hist", np.bincount(r["classes"].ravel(), minlength=4))
 
 
-def predict_wsis(name, ih, iw, ph, pw, sh, sw, scan_level, seed):
+def predict_wsis(name, ih, iw, ph, pw, sh, sw, scan_level, seed, scan_resize=1):
     """utils/eval.py:22-81 predict_wsis up to the argmax: canvas at scan-level resolution, cv2.resize to level 2."""
     sd = O.random_state_dict("unet", seed)
     model = H.UnetAdapter(sd)
@@ -118,11 +120,12 @@ def predict_wsis(name, ih, iw, ph, pw, sh, sw, scan_level, seed):
         levels = {scan_level: raster, 2: box_down(raster, 4)}
         mask = small_mask(ih // 4, iw // 4, 78)
     with tempfile.TemporaryDirectory() as td:
-        r = H.run_reference_predict_wsis(model, levels, mask, td, ph=ph, pw=pw, sh=sh, sw=sw, scan_level=scan_level, batch=5)
+        r = H.run_reference_predict_wsis(model, levels, mask, td, ph=ph, pw=pw, sh=sh, sw=sw, scan_level=scan_level, batch=5,
+                                         scan_resize=scan_resize)
     pred = r["pred"]
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
-        geom=np.array([ih, iw, ph, pw, sh, sw, scan_level], np.int32), seed=np.array(seed), mask=mask,
+        geom=np.array([ih, iw, ph, pw, sh, sw, scan_level], np.int32), seed=np.array(seed), mask=mask, scan_resize=np.array(scan_resize),
         tiles=np.array(r["tiles"], np.int32).reshape(-1, 2), pred=pred.astype(np.float32),
         classes=np.argmax(pred, 0).astype(np.uint8))
     print(name, "tiles", len(r["tiles"]), "pred", pred.shape, "classes hist", np.bincount(np.argmax(pred, 0).ravel(), minlength=4))
@@ -163,7 +166,17 @@ def normalise():
     np.savez_compressed(os.path.join(OUT, "normalise.npz"), tile=tile, out=t.numpy())
 
 
+def resize_only():
+    """The scan_resize goldens alone (ph, pw = tile * scan_resize as eval_tumorbed.py:39-40 sets them)."""
+    predict("seg_resize2", "unet_seg", 288, 352, 128, 128, 32, 32, "seg", seed=6, scan_resize=2)
+    predict_wsis("wsis_resize2", 288, 352, 128, 128, 64, 32, 2, 7, scan_resize=2)
+    predict("seg_resize3", "unet_seg", 300, 330, 96, 192, 48, 64, "seg", seed=9, scan_resize=3)
+
+
 if __name__ == "__main__":
+    if "--resize-only" in sys.argv:
+        resize_only()
+        sys.exit(0)
     plans()
     normalise()
     resnet_fwd()
@@ -173,3 +186,4 @@ if __name__ == "__main__":
     reg_tta()
     predict_wsis("wsis_l2", 160, 192, 64, 64, 32, 32, 2, 4)
     predict_wsis("wsis_l1", 256, 320, 64, 64, 32, 32, 1, 5)
+    resize_only()

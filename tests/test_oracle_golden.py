@@ -48,14 +48,17 @@ def test_resnet_multipatch_forward(golden_dir):
 
 @pytest.mark.parametrize("name,arch,mode", [("cls_small", "resnet18_cls", "cls"),
                                             ("cls_m4", "resnet18_cls", "cls"),
-                                            ("seg_small", "unet_seg", "seg")])
+                                            ("seg_small", "unet_seg", "seg"),
+                                            ("seg_resize2", "unet_seg", "seg"),
+                                            ("seg_resize3", "unet_seg", "seg")])
 def test_predict_tumorbed_matches_reference(golden_dir, name, arch, mode):
     g = _load(golden_dir, name)
     ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g["geom"])
     m = 1.0 if lvl == 2 else 0.25
     sd = O.random_state_dict("resnet18" if arch == "resnet18_cls" else "unet", int(g["seed"]))
     raster = synth.synth_slide(ih, iw, 1234)
-    r = O.predict_tumorbed(sd, arch, raster, g["mask"], ph, pw, sh, sw, mode, batch=16, m=m)
+    rs = int(g["scan_resize"]) if "scan_resize" in g else 1
+    r = O.predict_tumorbed(sd, arch, raster, g["mask"], ph, pw, sh, sw, mode, batch=16, m=m, scan_resize=rs)
     np.testing.assert_array_equal(np.array(r["tiles"], np.int32).reshape(-1, 2), g["tiles"])
     np.testing.assert_allclose(r["canvas"], g["canvas"], rtol=1e-4, atol=2e-4)
     # probabilities within the north-star fp32 tolerance, layout identical
@@ -79,7 +82,25 @@ def test_cv2_resize_restatement(shape):
     np.testing.assert_allclose(O.cv2_resize_linear(a, W2, H2), cv2.resize(a, (W2, H2)), rtol=0, atol=2e-14)
 
 
-@pytest.mark.parametrize("name", ["wsis_l2", "wsis_l1"])
+@pytest.mark.parametrize("shape", [(128, 128, 64, 64), (96, 192, 32, 64), (100, 150, 50, 50), (64, 64, 64, 64), (60, 90, 20, 30), (1024, 40, 512, 20),
+                                   (50, 70, 17, 31), (33, 47, 66, 94)])
+def test_pil_resize_restatement(shape):
+    """scan_resize (utils/dataset.py:180-181): the oracle restates PIL.Image.resize at its default filter — pinned, bit for
+    bit, against the Pillow of this image (the same one on the GPU box), and so are the host tables the CUDA path uses."""
+    from PIL import Image
+    from wsi_segmentation_pipeline_b200 import capi
+    H, W, oh, ow = shape
+    a = np.random.default_rng(H * ow).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    a[: H // 3] = (a[: H // 3] // 128) * 255                                # saturated edges: overshoot must clip like PIL's
+    np.testing.assert_array_equal(O.pil_resize(a, ow, oh), np.asarray(Image.fromarray(a).resize((ow, oh))))
+    for n_in, n_out in ((W, ow), (H, oh)):
+        b, k = capi.resample_coeffs(n_in, n_out)
+        b0, k0 = O.pil_resample_coeffs(n_in, n_out)
+        np.testing.assert_array_equal(b, b0)
+        np.testing.assert_array_equal(k, k0)
+
+
+@pytest.mark.parametrize("name", ["wsis_l2", "wsis_l1", "wsis_resize2"])
 def test_predict_wsis_matches_reference(golden_dir, name):
     """A9: predict_wsis (utils/eval.py:22-81) run unmodified up to pred_to_mask by oracle/ref_harness.py."""
     g = _load(golden_dir, name)
@@ -87,7 +108,7 @@ def test_predict_wsis_matches_reference(golden_dir, name):
     m = 1.0 if lvl == 2 else 0.25
     sd = O.random_state_dict("unet", int(g["seed"]))
     raster = synth.synth_slide(ih, iw, 4321)
-    r = O.predict_wsis(sd, raster, g["mask"], ph, pw, sh, sw, m=m, batch=16)
+    r = O.predict_wsis(sd, raster, g["mask"], ph, pw, sh, sw, m=m, batch=16, scan_resize=int(g["scan_resize"]) if "scan_resize" in g else 1)
     np.testing.assert_array_equal(np.array(r["tiles"], np.int32).reshape(-1, 2), g["tiles"])
     assert r["pred"].shape == g["pred"].shape == (4,) + g["mask"].shape
     np.testing.assert_allclose(r["pred"], g["pred"], rtol=1e-4, atol=2e-4)

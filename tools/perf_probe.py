@@ -17,6 +17,7 @@ def main():
     stride = int(sys.argv[3]) if len(sys.argv) > 3 else 128
     arch = sys.argv[4] if len(sys.argv) > 4 else "unet"
     batch = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    resize = int(sys.argv[6]) if len(sys.argv) > 6 else 1        # scan_resize: windows of tile * resize pixels, stride as given
     ctx = capi.Context(0)
     sd = O.random_state_dict(arch, 0)
     ctx.load_state_dict(capi.ARCH_UNET_R18 if arch == "unet" else capi.ARCH_RESNET18, sd)
@@ -24,8 +25,8 @@ def main():
     ctx.set_option("stage_timing", 1)
     ctx.set_option("batch_tiles", batch)
     rgb = ctx.synth_slide(size, size, 1234)
-    tiles = capi.plan_tiles(size, size, tile, tile, stride, stride)
-    sl = ctx.slide_desc(rgb, size, size, tile, tile)
+    tiles = capi.plan_tiles(size, size, tile * resize, tile * resize, stride, stride)
+    sl = ctx.slide_desc(rgb, size, size, tile * resize, tile * resize, resize=resize)
     for it in range(3):
         ctx.stage_reset()
         torch.cuda.synchronize()

@@ -35,7 +35,7 @@ SYMBOLS = (
     "wsi_ipc_alloc", "wsi_ipc_open", "wsi_ipc_close", "wsi_ipc_free",
     "wsi_morph", "wsi_tumor_bed", "wsi_overlay", "wsi_hull_rows", "wsi_host_register", "wsi_host_unregister",
     "wsi_tiff_open", "wsi_tiff_close", "wsi_tiff_last_error", "wsi_tiff_levels", "wsi_tiff_level_info", "wsi_tiff_unit_stream",
-    "wsi_tiff_read_rows",
+    "wsi_tiff_read_rows", "wsi_resample_ksize", "wsi_resample_coeffs",
 )
 
 
@@ -54,7 +54,7 @@ class SlideDesc(C.Structure):
                 ("ih", C.c_int64), ("iw", C.c_int64), ("row0", C.c_int64), ("rows", C.c_int64),
                 ("ph", C.c_int32), ("pw", C.c_int32), ("m", C.c_double),
                 ("H2", C.c_int64), ("W2", C.c_int64), ("own0", C.c_int64), ("own1", C.c_int64),
-                ("mask", C.c_void_p), ("mask_mem", C.c_int32)]
+                ("mask", C.c_void_p), ("mask_mem", C.c_int32), ("resize", C.c_int32)]
 
 
 class OutDesc(C.Structure):
@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
         "wsi_forward_batch_tta": (C.c_int, [vp, vp, i64, i32, i32, C.c_int, vp, C.c_int, vp]),
         "wsi_forward_patches": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp, C.c_int, vp]),
         "wsi_find_nuclei": (C.c_int, [vp, vp, i64, C.c_int, i64, i64, dbl, vp, C.c_int, vp]),
+        "wsi_resample_ksize": (C.c_int, [i32, i32]),
+        "wsi_resample_coeffs": (C.c_int, [i32, i32, vp, vp]),
         "wsi_plan_tiles_gpu": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, C.c_int, i64, i64, dbl, C.POINTER(C.POINTER(i32)),
                                          C.POINTER(i64), vp]),
     }
@@ -167,6 +169,19 @@ def plan_tiles(ih, iw, ph, pw, sh, sw, mask: Optional[np.ndarray] = None, m: flo
     finally:
         L.wsi_free(xy)
     return out
+
+
+def resample_coeffs(in_size: int, out_size: int):
+    """One axis of the scan_resize tile resize (PIL.Image.resize default = antialiased bicubic, utils/dataset.py:180-181):
+    (bounds int32 [out,2] = (first input sample, count), kk int32 [out,ksize] 22-bit fixed-point weights)."""
+    L = lib()
+    ks = L.wsi_resample_ksize(int(in_size), int(out_size))
+    if ks <= 0:
+        raise WsiError(-1, "bad resample sizes")
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ks), np.int32)
+    _check(L.wsi_resample_coeffs(int(in_size), int(out_size), _np_ptr(bounds), _np_ptr(kk)))
+    return bounds, kk
 
 
 def band_partition(ih, ph, sh, nranks) -> np.ndarray:
@@ -349,8 +364,9 @@ class Context:
     # ---- descriptors -------------------------------------------------------------------
     @staticmethod
     def slide_desc(raster, ih, iw, ph, pw, m=1.0, H2=None, W2=None, mask=None, row0=0, rows=0, own0=0, own1=0,
-                   row_stride=None):
-        """raster: u8 [rows, iw, 3] (numpy / torch CPU / torch CUDA); mask: u8 [own rows, W2] or None."""
+                   row_stride=None, resize=1):
+        """raster: u8 [rows, iw, 3] (numpy / torch CPU / torch CUDA); mask: u8 [own rows, W2] or None.
+        resize: myargs scan_resize — ph x pw = (tile_h * resize) x (tile_w * resize) windows, PIL-resized to the tile."""
         d = SlideDesc()
         p, mem, k1 = _ptr_and_mem(raster)
         d.rgb, d.rgb_mem = p, mem
@@ -362,6 +378,7 @@ class Context:
         d.own0, d.own1 = int(own0), int(own1)
         p, mem, k2 = _ptr_and_mem(mask)
         d.mask, d.mask_mem = p, mem
+        d.resize = int(resize)
         d._keep = (k1, k2)
         return d
 
@@ -551,7 +568,8 @@ class Context:
         import torch
         tiles_xy = np.ascontiguousarray(tiles_xy, dtype=np.int32).reshape(-1, 2)
         n = tiles_xy.shape[0]
-        shape = {HEAD_SEG: (n, 4, slide.ph, slide.pw), HEAD_CLS: (n, 4), HEAD_REG: (n, 1), HEAD_FEATURES: (n, 512)}[head]
+        r = max(1, slide.resize)
+        shape = {HEAD_SEG: (n, 4, slide.ph // r, slide.pw // r), HEAD_CLS: (n, 4), HEAD_REG: (n, 1), HEAD_FEATURES: (n, 512)}[head]
         y = torch.empty(shape, dtype=torch.float32, device=torch.device("cuda", self.device) if device_out else "cpu")
         _check(self._lib.wsi_forward_tiles(self._h, C.byref(slide), _np_ptr(tiles_xy), n, int(head), C.c_void_p(y.data_ptr()),
                                            MEM_DEVICE if device_out else MEM_HOST, _stream_ptr(stream)), self._h)
@@ -613,8 +631,9 @@ class Context:
         tiles_xy = np.ascontiguousarray(tiles_xy, dtype=np.int32).reshape(-1, 2)
         n = tiles_xy.shape[0]
         dev = torch.device("cuda", self.device)
-        norm = torch.empty((n, 3, slide.ph, slide.pw), dtype=torch.float32, device=dev) if want_norm else None
-        padded = torch.empty((n, slide.ph + 6, slide.pw + 8, 4), dtype=torch.bfloat16, device=dev) if want_padded else None
+        r = max(1, slide.resize)
+        norm = torch.empty((n, 3, slide.ph // r, slide.pw // r), dtype=torch.float32, device=dev) if want_norm else None
+        padded = torch.empty((n, slide.ph // r + 6, slide.pw // r + 8, 4), dtype=torch.bfloat16, device=dev) if want_padded else None
         _check(self._lib.wsi_debug_gather(self._h, C.byref(slide), _np_ptr(tiles_xy), n, C.c_void_p(norm.data_ptr()) if want_norm else None,
                                           C.c_void_p(padded.data_ptr()) if want_padded else None, _stream_ptr(None)), self._h)
         if not want_norm:

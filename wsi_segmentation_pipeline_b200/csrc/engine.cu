@@ -100,6 +100,9 @@ struct wsi_ctx {
   std::vector<EventSpan> spans;
   std::vector<cudaEvent_t> event_pool;
   // scratch reused across slides
+  // scan_resize != 1: per-axis resize tables (PIL bicubic, wsi_resample_coeffs) and the resized u8 tiles of one batch
+  DevBuf rs_hb, rs_hk, rs_vb, rs_vk, rs_tmp, rs_tiles, rs_xy;
+  int rs_key[4] = {0, 0, 0, 0}, rs_hks = 0, rs_vks = 0;
   DevBuf raster, maskbuf, logit_ring, classes, heatmap, tiles_dev, rect_tx, rect_rowy, rect_rowstart, rect_rows, rect_bx, rect_by, rect_cellx, rect_celly, cls_cells, tile_logits, scratch_f32, counts;
   // copy streams: chunked raster upload / strip-wise output download overlap the compute on the caller's stream
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -590,7 +593,15 @@ static void validate_slide(const wsi_slide_desc* sl) {
   WSI_REQUIRE(sl->row_stride >= 3 * sl->iw, WSI_ERR_INVALID, "row_stride %lld < 3*iw", (long long)sl->row_stride);
   WSI_REQUIRE(sl->row0 >= 0 && sl->rows >= 0 && sl->row0 + sl->rows <= sl->ih, WSI_ERR_INVALID, "raster rows [%lld,+%lld) outside the slide",
               (long long)sl->row0, (long long)sl->rows);
+  WSI_REQUIRE(sl->resize >= 0 && sl->resize <= 16, WSI_ERR_INVALID, "resize %d outside [0, 16]", sl->resize);
+  if (sl->resize > 1)
+    WSI_REQUIRE(sl->ph % sl->resize == 0 && sl->pw % sl->resize == 0 && sl->pw * 3 <= 48 * 1024, WSI_ERR_INVALID,
+                "resize %d: the tile %d x %d must be a multiple of it (ph = tile_h * scan_resize, eval_tumorbed.py:39-40) and at most 16384 wide",
+                sl->resize, sl->ph, sl->pw);
 }
+
+// scan_resize (myargs.py:115): the network sees (ph / r) x (pw / r) tiles
+static inline int slide_resize(const wsi_slide_desc* sl) { return sl->resize > 1 ? sl->resize : 1; }
 
 // ordering events (no timing), reused call after call
 static cudaEvent_t order_event(wsi_ctx* c) {
@@ -683,6 +694,48 @@ static void ensure_lut(wsi_ctx* c) {
   CUDA_CHECK(cudaDeviceSynchronize());
 }
 
+static void ensure_resample(wsi_ctx* c, int ph, int pw, int th, int tw) {
+  if (c->rs_key[0] == ph && c->rs_key[1] == pw && c->rs_key[2] == th && c->rs_key[3] == tw) return;
+  // weight rows padded with zeros to a multiple of 4 taps: the kernels fetch them with 16-byte loads
+  auto table = [](int in_size, int out_size, std::vector<int32_t>& b, std::vector<int32_t>& k) {
+    const int ks = wsi_resample_ksize(in_size, out_size), ksp = (ks + 3) & ~3;
+    std::vector<int32_t> raw((size_t)out_size * ks);
+    b.assign((size_t)out_size * 2, 0);
+    WSI_REQUIRE(wsi_resample_coeffs(in_size, out_size, b.data(), raw.data()) == WSI_OK, WSI_ERR_INVALID, "resize tables");
+    k.assign((size_t)out_size * ksp, 0);
+    for (int i = 0; i < out_size; ++i) memcpy(&k[(size_t)i * ksp], &raw[(size_t)i * ks], (size_t)ks * sizeof(int32_t));
+    return ksp;
+  };
+  std::vector<int32_t> hb, hk, vb, vk;
+  const int hks = table(pw, tw, hb, hk), vks = table(ph, th, vb, vk);
+  CUDA_CHECK(cudaDeviceSynchronize());                       // an earlier call may still read the old tables
+  upload(c->rs_hb, hb); upload(c->rs_hk, hk); upload(c->rs_vb, vb); upload(c->rs_vk, vk);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  c->rs_hks = hks; c->rs_vks = vks;
+  c->rs_key[0] = ph; c->rs_key[1] = pw; c->rs_key[2] = th; c->rs_key[3] = tw;
+}
+
+// K0 (+ K0r): n tiles of the raster -> the stem operand (and / or the fp32 normalised tiles).  With scan_resize r > 1 the
+// pw x ph windows are first resized to (pw / r) x (ph / r) u8 tiles exactly as PIL does it (utils/dataset.py:180-181).
+static void gather_batch(wsi_ctx* c, const wsi_slide_desc* sl, const uint8_t* rgb, int64_t rstride, const int32_t* xy_dev, int n, bf16* padded,
+                         float* norm_out, int planes, int64_t plane_stride, cudaStream_t s) {
+  const int r = slide_resize(sl);
+  if (r == 1) {
+    launch_gather(rgb, rstride, sl->row0, xy_dev, n, sl->ph, sl->pw, c->lut.as<float>(), padded, norm_out, s, &c->lc, planes, plane_stride);
+    return;
+  }
+  const int th = sl->ph / r, tw = sl->pw / r;
+  ensure_resample(c, sl->ph, sl->pw, th, tw);
+  c->rs_tmp.alloc((size_t)n * sl->ph * tw * 3);
+  c->rs_tiles.alloc((size_t)n * th * tw * 3);
+  c->rs_xy.alloc((size_t)n * 2 * sizeof(int32_t));
+  launch_resample_tiles(rgb, rstride, sl->row0, xy_dev, n, sl->ph, sl->pw, th, tw, c->rs_hb.as<int32_t>(), c->rs_hk.as<int32_t>(), c->rs_hks,
+                        c->rs_vb.as<int32_t>(), c->rs_vk.as<int32_t>(), c->rs_vks, c->rs_tmp.as<uint8_t>(), c->rs_tiles.as<uint8_t>(),
+                        c->rs_xy.as<int32_t>(), s, &c->lc);
+  launch_gather(c->rs_tiles.as<uint8_t>(), (int64_t)tw * 3, 0, c->rs_xy.as<int32_t>(), n, th, tw, c->lut.as<float>(), padded, norm_out, s, &c->lc,
+                planes, plane_stride);
+}
+
 // the hot path ------------------------------------------------------------------------------
 // Per slide / row band: sort the tiles by canvas origin; batches of tiles go gather -> network; SEG logits land in a
 // ring of the last few tile rows; whenever a run of canvas rows can receive no further tile (every later tile starts
@@ -701,6 +754,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   WSI_REQUIRE(own0 >= 0 && own1 >= own0 && own1 <= H2, WSI_ERR_INVALID, "bad owned rows");
   const int64_t orows = own1 - own0, plane = orows * W2;
   const int ph = sl->ph, pw = sl->pw;
+  const int rs = slide_resize(sl), th = ph / rs, tw = pw / rs;                            // th x tw: what the network sees
   const int64_t dx = (int64_t)(sl->m * (double)pw), dy = (int64_t)(sl->m * (double)ph);   // utils/eval.py:186
   if (head == WSI_HEAD_SEG)
     WSI_REQUIRE(dx == pw && dy == ph, WSI_ERR_UNSUPPORTED, "SEG needs m == 1 (the reference's slice-add requires equal shapes, utils/eval.py:213-215)");
@@ -821,6 +875,7 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   ri.R = (int32_t)rowy.size();
   ri.dx = (int32_t)dx;
   ri.dy = (int32_t)dy;
+  ri.up = (head == WSI_HEAD_SEG) ? rs : 1;
 
   SlideUpload up_r;
   if (T > 0) up_r = stage_raster(c, sl, rows_r, s);
@@ -860,11 +915,11 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
   fa.heat_mode = (head == WSI_HEAD_CLS) ? 1 : 0;
   fa.classes = cls_dev; fa.heatmap = heat_dev; fa.canvas_out = canvas_out; fa.probs_out = probs_out;
 
-  const int64_t B = auto_batch(c, ph, pw, std::max<int64_t>(T, 1));
-  NetPlan* plan = (T > 0) ? get_plan(c, head, (int)B, ph, pw) : nullptr;
+  const int64_t B = auto_batch(c, th, tw, std::max<int64_t>(T, 1));
+  NetPlan* plan = (T > 0) ? get_plan(c, head, (int)B, th, tw) : nullptr;
   const int cap = plan ? plan->cap : 1;
-  const double tile_px = (double)ph * pw;
-  const int64_t tile_elems = (int64_t)ph * pw * 4;
+  const double tile_px = (double)th * tw;
+  const int64_t tile_elems = (int64_t)th * tw * 4;
 
   // tile rows [r_lo, r_hi) that can touch canvas rows [ya, yb)
   auto row_range = [&](int64_t ya, int64_t yb, int* r_lo, int* r_hi) {
@@ -915,9 +970,11 @@ static void run_slide(wsi_ctx* c, const wsi_slide_desc* sl, const int32_t* tiles
       int64_t row_end = 0;
       for (int64_t i = t0; i < t0 + n; ++i) row_end = std::max<int64_t>(row_end, (int64_t)tiles_xy[2 * order[i] + 1] + ph - sl->row0);
       up_r.need(s, row_end);
-      StageScope scope(c, s, ST_GATHER, 9.0 * n * tile_px);
-      launch_gather(up_r.rgb, up_r.stride, sl->row0, c->tiles_dev.as<int32_t>() + 2 * t0, n, ph, pw, c->lut.as<float>(), plan->in_pad.as<bf16>(),
-                    nullptr, s, &c->lc, plan->in_planes(), plan->in_plane_stride());
+      // algorithmic bytes: 3 read + 8 (or 24) written per network pixel; resize: + the window read, the half-resized tile
+      // written and read, the resized tile written and read
+      StageScope scope(c, s, ST_GATHER, 9.0 * n * tile_px + (rs > 1 ? 3.0 * n * ((double)ph * pw + 2.0 * ph * tw + tile_px) : 0.0));
+      gather_batch(c, sl, up_r.rgb, up_r.stride, c->tiles_dev.as<int32_t>() + 2 * t0, n, plan->in_pad.as<bf16>(), nullptr, plan->in_planes(),
+                   plan->in_plane_stride(), s);
     }
     if (head == WSI_HEAD_SEG) {
       plan->set_logits_base(c->logit_ring.as<float>() + (t0 % ring_cap) * tile_elems);
@@ -1246,16 +1303,17 @@ int wsi_forward_tiles(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* 
   const int64_t rows_r = (slide->rows == 0 && slide->row0 == 0) ? slide->ih : slide->rows;
   check_tiles(slide, tiles_xy, n_tiles, rows_r);
   ensure_lut(ctx);
-  NetPlan* plan = get_plan(ctx, head, (int)n_tiles, slide->ph, slide->pw);
+  const int rs = slide_resize(slide);
+  NetPlan* plan = get_plan(ctx, head, (int)n_tiles, slide->ph / rs, slide->pw / rs);
   int64_t rstride = 0;
   const uint8_t* rgb = stage_raster_all(ctx, slide, rows_r, &rstride, s);
   std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * n_tiles);
   upload(ctx->tiles_dev, xy, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
   {
-    StageScope scope(ctx, s, ST_GATHER, 9.0 * n_tiles * slide->ph * slide->pw);
-    launch_gather(rgb, rstride, slide->row0, ctx->tiles_dev.as<int32_t>(), (int)n_tiles, slide->ph, slide->pw, ctx->lut.as<float>(),
-                  plan->in_pad.as<bf16>(), nullptr, s, &ctx->lc, plan->in_planes(), plan->in_plane_stride());
+    StageScope scope(ctx, s, ST_GATHER, 9.0 * n_tiles * (slide->ph / rs) * (slide->pw / rs));
+    gather_batch(ctx, slide, rgb, rstride, ctx->tiles_dev.as<int32_t>(), (int)n_tiles, plan->in_pad.as<bf16>(), nullptr, plan->in_planes(),
+                 plan->in_plane_stride(), s);
   }
   forward_common(ctx, plan, (int)n_tiles, head, out, mem, s);
   WSI_API_END(ctx)
@@ -1574,9 +1632,9 @@ int wsi_debug_gather(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* t
   std::vector<int32_t> xy(tiles_xy, tiles_xy + 2 * (size_t)n);
   upload(ctx->tiles_dev, xy, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
-  if (padded_out) CUDA_CHECK(cudaMemsetAsync(padded_out, 0, (size_t)n * (slide->ph + 6) * (slide->pw + 8) * 8, s));
-  launch_gather(rgb, rstride, slide->row0, ctx->tiles_dev.as<int32_t>(), n, slide->ph, slide->pw, ctx->lut.as<float>(),
-                static_cast<bf16*>(padded_out), norm_out, s, &ctx->lc);
+  const int rs = slide_resize(slide);
+  if (padded_out) CUDA_CHECK(cudaMemsetAsync(padded_out, 0, (size_t)n * (slide->ph / rs + 6) * (slide->pw / rs + 8) * 8, s));
+  gather_batch(ctx, slide, rgb, rstride, ctx->tiles_dev.as<int32_t>(), n, static_cast<bf16*>(padded_out), norm_out, 1, 0, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
   WSI_API_END(ctx)
 }

@@ -140,6 +140,140 @@ void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const i
   if (lc) lc->n++;
 }
 
+// =============================================================================================
+// K0r: tile resize of the scan_resize != 1 branch — `image.resize((tile_w, tile_h))`, utils/dataset.py:180-181
+//   = PIL.Image.resize at its default filter on the pw x ph window of every tile (a standalone RGB image): antialiased
+//   bicubic in 22-bit fixed point, horizontal pass first, u8 intermediate (libImaging/Resample.c, 8bpc paths).  The
+//   per-axis windows / weights come from the host (wsi_resample_coeffs, planner.cpp) and are the same for every tile.
+//   Integer arithmetic end to end: bit-exact with PIL.  Output: u8 tiles [n][th][tw][3], which the gather kernel then
+//   reads as a raster of stacked tiles at origins (0, i * th) written to out_xy.
+// =============================================================================================
+__device__ __forceinline__ uint8_t resample_clip8(int v) {
+  v >>= 22;                                             // PRECISION_BITS = 32 - 8 - 2; arithmetic shift like the C code
+  return (uint8_t)min(max(v, 0), 255);
+}
+
+// Weight rows are padded to KS = a multiple of 4 taps (zeros), so a thread fetches the weights of its output sample with
+// 16-byte loads and runs 4 taps x 3 channels per loop trip; taps past the window read the zero-filled tail of the staged row
+// (h) or a clamped row (v) under a zero weight.  Both passes are instruction-bound (one byte load + one IMAD per tap and
+// channel), not HBM-bound: the window bytes are read once, the half-resized tile is written and read once.
+__global__ void __launch_bounds__(128) resample_h_kernel(const uint8_t* __restrict__ rgb, int64_t row_stride, int64_t row0,
+                                                          const int32_t* __restrict__ tiles_xy, int n_tiles, int ph, int pw, int tw,
+                                                          const int32_t* __restrict__ bounds, const int4* __restrict__ kk, int ks4,
+                                                          uint8_t* __restrict__ tmp) {
+  extern __shared__ __align__(16) uint8_t s_raw[];      // one window row (pw * 3 bytes) + 12 * ks4 + 8 zero bytes + 4 bytes of alignment slack
+  const int row_bytes = pw * 3;
+  const int64_t n_jobs = (int64_t)n_tiles * ph;
+  for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    const int t = (int)(job / ph), r = (int)(job - (int64_t)t * ph);
+    const int x0 = __ldg(tiles_xy + 2 * t), y0 = __ldg(tiles_xy + 2 * t + 1);
+    const uint8_t* src = rgb + (int64_t)(y0 + r - row0) * row_stride + (int64_t)x0 * 3;
+    // The raster has no alignment contract: bytes up to the first 4-byte boundary of the source, whole words, tail bytes.
+    // The row is staged at the same offset modulo 4, so the word loads are stored as words.
+    const int head = (int)((4 - (reinterpret_cast<uintptr_t>(src) & 3)) & 3);
+    uint8_t* s_row = s_raw + ((4 - head) & 3);
+    __syncthreads();                                             // the previous job's readers are done
+    {
+      const int words = (row_bytes - head) >> 2;
+      if (threadIdx.x < head) s_row[threadIdx.x] = __ldg(src + threadIdx.x);
+      const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src + head);
+      uint32_t* dst4 = reinterpret_cast<uint32_t*>(s_row + head);
+      for (int i = threadIdx.x; i < words; i += blockDim.x) dst4[i] = __ldg(src4 + i);
+      const int done = head + 4 * words;                         // tail bytes, then the zero weights' bytes
+      for (int i = done + threadIdx.x; i < row_bytes + 12 * ks4 + 8; i += blockDim.x) s_row[i] = (i < row_bytes) ? __ldg(src + i) : (uint8_t)0;
+    }
+    __syncthreads();
+    uint8_t* dst = tmp + job * (int64_t)tw * 3;
+    const int off = (4 - head) & 3;
+    for (int xx = threadIdx.x; xx < tw; xx += blockDim.x) {
+      // The window of 4 * ks4 pixels starts at an arbitrary byte of the staged row.  Byte loads would make the kernel
+      // LSU-bound (36 LDS.U8 per output pixel at 9 taps): aligned words + a funnel shift put the window on word boundaries,
+      // then one PRMT per byte (ALU pipe) feeds the IMAD.
+      const int b = off + __ldg(bounds + 2 * xx) * 3;
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_raw) + (b >> 2);
+      const int sh = (b & 3) * 8;
+      const int4* k = kk + (int64_t)xx * ks4;
+      int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+      uint32_t w0 = wp[0];
+#define WSI_B(v, i) ((int)__byte_perm((v), 0u, 0x4440u + (i)))
+      for (int q = 0; q < ks4; ++q, wp += 3) {
+        const int4 c = __ldg(k + q);
+        const uint32_t w1 = wp[1], w2 = wp[2], w3 = wp[3];
+        const uint32_t A0 = __funnelshift_r(w0, w1, sh), A1 = __funnelshift_r(w1, w2, sh), A2 = __funnelshift_r(w2, w3, sh);
+        a0 += WSI_B(A0, 0) * c.x + WSI_B(A0, 3) * c.y + WSI_B(A1, 2) * c.z + WSI_B(A2, 1) * c.w;
+        a1 += WSI_B(A0, 1) * c.x + WSI_B(A1, 0) * c.y + WSI_B(A1, 3) * c.z + WSI_B(A2, 2) * c.w;
+        a2 += WSI_B(A0, 2) * c.x + WSI_B(A1, 1) * c.y + WSI_B(A2, 0) * c.z + WSI_B(A2, 3) * c.w;
+        w0 = w3;
+      }
+#undef WSI_B
+      dst[3 * xx] = resample_clip8(a0); dst[3 * xx + 1] = resample_clip8(a1); dst[3 * xx + 2] = resample_clip8(a2);
+    }
+  }
+}
+
+// VEC: the half-resized rows are read as 32-bit words, four output bytes per thread (needs tw * 3 % 4 == 0)
+template <bool VEC>
+__global__ void __launch_bounds__(128) resample_v_kernel(const uint8_t* __restrict__ tmp, int n_tiles, int ph, int th, int tw,
+                                                          const int32_t* __restrict__ bounds, const int4* __restrict__ kk, int ks4,
+                                                          uint8_t* __restrict__ out, int32_t* __restrict__ out_xy) {
+  const int64_t n_jobs = (int64_t)n_tiles * th;
+  const int row = tw * 3;
+  for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    const int t = (int)(job / th), yy = (int)(job - (int64_t)t * th);
+    const int ymin = __ldg(bounds + 2 * yy);
+    const int4* k = kk + (int64_t)yy * ks4;
+    const uint8_t* src = tmp + (int64_t)t * ph * row;
+    uint8_t* dst = out + job * (int64_t)row;
+    if (VEC) {
+      for (int e = threadIdx.x; e < (row >> 2); e += blockDim.x) {
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21, a3 = 1 << 21;
+        for (int q = 0; q < ks4; ++q) {
+          const int4 c = __ldg(k + q);
+          const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int y = min(ymin + 4 * q + j, ph - 1);           // past the window: weight 0
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)y * row) + e);
+            a0 += (int)(v & 255u) * cc[j]; a1 += (int)((v >> 8) & 255u) * cc[j]; a2 += (int)((v >> 16) & 255u) * cc[j]; a3 += (int)(v >> 24) * cc[j];
+          }
+        }
+        const uint32_t o = (uint32_t)resample_clip8(a0) | ((uint32_t)resample_clip8(a1) << 8) | ((uint32_t)resample_clip8(a2) << 16) |
+                           ((uint32_t)resample_clip8(a3) << 24);
+        reinterpret_cast<uint32_t*>(dst)[e] = o;
+      }
+    } else {
+      for (int e = threadIdx.x; e < row; e += blockDim.x) {
+        int acc = 1 << 21;
+        for (int q = 0; q < ks4; ++q) {
+          const int4 c = __ldg(k + q);
+          const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc += (int)src[(int64_t)min(ymin + 4 * q + j, ph - 1) * row + e] * cc[j];
+        }
+        dst[e] = resample_clip8(acc);
+      }
+    }
+    if (yy == 0 && threadIdx.x == 0) { out_xy[2 * t] = 0; out_xy[2 * t + 1] = t * th; }
+  }
+}
+
+void launch_resample_tiles(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n, int ph, int pw, int th,
+                           int tw, const int32_t* hb, const int32_t* hk, int hks, const int32_t* vb, const int32_t* vk, int vks,
+                           uint8_t* tmp, uint8_t* out, int32_t* out_xy, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return;
+  // hks / vks: taps per weight row, padded by the caller to a multiple of 4; tmp / out: 4-byte aligned (device allocations)
+  const unsigned gh = (unsigned)std::min<int64_t>((int64_t)n * ph, 148 * 16), gv = (unsigned)std::min<int64_t>((int64_t)n * th, 148 * 16);
+  resample_h_kernel<<<gh, 128, (size_t)pw * 3 + 3 * hks + 16, s>>>(rgb, row_stride, row0, tiles_xy_dev, n, ph, pw, tw, hb,
+                                                              reinterpret_cast<const int4*>(hk), hks / 4, tmp);
+  CUDA_CHECK(cudaGetLastError());
+  if ((tw * 3) % 4 == 0)
+    resample_v_kernel<true><<<gv, 128, 0, s>>>(tmp, n, ph, th, tw, vb, reinterpret_cast<const int4*>(vk), vks / 4, out, out_xy);
+  else
+    resample_v_kernel<false><<<gv, 128, 0, s>>>(tmp, n, ph, th, tw, vb, reinterpret_cast<const int4*>(vk), vks / 4, out, out_xy);
+  CUDA_CHECK(cudaGetLastError());
+  if (lc) lc->n += 2;
+}
+
 // view: the test-time-augmentation views of predict_reg / predict_breastpathq (utils/eval.py:305-310, square tiles):
 //   0 image, 1 image.transpose(2, 3), 2 image.flip(2), 3 image.transpose(2, 3).flip(3) — folded into the read address
 __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ x, int h, int w, int view, bf16* __restrict__ padded, int planes,
@@ -558,25 +692,29 @@ __device__ __forceinline__ void for_each_candidate(const RectIndex& ri, int t_lo
 // flight.  Cost split by elimination: float accumulation instead of double -0.9 ms of 13.3, float finalise -2.0 ms,
 // both -3.4 ms (3.55 TB/s): the float64 arithmetic that makes the stage bit-compatible with the reference's float64
 // canvas costs a quarter of it; the rest is the 16-way gather itself (28 address streams per CTA, 92 strip launches).
-template <int PX>
+// UP: the scan_resize != 1 branch — F.interpolate(pred_src, (tile_h * r, tile_w * r)) at its default mode 'nearest'
+// (utils/eval.py:202-206) before the slice-add: canvas pixel (oy, ox) of a rectangle reads logit (oy / r, ox / r) of the
+// (dy / r) x (dx / r) tile (integer r: floor(dst * in / out) == dst / r).
+template <int PX, bool UP>
 __global__ void __launch_bounds__(256) stitch_finalise_seg_kernel(RectIndex ri, const float4* __restrict__ ring, int ring_cap, int t_lo, int t_hi,
                                                                    int r_lo, int r_hi, int y0, FinaliseArgs a) {
   const int Y = y0 + blockIdx.x;
   const int X0 = blockIdx.y * (256 * PX);
   const int Xt = X0 + threadIdx.x;
-  const int64_t tile_px = (int64_t)ri.dx * ri.dy;
+  const int lw = UP ? ri.dx / ri.up : ri.dx;                       // logit tile width
+  const int64_t tile_px = UP ? (int64_t)lw * (ri.dy / ri.up) : (int64_t)ri.dx * ri.dy;
   double s[PX][4];
 #pragma unroll
   for (int k = 0; k < PX; ++k) s[k][0] = s[k][1] = s[k][2] = s[k][3] = 0.0;
   for_each_candidate(ri, t_lo, t_hi, r_lo, r_hi, X0, 256 * PX, Y, [&](int i, int tx, int oy) {
-    const float4* src = ring + (int64_t)(i % ring_cap) * tile_px + (int64_t)oy * ri.dx;
+    const float4* src = ring + (int64_t)(i % ring_cap) * tile_px + (int64_t)(UP ? oy / ri.up : oy) * lw;
     float4 v[PX];
     bool hit[PX];
 #pragma unroll
     for (int k = 0; k < PX; ++k) {
       const int ox = Xt + 256 * k - tx;
       hit[k] = (ox >= 0) && (ox < ri.dx) && (Xt + 256 * k < a.W2);
-      if (hit[k]) v[k] = __ldg(src + ox);
+      if (hit[k]) v[k] = __ldg(src + (UP ? ox / ri.up : ox));
     }
 #pragma unroll
     for (int k = 0; k < PX; ++k)
@@ -599,7 +737,8 @@ void launch_stitch_finalise_seg(const RectIndex& ri, const float4* ring, int rin
   if (y1 <= y0 || a.W2 <= 0) return;
   constexpr int px = 2;
   dim3 grid((unsigned)(y1 - y0), (unsigned)ceil_div(a.W2, 256 * px));
-  stitch_finalise_seg_kernel<px><<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, r_lo, r_hi, (int)y0, a);
+  if (ri.up > 1) stitch_finalise_seg_kernel<px, true><<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, r_lo, r_hi, (int)y0, a);
+  else stitch_finalise_seg_kernel<px, false><<<grid, 256, 0, s>>>(ri, ring, ring_cap > 0 ? ring_cap : 1, t_lo, t_hi, r_lo, r_hi, (int)y0, a);
   CUDA_CHECK(cudaGetLastError());
   if (lc) lc->n++;
 }

@@ -25,6 +25,7 @@ struct RectIndex {
   const RowInfo* rows;      // [R]
   int32_t R;
   int32_t dx, dy;           // rectangle size on the canvas
+  int32_t up = 1;           // SEG: the logit tile is (dy / up) x (dx / up), nearest-upsampled onto the rectangle (scan_resize, utils/eval.py:202-206)
 };
 
 struct FinaliseArgs {
@@ -44,6 +45,11 @@ void launch_gather(const uint8_t* rgb, int64_t row_stride, int64_t row0, const i
                    int ph, int pw, const float* lut_dev /*f32 [3][256]*/, bf16* padded_or_null, float* norm_out_or_null,
                    cudaStream_t s, LaunchCounter* lc, int planes = 1, int64_t plane_stride = 0);
 // (planes == 3, fp32-emulated precision: three padded buffers plane_stride elements apart hold the bf16 expansion a + b + c)
+// K0r: PIL-exact bicubic resize of every tile window pw x ph -> tw x th (scan_resize != 1); tmp u8 [n][ph][tw][3] scratch,
+// out u8 [n][th][tw][3], out_xy int32 [n][2] = origins of the resized tiles inside `out` seen as one raster of width tw
+void launch_resample_tiles(const uint8_t* rgb, int64_t row_stride, int64_t row0, const int32_t* tiles_xy_dev, int n, int ph, int pw, int th,
+                           int tw, const int32_t* hb, const int32_t* hk, int hks, const int32_t* vb, const int32_t* vk, int vks,
+                           uint8_t* tmp, uint8_t* out, int32_t* out_xy, cudaStream_t s, LaunchCounter* lc);
 // normalised f32 NCHW -> padded bf16 tiles (nn.Module shim forward)
 void launch_pack_nchw(const float* x, int n, int h, int w, bf16* padded, cudaStream_t s, LaunchCounter* lc, int view = 0, int planes = 1,
                       int64_t plane_stride = 0);

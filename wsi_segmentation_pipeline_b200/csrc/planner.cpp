@@ -7,6 +7,7 @@
 // window [int(y*m) : +int(ph*m), int(x*m) : +int(pw*m)] with numpy's silent clipping at the mask
 // edge.  Geometries on which the reference itself raises (empty window -> ZeroDivisionError) or
 // indexes with a negative origin return WSI_ERR_DEGENERATE.
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -155,5 +156,67 @@ extern "C" int wsi_band_tiles(const int32_t* xy, int64_t n, int32_t ph, double m
   if (!keep.empty()) memcpy(buf, keep.data(), keep.size() * sizeof(int64_t));
   *idx_out = buf;
   *n_out = (int64_t)keep.size();
+  return WSI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Coefficients of the tile resize of the scan_resize != 1 branch (utils/dataset.py:180-181):
+// `image.resize((tile_w, tile_h))` = PIL.Image.resize at its default filter.  Pillow is a third-party dependency of
+// the reference (not vendored, no version pinned in the tree); this restates the published algorithm of the Pillow
+// installed in this image (12.2: default filter BICUBIC for RGB images; libImaging/Resample.c precompute_coeffs +
+// normalize_coeffs_8bpc): antialiased bicubic (a = -0.5), support 2 * max(scale, 1), window
+// [int(center - support + 0.5), int(center + support + 0.5)) clipped to the image, weights normalised in double and
+// rounded to 22-bit fixed point.  One axis; the tile is a standalone image, so every tile shares one table per axis.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+double bicubic_weight(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+}  // namespace
+
+extern "C" int wsi_resample_ksize(int32_t in_size, int32_t out_size) {
+  if (in_size <= 0 || out_size <= 0) return 0;
+  double fs = (double)in_size / (double)out_size;
+  if (fs < 1.0) fs = 1.0;
+  return (int)ceil(2.0 * fs) * 2 + 1;
+}
+
+extern "C" int wsi_resample_coeffs(int32_t in_size, int32_t out_size, int32_t* bounds /*[out_size][2]*/, int32_t* kk /*[out_size][ksize]*/) {
+  if (in_size <= 0 || out_size <= 0 || !bounds || !kk) return WSI_ERR_INVALID;
+  const int precision_bits = 32 - 8 - 2;
+  const double scale = (double)in_size / (double)out_size;
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * fs;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  const double ss = 1.0 / fs;
+  std::vector<double> k((size_t)ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    int x = 0;
+    for (; x < xmax; ++x) {
+      const double w = bicubic_weight((x + xmin - center + 0.5) * ss);
+      k[(size_t)x] = w;
+      ww += w;
+    }
+    for (int i = 0; i < xmax; ++i)
+      if (ww != 0.0) k[(size_t)i] /= ww;
+    for (; x < ksize; ++x) k[(size_t)x] = 0.0;
+    for (int i = 0; i < ksize; ++i) {
+      const double v = k[(size_t)i];
+      kk[(size_t)xx * ksize + i] = (v < 0) ? (int)(-0.5 + v * (1 << precision_bits)) : (int)(0.5 + v * (1 << precision_bits));
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
   return WSI_OK;
 }

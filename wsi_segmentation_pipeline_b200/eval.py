@@ -42,8 +42,21 @@ def _merge_args(args):
     return a
 
 
-def run_slide(ctx: capi.Context, entry: dict, params, mode: str, **kw) -> dict:
-    """One slide through the CUDA path.  entry: a ``Dataset_wsis.wsis[key]`` dict."""
+def _scan_resize(a, params) -> int:
+    """myargs.py:115 (type=int).  The Dataset params must have been built as the reference's scripts build them:
+    ph, pw = tile_h * scan_resize, tile_w * scan_resize (eval_tumorbed.py:39-40)."""
+    rs = int(a.scan_resize)
+    if rs < 1:
+        raise ValueError(f"scan_resize must be a positive integer (got {a.scan_resize})")
+    if rs != 1 and (params.ph % rs or params.pw % rs):
+        raise ValueError(f"scan_resize={rs}: params.ph/pw ({params.ph}, {params.pw}) must be tile_h/tile_w * scan_resize")
+    return rs
+
+
+def run_slide(ctx: capi.Context, entry: dict, params, mode: str, scan_resize: int = 1, **kw) -> dict:
+    """One slide through the CUDA path.  entry: a ``Dataset_wsis.wsis[key]`` dict.  scan_resize (myargs.py:115):
+    ``params.ph/pw`` are tile * scan_resize (eval_tumorbed.py:39-40); the windows are resized like PIL does and the
+    logits re-interpolated (nearest) inside ``wsi_run_slide``."""
     it = entry["iterator"]
     scan = entry["scan"]
     raster = it.raster()
@@ -51,7 +64,7 @@ def run_slide(ctx: capi.Context, entry: dict, params, mode: str, **kw) -> dict:
     W2, H2 = scan.level_dimensions[2]                          # utils/eval.py:182
     mask = entry.get("mask")
     mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-    sl = ctx.slide_desc(raster, ih, iw, params.ph, params.pw, m=it.m, H2=H2, W2=W2, mask=mask)
+    sl = ctx.slide_desc(raster, ih, iw, params.ph, params.pw, m=it.m, H2=H2, W2=W2, mask=mask, resize=scan_resize)
     return ctx.run_slide(sl, it.tiles, capi.HEAD_SEG if mode == "seg" else capi.HEAD_CLS, **kw)
 
 
@@ -59,8 +72,10 @@ def predict_tumorbed(model, dataset, ep, mode: str = "seg", args=None, return_ou
     """utils/eval.py:155-286.  Returns {key: {'classes': u8 [H2,W2], 'heatmap': u8 [H2,W2]}}."""
     assert mode in ("seg", "cls")
     a = _merge_args(args)
-    if a.scan_resize != 1:
-        raise NotImplementedError("scan_resize != 1 (nearest re-interpolation of tiles, utils/eval.py:202-206) is not on the CUDA path")
+    rs = _scan_resize(a, dataset.params)
+    if rs != 1 and mode == "cls":
+        # the reference fails here too: F.interpolate on the [B, C] classifier output (utils/eval.py:202-206)
+        raise ValueError("scan_resize != 1 with mode='cls': F.interpolate needs (N, C, d1, d2) input (utils/eval.py:202-206 raises)")
     ctx = _engine_of(model)
     ctx.set_class_probs(a.class_probs)
     if hasattr(model, "eval"):
@@ -73,7 +88,7 @@ def predict_tumorbed(model, dataset, ep, mode: str = "seg", args=None, return_ou
         entry = dataset.wsis[key]
         if entry is None:
             continue
-        r = run_slide(ctx, entry, dataset.params, mode)
+        r = run_slide(ctx, entry, dataset.params, mode, scan_resize=rs)
         heat, classes = r["heatmap"].numpy(), r["classes"].numpy()
         if save:
             from PIL import Image
@@ -122,8 +137,7 @@ def predict_wsis(model, dataset, ep, args=None):
     Not mirrored: the ground-truth scores, tumour-bed morphology and colour-mask PNG after the
     argmax — ``pred_to_mask`` (utils/preprocessing.py:186-189) raises in the reference itself."""
     a = _merge_args(args)
-    if a.scan_resize != 1:
-        raise NotImplementedError("scan_resize != 1 (utils/eval.py:52-55) is not on the CUDA path")
+    rs = _scan_resize(a, dataset.params)
     ctx = _engine_of(model)
     ctx.set_class_probs([0.0, 0.0, 0.0, 0.0])
     if hasattr(model, "eval"):
@@ -138,7 +152,7 @@ def predict_wsis(model, dataset, ep, args=None):
         ih, iw = raster.shape[:2]
         W2, H2 = scan.level_dimensions[2]
         # the canvas lives at scan-level resolution: tiles land at (x, y) unscaled, no foreground mask inside the loop
-        sl = ctx.slide_desc(raster, ih, iw, dataset.params.ph, dataset.params.pw, m=1.0, H2=ih, W2=iw, mask=None)
+        sl = ctx.slide_desc(raster, ih, iw, dataset.params.ph, dataset.params.pw, m=1.0, H2=ih, W2=iw, mask=None, resize=rs)
         r = ctx.run_slide(sl, it.tiles, capi.HEAD_SEG, device_out=True, want_canvas=True)
         classes, pred = ctx.resize_argmax(r["canvas"], H2, W2)
         outputs[key] = {"classes": classes.cpu().numpy(), "pred": pred.cpu().numpy()}
