@@ -204,6 +204,22 @@ __device__ __forceinline__ void ld_global_nc_256(const void* ptr, uint4& lo, uin
                : "l"(ptr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 accumulator columns of this warp's 32 lanes <- 0.  The row kernels hand an accumulator slot back ZEROED, so the MMA
+// that opens the next output row in it can accumulate like every other one (no separate overwriting MMA per row).
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "{\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {z,z,z,z,z,z,z,z,z,z,z,z,z,z,z,z};\n\t}" ::"r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// all accumulator columns [0, cols) <- 0 by the epilogue warps (warps 2 .., groups of 4 covering the 4 lane quarters)
+__device__ __forceinline__ void tmem_zero_all(uint32_t tmem_base, int warp, int n_groups, int cols) {
+  const int grp = (warp - 2) >> 2, per = cols / n_groups;
+  const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  for (int c = grp * per; c < (grp + 1) * per; c += 16) tmem_st16_zero(tb + (uint32_t)c);
+  tmem_st_wait();
+}
 }  // namespace ptx
 
 // SM100 shared-memory matrix descriptor, K-major operand, rows of (BLOCK_K*2) bytes packed densely,

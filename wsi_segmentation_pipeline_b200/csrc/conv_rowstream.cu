@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // every accumulator slot starts (and is handed back by the epilogue) zeroed: see the MMA issuer's interior path
+  if (warp >= 2) {
+    ptx::tmem_zero_all(*tmem_holder, warp, 2, (int)kTmemCols);
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  ptx::tc_fence_after();
 
 
   if (warp == 0) {
@@ -189,11 +196,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
             ptx::umma_bf16(tmem_base + 96, a_row + 1, b_desc0 + (uint64_t)kWShift, id3, 1u);
             ptx::umma_bf16(tmem_base + 144, a_row + 2, b_desc0 + (uint64_t)(2 * kWShift), id3, 1u);
           } else if (t >= 2 && opens && slot_lo <= RS - 3) {
-            // fast path (interior row, the three target slots are contiguous): 3 MMAs of N = 3*BN per slab,
-            // except that the very first one is split so that the newly opened row is overwritten
+            // fast path (interior row, the three target slots are contiguous): 3 MMAs of N = 3*BN per slab.  The slot
+            // of the newly opened row was zeroed by the epilogue when it drained it (or at kernel start), so its first
+            // contribution accumulates like the others — no separate overwriting MMA (every MMA costs a 4 KB A fetch
+            // and a place in the dependent chain whatever its N)
             const uint32_t d_lo = tmem_base + slot_lo * BN;
-            ptx::umma_bf16(d_lo + 2 * BN, a_row, b_desc0 + (uint64_t)(2 * BN), id1, 0u);
-            ptx::umma_bf16(d_lo, a_row, b_desc0, id2, 1u);
+            ptx::umma_bf16(d_lo, a_row, b_desc0, id3, 1u);
             ptx::umma_bf16(d_lo, a_row + 1, b_desc0 + (uint64_t)kWShift, id3, 1u);
             ptx::umma_bf16(d_lo, a_row + 2, b_desc0 + (uint64_t)(2 * kWShift), id3, 1u);
             uint64_t a_sl = a_row, b_sl = b_desc0;
@@ -297,6 +305,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           uint32_t v[16];
           ptx::tmem_ld16(t_row + (uint32_t)c, v);
           ptx::tmem_ld_wait();
+          ptx::tmem_st16_zero(t_row + (uint32_t)c);              // the slot goes back to the MMA issuer zeroed
           float yv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -356,6 +365,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           }
         }
         if (HEAD && valid) reinterpret_cast<float4*>(p.head_out)[pix] = hacc;
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&slot_free[slot]);
       }
@@ -449,6 +459,13 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // every accumulator slot starts (and is handed back by the epilogue) zeroed: see the MMA issuer's interior path
+  if (warp >= 2) {
+    ptx::tmem_zero_all(*tmem_holder, warp, 4, (int)kTmemCols);
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  ptx::tc_fence_after();
 
   if (warp == 0) {
     // ================================ producer ==========================================
@@ -530,10 +547,8 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
             // interior row, contiguous slots: lanes alternate, so consecutive MMAs never share an accumulator
             const uint32_t dA = tmem_base + slot_lo * BN, dB = dA + kLane;
             const uint64_t a_B = a_row + kLaneUnits;
-            ptx::umma_bf16(dA + 2 * BN, a_row, b_desc0 + (uint64_t)(2 * BN), id1, 0u);       // newly opened row: overwrite
-            ptx::umma_bf16(dB + 2 * BN, a_B, b_desc0 + (uint64_t)(2 * BN), id1, 0u);
-            ptx::umma_bf16(dA, a_row, b_desc0, id2, 1u);
-            ptx::umma_bf16(dB, a_B, b_desc0, id2, 1u);
+            ptx::umma_bf16(dA, a_row, b_desc0, id3, 1u);       // the newly opened row's slot is zero (epilogue hands it back zeroed)
+            ptx::umma_bf16(dB, a_B, b_desc0, id3, 1u);
             ptx::umma_bf16(dA, a_row + 1, b_desc0 + (uint64_t)kWShift, id3, 1u);
             ptx::umma_bf16(dB, a_B + 1, b_desc0 + (uint64_t)kWShift, id3, 1u);
             ptx::umma_bf16(dA, a_row + 2, b_desc0 + (uint64_t)(2 * kWShift), id3, 1u);
@@ -626,6 +641,7 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
           uint32_t v[16];
           ptx::tmem_ld16(t_row + (uint32_t)c, v);
           ptx::tmem_ld_wait();
+          ptx::tmem_st16_zero(t_row + (uint32_t)c);              // the slot goes back to the MMA issuer zeroed
           float yv[16];
           if (HEAD) {
             // d5b + final_conv: BN, ReLU and the 16 -> 4 head as packed FMAs; constants are broadcast smem reads.
@@ -693,6 +709,7 @@ __global__ void __launch_bounds__(kStream2Threads, 1) conv_rowstream2_kernel(con
           }
         }
         if (HEAD && valid) reinterpret_cast<float4*>(p.head_out)[pix] = hacc;
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&slot_free[slot]);
       }

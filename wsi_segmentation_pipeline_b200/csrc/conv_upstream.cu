@@ -102,6 +102,13 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_upstream_kernel(const __gr
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // every accumulator slot starts (and is handed back by the epilogue) zeroed: see the MMA issuer's interior path
+  if (warp >= 2) {
+    ptx::tmem_zero_all(*tmem_holder, warp, 4, (int)kTmemCols);
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  ptx::tc_fence_after();
 
   if (warp == 0) {
     // ================================ producer ==========================================
@@ -201,22 +208,16 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_upstream_kernel(const __gr
             const uint32_t slot0 = j0 & RM;
             if (no_mma) {
             } else if (b_lo == 0 && b_hi == 3 && slot0 + 3 <= RM) {
-              // interior step, no ring wrap: per (slab, tap, parity) one MMA of N = 4*BN; the first per parity is
-              // split so that the two newly opened rows are overwritten
+              // interior step, no ring wrap: per (slab, tap, parity) one MMA of N = 4*BN.  The slots of the two newly
+              // opened rows were zeroed by the epilogue when it drained them (or at kernel start): they accumulate like
+              // the other two, no separate overwriting MMAs
               const uint32_t d0 = tmem_base + slot0 * BN;
 #pragma unroll 1
               for (int sl = 0; sl < nslabs_u; ++sl) {
                 const uint64_t a_sl = a_base + (uint64_t)(sl * 2 * kRunUnits);
                 const uint64_t b_sl = bu0 + (uint64_t)(sl * 4 * kBuBlock);
-                if (sl == 0) {
-                  ptx::umma_bf16(d0 + 2 * BN, a_sl - 1, b_sl + (uint64_t)(2 * BN), id2, 0u);                               // p0, tap 0, new rows
-                  ptx::umma_bf16(d0 + kPar + 2 * BN, a_sl, b_sl + (uint64_t)(2 * kBuBlock + 2 * BN), id2, 0u);              // p1, tap 0, new rows
-                  ptx::umma_bf16(d0, a_sl - 1, b_sl, id2, 1u);
-                  ptx::umma_bf16(d0 + kPar, a_sl, b_sl + (uint64_t)(2 * kBuBlock), id2, 1u);
-                } else {
-                  ptx::umma_bf16(d0, a_sl - 1, b_sl, id4, 1u);
-                  ptx::umma_bf16(d0 + kPar, a_sl, b_sl + (uint64_t)(2 * kBuBlock), id4, 1u);
-                }
+                ptx::umma_bf16(d0, a_sl - 1, b_sl, id4, 1u);                                                               // p0, tap 0
+                ptx::umma_bf16(d0 + kPar, a_sl, b_sl + (uint64_t)(2 * kBuBlock), id4, 1u);                                 // p1, tap 0
                 ptx::umma_bf16(d0, a_sl, b_sl + (uint64_t)kBuBlock, id4, 1u);                                              // p0, tap 1
                 ptx::umma_bf16(d0 + kPar, a_sl + 1, b_sl + (uint64_t)(3 * kBuBlock), id4, 1u);                             // p1, tap 1
               }
@@ -324,6 +325,8 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_upstream_kernel(const __gr
             ptx::tmem_ld16(t_row + (uint32_t)c, v0);
             ptx::tmem_ld16(t_row + kPar + (uint32_t)c, v1);
             ptx::tmem_ld_wait();
+            ptx::tmem_st16_zero(t_row + (uint32_t)c);            // the slot goes back to the MMA issuer zeroed
+            ptx::tmem_st16_zero(t_row + kPar + (uint32_t)c);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
               uint32_t w0[4], w1[4];
@@ -345,6 +348,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_upstream_kernel(const __gr
               }
             }
           }
+          ptx::tmem_st_wait();
           ptx::tc_fence_before();
           ptx::mbar_arrive(&slot_free[slot]);
         }

@@ -1646,6 +1646,7 @@ int wsi_debug_stem(wsi_ctx* ctx, const wsi_slide_desc* slide, const int32_t* til
   CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
   validate_slide(slide);
+  WSI_REQUIRE(slide_resize(slide) == 1, WSI_ERR_UNSUPPORTED, "wsi_debug_stem: resize is not applied here");
   const int64_t rows_r = (slide->rows == 0 && slide->row0 == 0) ? slide->ih : slide->rows;
   check_tiles(slide, tiles_xy, n, rows_r);
   ensure_lut(ctx);
