@@ -22,6 +22,7 @@ OBJ = os.path.join(HERE, "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+NVCC_FLAGS += os.environ.get("WSI_EXTRA_NVCC_FLAGS", "").split()          # timing experiments only (e.g. -DWSI_DEBUG_SWITCHES)
 SOURCES = ["engine.cu", "conv_igemm.cu", "conv_rowtile.cu", "conv_rowstream.cu", "conv_upstream.cu", "kernels.cu", "postproc.cu", "tiff_ingest.cu", "planner.cpp"]
 
 
