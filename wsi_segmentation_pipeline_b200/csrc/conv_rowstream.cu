@@ -54,7 +54,7 @@ struct UnitIter {
 };
 
 template <int BN, bool HEAD, int RS>
-__global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const __grid_constant__ StreamParams p) {
+__global__ void __launch_bounds__(kStreamThreads, (BN <= 32) ? 2 : 1) conv_rowstream_kernel(const __grid_constant__ StreamParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int w_bytes = p.nslabs * 3 * 2 * 3 * BN * 16;
@@ -245,19 +245,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
     const int q = warp & 3;
     const int egrp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    constexpr int RB = (BN <= 32) ? BN : 1;
-    float r_scale[RB], r_bias[RB];
-    if (BN <= 32) {
-#pragma unroll
-      for (int j = 0; j < RB; ++j) { r_scale[j] = s_scale[j]; r_bias[j] = s_bias[j]; }
-    }
-    float r_hw[HEAD ? 64 : 1], r_hb[HEAD ? 4 : 1];
-    if (HEAD) {
-#pragma unroll
-      for (int j = 0; j < 64; ++j) r_hw[HEAD ? j : 0] = s_hw[j];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r_hb[HEAD ? j : 0] = s_hb[j];
-    }
+    // folded-BN constants and the fused head are read from the parameter (constant) bank: p.k
     const float lo = p.relu ? 0.f : -INFINITY;
     const bool planar_out = (p.out_layout == LAYOUT_PLANAR);
     const bool planar_res = (p.res_layout == LAYOUT_PLANAR);
@@ -309,9 +297,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
           float yv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float sc = (BN <= 32) ? r_scale[(BN <= 32) ? c + j : 0] : p.k.scale[c + j];
-            const float bi = (BN <= 32) ? r_bias[(BN <= 32) ? c + j : 0] : p.k.bias[c + j];
-            yv[j] = fmaf(__uint_as_float(v[j]), sc, bi);
+            yv[j] = fmaf(__uint_as_float(v[j]), p.k.scale[c + j], p.k.bias[c + j]);
           }
           if (has_res) {
 #pragma unroll
@@ -334,10 +320,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) conv_rowstream_kernel(const
               float s0 = 0.f, s1 = 0.f;      // two independent chains per logit, summed in a fixed order
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                s0 = fmaf(yv[j], r_hw[HEAD ? k * 16 + j : 0], s0);
-                s1 = fmaf(yv[j + 1], r_hw[HEAD ? k * 16 + j + 1 : 0], s1);
+                s0 = fmaf(yv[j], p.k.head[k * 16 + j], s0);
+                s1 = fmaf(yv[j + 1], p.k.head[k * 16 + j + 1], s1);
               }
-              hp[k] = (s0 + s1) + r_hb[HEAD ? k : 0];
+              hp[k] = (s0 + s1) + p.k.head[64 + k];
             }
           }
           if (valid && p.out != nullptr) {
@@ -760,7 +746,14 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   p.nslabs = C / 16;
   p.N = N; p.OH = OH; p.OW = OW; p.Cout = BN;
   // Cout 16 / 32: two 128-column lanes per CTA (conv_rowstream2_kernel)
-  p.lanes = (BN <= 32 && getenv("WSI_STREAM_LANES1") == nullptr) ? 2 : 1;
+  // Cout 16 / 32, when the stage ring fits in half the shared memory (d5b, d4b): the one-lane kernel at TWO CTAs per SM
+  // (256 TMEM columns each) — two independent pipelines per SM overlap one CTA's epilogue with the other's MMAs a little
+  // better than two lanes inside one CTA (same-box A/B: conv stage -0.8 %).  Otherwise two 128-column lanes per CTA
+  // (conv_rowstream2_kernel).
+  const int ring2 = 256 / BN;
+  const int stages2 = std::min(24, (110 * 1024 - (128 + (((C / 16) * 3 * 2 * 3 * BN * 16 + (2 * BN + 68) * 4 + 127) & ~127) + 1024)) / ((C / 16) * kStreamStageBytes));
+  const bool ctas2 = BN <= 32 && stages2 + 2 >= ring2 && stages2 >= 8 && getenv("WSI_STREAM_CTAS1") == nullptr;
+  p.lanes = (BN <= 32 && getenv("WSI_STREAM_LANES1") == nullptr && !ctas2) ? 2 : 1;
   p.tiles_x = (int)ceil_div(OW, 128 * p.lanes);
   const long long total = (long long)N * p.tiles_x * OH;      // (strip, output row) pairs, split evenly over the CTAs
   WSI_REQUIRE(total < (1LL << 31), WSI_ERR_UNSUPPORTED, "row-stream conv: too many rows");
@@ -809,7 +802,7 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   const int w_bytes = p.nslabs * 3 * 2 * 3 * BN * 16;
   const int fixed = 128 + ((w_bytes + (2 * BN + 68) * 4 + 127) & ~127) + 1024;
   const int stage_bytes = (p.lanes == 2) ? p.nslabs * 2 * kRun2Bytes : p.nslabs * kStreamStageBytes;
-  p.stages = std::min(24, (226 * 1024 - fixed) / stage_bytes);
+  p.stages = std::min(24, ((ctas2 ? 110 : 226) * 1024 - fixed) / stage_bytes);
   if (p.lanes == 2) {
     WSI_REQUIRE(p.stages >= 3, WSI_ERR_UNSUPPORTED, "row-stream conv: not enough shared memory");
     p.ring = 256 / BN;
@@ -822,9 +815,10 @@ void RowStreamOp::build(const ConvInputPart& part, const ConvSpec& spec, const f
   // commit -> epilogue drain -> slot_free -> MMA of a later row has more slack to hide in
   p.ring = (BN <= 32 && p.stages >= 18) ? 16 : 8;
   if (const char* e = getenv("WSI_STREAM_RING")) { const int r = atoi(e); if ((r == 8 || r == 16) && r * BN <= 512) p.ring = r; }
+  if (ctas2) p.ring = std::min(p.ring, 256 / BN);                       // two CTAs share the 512 TMEM columns
   WSI_REQUIRE(p.stages + 2 >= p.ring, WSI_ERR_UNSUPPORTED, "row-stream conv: not enough shared memory");   // see the epilogue wait
   smem_ = fixed + p.stages * stage_bytes;
-  grid_ = (int)std::min<long long>(total, num_sms);
+  grid_ = (int)std::min<long long>(total, ctas2 ? 2 * num_sms : num_sms);
   CUDA_CHECK(cudaStreamSynchronize(0));
 }
 
