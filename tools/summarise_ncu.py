@@ -104,7 +104,7 @@ def batch(path, bench_json=None):
         d = json.load(open(bench_json))
         for row in (d.get("roofline", {}).get("kernels") or []):
             live.setdefault(row["kernel"], []).append(row)
-    print(f"# four consecutive batches of 74 tiles of 512^2 (130 launches, steady state) inside: {CMD} --no-library --no-kernel-table ; ncu --metrics ... --clock-control none -s 4000 -c 130")
+    print(f"# four consecutive batches of 444 tiles of 512^2 (130 launches, steady state) inside: {CMD} --no-library --no-kernel-table ; ncu --metrics ... --clock-control none -s 2200 -c 130")
     print("# ncu times are cold-cache and serialised (compare SHARES); live_* columns come from bench.py's traced step (CUDA events, warm)")
     print("kernel,launches,ncu_us_total,share_pct,tensor_pipe_active_pct,dram_bytes_per_launch_MB,dram_throughput_pct,registers,live_ms_sum,live_alg_tflops,live_alg_gbs")
     conv_t = conv_tx = 0.0

@@ -570,12 +570,15 @@ static void check_device_flag(wsi_ctx* c, cudaStream_t s) {
 static int64_t auto_batch(const wsi_ctx* c, int ph, int pw, int64_t T) {
   int64_t b = c->batch_tiles;
   if (b <= 0) {
-    // ~16 Mpx of tile area per batch (64 tiles of 512^2): the deepest layers need >= 2 full waves of
-    // output tiles on 148 SMs (measured: 16 -> 204, 32 -> 228, 64 -> 239, 96 -> 232 slide-Mpx/s)
-    b = std::max<int64_t>(1, (16LL << 20) / ((int64_t)ph * pw));
+    // Three 512^2 tiles' worth of pixels per SM and batch (444 tiles of 512^2 on 148 SMs; one per SM in the fp32-emulated
+    // precision, whose activations are three times as large).  The persistent row kernels cut the batch into one contiguous
+    // range per CTA: whole tiles per CTA mean no split units, and an ODD number of them keeps the CTAs' start addresses from
+    // being large powers of two apart.  Same-box sweep, 20k x 20k slide (tools/gpu_batch_ab.sh, slide-Mpx/s): 74 -> 352,
+    // 148 -> 361, 222 -> 362-367, 296 -> 360, 370 -> 361, 407 -> 360, 444 -> 370.5, 481 -> 361, 518 -> 363, 592 -> 358.
+    const int64_t per_sm_px = (c->precision == WSI_PRECISION_FP32 ? 1LL : 3LL) * 512 * 512;
+    b = std::max<int64_t>(1, per_sm_px * c->num_sms / ((int64_t)ph * pw));
     // ... rounded to a multiple of num_sms / 4: every layer's output-tile count is batch x (H x W / 128) x N tiles
-    // with power-of-two factors, so this makes all of them whole waves over the SMs / SM pairs (74 tiles of 512^2
-    // on 148 SMs: 4.0 waves at 32x32x256 instead of 3.46)
+    // with power-of-two factors, so this makes all of them whole waves over the SMs / SM pairs
     const int64_t q = std::max(1, c->num_sms / 4);
     if (2 * b >= q) b = std::max<int64_t>(1, (b + q / 2) / q) * q;
     b = std::min<int64_t>(b, 1036);
