@@ -1,5 +1,9 @@
 #!/bin/bash
-# A/B/C on ONE box, alternating, with the SM clock sampled during each run (boxes differ in how hard the power cap bites)
+# A/B/C on ONE box, alternating, with the SM clock sampled during each run (boxes differ in how hard the power cap bites).
+# Variants are prebuilt libraries ab/lib<NAME>.so (git-ignored, travel with the gpurun snapshot):
+#   <edit or check out the sources of the variant>; python -m wsi_segmentation_pipeline_b200.build
+#   (WSI_EXTRA_NVCC_FLAGS="-D..." for compile-time switches); cp wsi_segmentation_pipeline_b200/libwsi_b200.so ab/libA.so
+# usage: gpu_ab.sh A B C   — capi loads the library named by WSI_B200_LIB
 mkdir -p gpurun_out
 for round in 1 2; do
 for v in "$@"; do
