@@ -598,8 +598,8 @@ static void validate_slide(const wsi_slide_desc* sl) {
               (long long)sl->row0, (long long)sl->rows);
   WSI_REQUIRE(sl->resize >= 0 && sl->resize <= 16, WSI_ERR_INVALID, "resize %d outside [0, 16]", sl->resize);
   if (sl->resize > 1)
-    WSI_REQUIRE(sl->ph % sl->resize == 0 && sl->pw % sl->resize == 0 && sl->pw * 3 <= 48 * 1024, WSI_ERR_INVALID,
-                "resize %d: the tile %d x %d must be a multiple of it (ph = tile_h * scan_resize, eval_tumorbed.py:39-40) and at most 16384 wide",
+    WSI_REQUIRE(sl->ph % sl->resize == 0 && sl->pw % sl->resize == 0 && sl->pw <= 16000, WSI_ERR_INVALID,   // one window row + weights' tail in 48 KB of shared memory
+                "resize %d: the tile %d x %d must be a multiple of it (ph = tile_h * scan_resize, eval_tumorbed.py:39-40) and at most 16000 wide",
                 sl->resize, sl->ph, sl->pw);
 }
 
