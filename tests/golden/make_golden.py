@@ -12,6 +12,7 @@ Scenarios
   wsis_l2/l1  predict_wsis up to the argmax (scan_level 2: resize is the identity; scan_level 1: cv2.resize 4x down)
   resnet_fwd  resnets_shift.ResNet.forward (multi-patch) on a [2,16,3,64,64] batch
   normalise   standard_augmentor(True) on a PIL tile
+  threshold_floor   preprocessing.threshold_probs with non-zero class_probs (the per-class floor)
   seg_resize2/3, wsis_resize2   predict_tumorbed / predict_wsis with scan_resize = 2 / 3 (PIL resize of the tiles,
               nearest re-interpolation of the logits); non-square tile for scan_resize 3
 """
@@ -166,6 +167,24 @@ def normalise():
     np.savez_compressed(os.path.join(OUT, "normalise.npz"), tile=tile, out=t.numpy())
 
 
+def threshold_floor():
+    """preprocessing.threshold_probs with non-zero args.class_probs (the per-class probability floor, myargs.py:15) on a
+    random float64 canvas — the floor branch the predict_tumorbed goldens (class_probs = 0) never take."""
+    R = H.ref_modules()
+    rng = np.random.default_rng(11)
+    canvas = rng.standard_normal((4, 48, 60)) * 2.5
+    canvas[:, :6] = 0.0                                   # uncovered pixels: softmax 0.25 each, below some floors
+    out = {"canvas": canvas}
+    for i, cp in enumerate([(0.0, 0.3, 0.25, 0.5), (0.3, 0.3, 0.3, 0.3), (0.9, 0.0, 0.0, 0.0)]):
+        R.args.num_classes, R.args.class_probs = 4, list(cp)
+        classes, probs = R.preprocessing.threshold_probs(canvas.copy())
+        out[f"cp{i}"], out[f"classes{i}"], out[f"probs{i}"] = np.array(cp), classes, probs
+    R.args.class_probs = [0.0, 0.0, 0.0, 0.0]
+    out["n"] = np.array(3)
+    np.savez_compressed(os.path.join(OUT, "threshold_floor.npz"), **out)
+    print("threshold_floor: classes hist", [np.bincount(out[f"classes{i}"].ravel(), minlength=4).tolist() for i in range(3)])
+
+
 def resize_only():
     """The scan_resize goldens alone (ph, pw = tile * scan_resize as eval_tumorbed.py:39-40 sets them)."""
     predict("seg_resize2", "unet_seg", 288, 352, 128, 128, 32, 32, "seg", seed=6, scan_resize=2)
@@ -177,6 +196,9 @@ if __name__ == "__main__":
     if "--resize-only" in sys.argv:
         resize_only()
         sys.exit(0)
+    if "--threshold-only" in sys.argv:
+        threshold_floor()
+        sys.exit(0)
     plans()
     normalise()
     resnet_fwd()
@@ -187,3 +209,4 @@ if __name__ == "__main__":
     predict_wsis("wsis_l2", 160, 192, 64, 64, 32, 32, 2, 4)
     predict_wsis("wsis_l1", 256, 320, 64, 64, 32, 32, 1, 5)
     resize_only()
+    threshold_floor()

@@ -73,6 +73,17 @@ def test_predict_tumorbed_matches_reference(golden_dir, name, arch, mode):
         assert (r["heatmap"][unc] == 127 * g["mask"][unc]).all()
 
 
+def test_threshold_probs_floor_matches_reference(golden_dir):
+    """threshold_probs with non-zero class_probs (utils/preprocessing.py:156-172): the reference run on a random float64
+    canvas — classes bit-exact, probabilities to the last ulp of torch's float64 softmax."""
+    g = _load(golden_dir, "threshold_floor")
+    for i in range(int(g["n"])):
+        classes, probs = O.threshold_probs(g["canvas"].copy(), tuple(float(v) for v in g[f"cp{i}"]))
+        np.testing.assert_array_equal(classes, g[f"classes{i}"])
+        np.testing.assert_allclose(probs, g[f"probs{i}"], rtol=0, atol=1e-15)
+        assert classes.dtype == np.uint8 and probs.dtype == np.float64
+
+
 @pytest.mark.parametrize("shape", [(256, 320, 64, 80), (100, 130, 33, 47), (64, 64, 32, 32), (40, 60, 80, 120), (97, 61, 13, 9), (37, 53, 37, 53)])
 def test_cv2_resize_restatement(shape):
     """A9: the oracle restates cv2.resize(INTER_LINEAR, CV_64F) — pinned against cv2 itself (same image on the GPU box)."""
