@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 LIB = "wsi_segmentation_pipeline_b200/libwsi_b200.so"
-KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UBLKCP", "UTCBAR", "SYNCS", "LDG", "STG", "LDS", "STS", "DADD", "DFMA", "F2F", "HMMA"]
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UTCBAR", "SYNCS", "LDG", "STG", "LDS", "STS", "DADD", "DFMA", "F2F", "HMMA"]
 
 
 def main(out):
