@@ -38,6 +38,29 @@ def test_empty_slide_is_dropped_like_the_reference():
     assert len(ds.Dataset_wsi(short, ds.DotDict(ph=8, pw=8, sh=8, sw=8), None, scan_level=2)) == 0   # :123-124
 
 
+def test_scan_resize_argument_checks(golden_dir):
+    """myargs.py:115 scan_resize: the Dataset params carry tile * scan_resize (eval_tumorbed.py:39-40); the mirror checks that
+    before anything reaches the device, and the tile plan for such windows equals the reference's (golden of the unmodified
+    reference run with scan_resize = 2)."""
+    P = ds.DotDict(ph=128, pw=128, sh=32, sw=32)
+    assert ev._scan_resize(ds.DotDict(scan_resize=1), P) == 1 and ev._scan_resize(ds.DotDict(scan_resize=2), P) == 2
+    for bad in (0, -1, 3):                                   # 128 is not a multiple of 3
+        with pytest.raises(ValueError):
+            ev._scan_resize(ds.DotDict(scan_resize=bad), P)
+    g = np.load(os.path.join(golden_dir, "seg_resize2.npz"))
+    ih, iw, ph, pw, sh, sw, lvl = (int(v) for v in g["geom"])
+    data = ds.Dataset_wsis({"s.svs": ds.ArraySlide({2: synth.synth_slide(ih, iw, 1234)})}, {"ph": ph, "pw": pw, "sh": sh, "sw": sw},
+                           masks={"s.svs": g["mask"]})
+    np.testing.assert_array_equal(data.wsis["s.svs"]["iterator"].tiles, g["tiles"])
+    # the host tables of the device resize equal the oracle's restatement of Pillow's (also for an upscale and odd sizes)
+    for n_in, n_out in ((128, 64), (96, 32), (1024, 512), (50, 17), (33, 66)):
+        b, k = capi.resample_coeffs(n_in, n_out)
+        b0, k0 = O.pil_resample_coeffs(n_in, n_out)
+        np.testing.assert_array_equal(b, b0)
+        np.testing.assert_array_equal(k, k0)
+        assert (k.sum(axis=1) - (1 << 22)).__abs__().max() <= k.shape[1]      # weights sum to 1 in 22-bit fixed point (rounding)
+
+
 def test_no_cpu_find_nuclei_in_the_product_package():
     """find_nuclei runs on the GPU only: without an engine and without a cached mask the dataset refuses (no CPU fallback)."""
     assert not hasattr(ds, "find_nuclei_hsv")
